@@ -1,0 +1,199 @@
+/*
+ * turtle_b200.h -- C ABI of libturtle_b200.so: the sm_100a kernels behind Turtle's inference
+ * hot path (truncated Causal History Model + per-frame U-Net blocks).
+ *
+ * The reference (sflindrs/TurtleVSR) is pure PyTorch: every op below replaces a group of ATen
+ * calls issued from basicsr/models/archs/turtle_t1_arch.py ("T1"), turtle_arch.py ("T0") or
+ * turtlesuper_t1_arch.py ("TS").  The citation on each entry point is the reference code it
+ * replaces.  A maintainer binds these with ctypes; nothing here takes or
+ * returns a torch type.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 unless stated; activations are channels-last
+ *     ("NHWC"): element (b,y,x,c) of a [B,H,W,C] map lives at ((b*H+y)*W+x)*ld + c, where the
+ *     row pitch ld (in floats) lets a call address a channel slice of a wider tensor;
+ *   - every function enqueues work on `stream` (a cudaStream_t passed as void*) and returns
+ *     immediately: 0 on success, a negative TURTLE_E* code on bad arguments or launch failure.
+ *     Nothing allocates, synchronises or throws; the caller owns all buffers;
+ *   - `mode`: TURTLE_FP32 = CUDA-core fp32 FMA (exact mode: bit-exact top-k contract),
+ *             TURTLE_TF32 = tcgen05 tensor cores, TF32 operands, fp32 accumulate in TMEM.
+ */
+#ifndef TURTLE_B200_H
+#define TURTLE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TURTLE_OK 0
+#define TURTLE_EINVAL (-1)   /* bad shape / alignment / unsupported combination */
+#define TURTLE_ELAUNCH (-2)  /* cudaGetLastError() != cudaSuccess after the launch */
+#define TURTLE_ENOTSUP (-3)  /* shape not supported by the requested mode (caller picks TURTLE_FP32) */
+
+#define TURTLE_FP32 0
+#define TURTLE_TF32 1
+
+#define TURTLE_ACT_NONE 0
+#define TURTLE_ACT_GELU 1    /* exact erf GELU (F.gelu default) */
+
+#define TURTLE_STORE_PLAIN 0
+#define TURTLE_STORE_UNSHUFFLE2 1  /* nn.PixelUnshuffle(2) folded into the store (T1:140-141) */
+#define TURTLE_STORE_SHUFFLE2 2    /* nn.PixelShuffle(2) folded into the store   (T1:150-151) */
+
+#define TURTLE_MAX_SEG 48
+#define TURTLE_SAB_SLOTS 48  /* 5 top-k + 41 local-window entries, padded to 48 */
+
+int turtle_abi_version(void);          /* bumps when a signature changes */
+const char *turtle_build_info(void);   /* "sm_100a nvcc <ver> ..." */
+
+/* ---------------------------------------------------------------------------------------
+ * Frame entry / exit
+ * ------------------------------------------------------------------------------------- */
+
+/* check_image_size zero pad (T1:1134-1140) + NCHW->NHWC of the selected frame inp[:,1]
+ * (T1:1059-1061); with upscale==4 also nn.Upsample(x4, bilinear, align_corners=False)
+ * (TS:975-978, 1063-1070).  src: [B,C,Hs,Ws] with batch stride src_bstride (floats);
+ * dst: [B,Hp,Wp,C] dense, Hp>=Hs*upscale, Wp>=Ws*upscale, zero outside. */
+int turtle_pack_frame(const float *src, int64_t src_bstride, float *dst, int B, int C, int Hs, int Ws,
+                      int Hp, int Wp, int upscale, void *stream);
+
+/* input_projection: 3x3 conv, tiny Cin (3 or 6), zero pad 1 (T1:975-978, 1063).
+ * x [B,H,W,Cin] dense; w [Cout,Cin,3,3] (reference layout); bias nullable; y [B,H,W,Cout]. */
+int turtle_conv3x3_first(const float *x, const float *w, const float *bias, float *y, int B, int H, int W,
+                         int Cin, int Cout, void *stream);
+
+/* ending: 3x3 conv Cin->Cout(<=4) + bias + residual `current` + crop, written NCHW (T1:1128-1132).
+ * x [B,H,W,Cin]; w [Cout,Cin,3,3]; cur [B,H,W,cur_ld] (first Cout channels used);
+ * out [B,Cout,Hc,Wc] dense NCHW with Hc<=H, Wc<=W. */
+int turtle_conv3x3_last(const float *x, const float *w, const float *bias, const float *cur, int cur_ld,
+                        int cur_coff, float *out, int B, int H, int W, int Cin, int Cout, int Hc, int Wc,
+                        void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Per-pixel channel LayerNorm (WithBias_LayerNorm / BiasFree_LayerNorm, T1:67-112)
+ *   y[p,:] = (x[p,:]-mu)/sqrt(var_biased+1e-5)*w + b      (b==NULL: BiasFree, no mean subtraction
+ *   in the numerator, exactly as T1:79-81)
+ * ------------------------------------------------------------------------------------- */
+int turtle_layernorm(const float *x, int ldx, const float *w, const float *b, float *y, int ldy, int64_t P,
+                     int C, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Contractions over channels: 1x1 convs, the skip-cat + reduce_chan, the folded
+ * channel-attention apply, and (im2col==1) the dense 3x3 convs of Down/Upsample.
+ *
+ *   acc[p,o] = sum_k A(p,k) * W[o,k]                        k in [0, nseg*segw)
+ *   v        = acc + bias[o];  v = act(v);  v *= scale[o];  v += res[p*ldres+o]
+ *   out      = store(v)
+ *
+ * A(p,k): im2col==0 -> segment s=k/segw: A[s][p*lda[s] + k%segw]   (K-concatenated sources:
+ *                      torch.cat([up, enc],1) T1:1098; history rows T1:272-273)
+ *         im2col==1 -> one segment, k=(tap*Cin+c), zero-padded 3x3 neighbourhood of pixel p in
+ *                      an [B,H,W,Cin] map (T1:140,150); W is [Cout, 9*Cin] tap-major.
+ * Replaces: nn.Conv2d 1x1 everywhere (T1:166,171,188,193,236,238,298,301,305,307,310,623,674,
+ * 676,708,724,1008,1015,1023), the bias/GELU/beta/gamma/residual elementwise ops around them
+ * (T1:176,206,210,739,742,808-810) and attn@v + project_out (T1:697-701, 280-284).
+ * ------------------------------------------------------------------------------------- */
+typedef struct TurtleGemmArgs {
+    int32_t mode;        /* TURTLE_FP32 | TURTLE_TF32 */
+    int32_t im2col;      /* 0 | 1 */
+    int64_t P;           /* rows (pixels, batch folded in) */
+    int32_t B, H, W;     /* geometry, used by im2col and by the (un)shuffle stores */
+    int32_t Cout;
+    int32_t nseg, segw;  /* K = nseg*segw (im2col: nseg=1, segw=Cin, K=9*Cin) */
+    const float *A[TURTLE_MAX_SEG];
+    int32_t lda[TURTLE_MAX_SEG];
+    const float *Wt;     /* [Cout, K] row-major */
+    const float *bias;   /* [Cout] or NULL */
+    const float *scale;  /* [Cout] or NULL */
+    int32_t act;         /* TURTLE_ACT_* */
+    const float *res;    /* or NULL */
+    int32_t ldres;
+    float *out;
+    int32_t ldo;
+    int32_t store;       /* TURTLE_STORE_* */
+} TurtleGemmArgs;
+
+int turtle_gemm(const TurtleGemmArgs *args, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Depthwise 3x3, stride 1, zero pad 1 (T1:168-170, 237, 299, 302, 624, 675, 716-722)
+ *   fuse: 0 plain(+bias) | 1 GELU(dw+bias)  (ReducedAttn T1:738-739)
+ *         2 gate: y[:,j] = GELU(dw[:,j]) * dw[:,j+C/2], y has C/2 channels (GFFW T1:175-176)
+ *   layout: 0 NHWC | 1 SAB "dilated patch" rows 'b d (p1 h)(p2 w) -> b (h w) (p1 p2 d)' (T1:573),
+ *           y is then [NB, (H/ws)*(W/ws), ws*ws*C] dense.
+ * x [NB,H,W,C] pitch ldx; w tap-major [9,C] (= weight.view(C,9).t(), packed once by the host);
+ * bias nullable.
+ * ------------------------------------------------------------------------------------- */
+int turtle_dwconv3x3(const float *x, int ldx, const float *w, const float *bias, float *y, int ldy, int NB,
+                     int H, int W, int C, int fuse, int layout, int ws, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Transposed (channel) attention: ChannelAttention T1:680-702, FrameHistoryRouter T1:243-286,
+ * and the router inside CausalHistoryModel T1:649-660.
+ *
+ * Step 1 (per key segment): per-head Gram over pixels plus squared column norms
+ *     G[h,i,j] = sum_p q[p, h*q_hs+i] * k[p, h*k_hs+j]     i,j in [0,ch)
+ *   written as `nsplit` partial sums (deterministic two-stage reduction):
+ *     gpart [nsplit, heads, ch, ch], sqq [nsplit, heads*ch], sqk [nsplit, heads*ch]
+ * Step 2: P = softmax_j over all segments( G / (max(|q_i|,1e-12) * max(|k_j|,1e-12)) * temp[h] )
+ *   (F.normalize folded in as diagonal scaling; seg_prenorm[s]!=0 means the key rows of segment s
+ *   were cached already normalised, T1:272 -> divisor 1).
+ * Step 3: M[o, s*C + h*ch + j] = sum_i Wo[o, h*ch+i] * P[h,i,s*ch+j]   (project_out folded in)
+ *   so that out = res + M @ [v_seg0; v_seg1; ...] is one turtle_gemm.
+ * ------------------------------------------------------------------------------------- */
+int turtle_chan_gram(const float *q, int ldq, int q_hs, const float *k, int ldk, int k_hs, int64_t P, int heads,
+                     int ch, int nsplit, float *gpart, float *sqq, float *sqk, int mode, void *stream);
+
+int turtle_chan_softmax(const float *gpart, const float *sqq, const float *sqk, const int32_t *seg_prenorm,
+                        const float *temperature, int nseg, int nsplit, int heads, int ch, float *Pout,
+                        float *inv_knorm /* [nseg, heads*ch], 1/max(|k|,1e-12) (1 for prenormalised) */,
+                        void *stream);
+
+int turtle_chan_fold(const float *Pm, const float *Wo, int nseg, int heads, int ch, float *M, void *stream);
+
+/* y[p, h*y_hs + j] = x[p, h*x_hs + j] * s[h*ch + j]  (s==NULL: copy).  Used to push the normalised
+ * key rows / raw value rows of a frame into the history ring (T1:272-273, 286). */
+int turtle_scale_cols(const float *x, int ldx, int x_hs, const float *s, float *y, int ldy, int y_hs, int64_t P,
+                      int heads, int ch, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * StateAlignBlock (T1:548-610; T0:459-533 with halve=1)
+ * ------------------------------------------------------------------------------------- */
+
+/* k2_dwconv / q2_dwconv: depthwise ws x ws, stride ws, pad 1, then 'b d h w -> b (h w) d' and
+ * F.normalize over d (T1:306-308, 559-560, 569-572, 577-578).
+ * t [B,H,W,D] pitch ldt (the 1x1 k2/q2 output); w tap-major [ws*ws,D] (= weight.view(D,-1).t());
+ * out [B, N=(H/ws)*(W/ws), D] dense,
+ * batch stride out_bstride floats. */
+int turtle_sab_window_reduce(const float *t, int ldt, const float *w, float *out, int64_t out_bstride, int B,
+                             int H, int W, int D, int ws, void *stream);
+
+/* 'b d (p1 h)(p2 w) -> b (h w) (p1 p2 d)' + F.normalize, for the T0 q/k path (T0:487-498). */
+int turtle_sab_patch_normalize(float *rows, int64_t n_rows, int D, void *stream);
+
+/* Correlation + top-5 + local L1 window + clipped softmax, never materialising [F,N,N]
+ * (T1:585-596, 394-416, 448-464, 115-132).
+ *   qn [N,D] normalised queries; kn: F key frames, frame f at kn + f*k_fstride, each [N,D];
+ *   S[f,i,j] = temp * <qn_i, kn_fj>.
+ * Outputs, per (f,i): idx[f,i,0:5] = top-5 keys in descending score order, idx[f,i,5:46] = the
+ * local-window keys (|dy|+|dx|<=4) not already in the top-5, -1 = empty; wgt = clipped-softmax
+ * weight of each slot (entries in both sets carry the doubled logit, T1:595). */
+int turtle_sab_select(const float *qn, const float *kn, int64_t k_fstride, int F, int Hg, int Wg, int D,
+                      const float *temperature, int halve, int32_t *idx, float *wgt, int mode, void *stream);
+
+/* attn @ v with the sparse weights, un-patched straight to NHWC (T1:599-604):
+ *   y[f, p1*Hg+iy, p2*Wg+ix, d] = sum_t wgt[f,i,t] * V[f][idx[f,i,t]][(p1*ws+p2)*c + d]
+ * v: frame f at v + f*v_fstride, [N, ws*ws*c];  y [F,H,W,c] dense.
+ * passthrough!=0 reproduces T0:523 (`out = v`): y is the un-patched V itself. */
+int turtle_sab_aggregate(const int32_t *idx, const float *wgt, const float *v, int64_t v_fstride, float *y, int F,
+                         int Hg, int Wg, int ws, int c, int passthrough, void *stream);
+
+/* T0 only: x + positionalencoding2d(c,h,w) (T0:412-439, 475-476), evaluated analytically. */
+int turtle_add_posenc(const float *x, float *y, int B, int H, int W, int C, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TURTLE_B200_H */

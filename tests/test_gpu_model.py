@@ -1,0 +1,121 @@
+"""GPU parity of the whole drop-in model against the fixtures the reference produced, and against
+the oracle on fresh seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from helpers import load_case  # noqa: E402
+from oracle.turtle_oracle import ArchSpec, Oracle, psnr  # noqa: E402
+from turtlevsr_b200.archs import create_video_model  # noqa: E402
+from turtlevsr_b200.clip import run_clip  # noqa: E402
+
+
+def build(opt, sd, precision="fp32"):
+    net = create_video_model(opt)
+    net.load_state_dict(sd, strict=True)
+    return net.cuda().eval().set_precision(precision)
+
+
+def topk_report(z, trace, tag):
+    """Compare top-5 index sets with the reference's torch.topk; returns (#rows, #mismatching rows)."""
+    rows = bad = 0
+    mods = [k for k in trace if k.endswith("spatial_aligner.")]
+    for lvl, key in enumerate(mods):
+        for fr, rec in enumerate(trace[key]):
+            name = f"topk_f{fr}_l{lvl}"
+            if name not in z.files:
+                continue
+            want = np.sort(z[name], -1)
+            got = np.sort(rec["idx"][0, :, :, :5].cpu().numpy(), -1)
+            rows += want.shape[0] * want.shape[1]
+            bad += int((want != got).any(-1).sum())
+    return rows, bad
+
+
+@pytest.mark.parametrize("name", ["tiny_t1_live.npz", "tiny_super_live.npz", "tiny_t0_live.npz", "full_t1_init.npz",
+                                  "full_t1_live.npz"])
+def test_fp32_mode_matches_reference_fixture(name):
+    opt, sd, clip, ref_out, z = load_case(name)
+    net = build(opt, sd)
+    net.record_trace = True
+    outs, k, v = [], None, None
+    trace_all = {}
+    for j in range(clip.shape[1]):
+        x = torch.stack([clip[:, max(j - 1, 0)], clip[:, j]], 1).cuda()
+        o, k, v = net(x, k, v)
+        outs.append(o.cpu())
+        for key, recs in net._engine.last_trace.items():
+            trace_all.setdefault(key, []).extend(recs)
+    out = torch.stack(outs, 1)
+    err = (out - ref_out).abs().amax(dim=(0, 2, 3, 4))
+    print(name, "per-frame max|d|", err.tolist())
+    assert err.max() < 1e-4, f"fp32 mode must be within 1e-4 of the reference (got {err.max():.3e})"
+    if name.startswith(("tiny_t1", "full_t1", "tiny_super")):
+        rows, bad = topk_report(z, trace_all, name)
+        print(name, f"top-5 rows {rows}, mismatching {bad}")
+        assert rows > 0 and bad <= max(1, rows // 2000)
+    # caches: same protocol as the reference (None for encoder slots, shapes, values via digest)
+    dig = z["cache_digest"].reshape(clip.shape[1], 16, 2)[-1]
+    for i, t in enumerate(list(k) + list(v)):
+        if t is None:
+            assert dig[i, 1] == 0
+        else:
+            s, a = float(t.double().sum()), float(t.double().abs().sum())
+            assert abs(a - dig[i, 1]) <= 1e-4 * max(1.0, dig[i, 1]), (i, a, dig[i, 1])
+
+
+def test_tf32_mode_within_fast_tolerance():
+    opt, sd, clip, ref_out, z = load_case("full_t1_live.npz")
+    net = build(opt, sd, "tf32")
+    out, _, _ = run_clip(net, clip.cuda())
+    out = out.cpu()
+    err = (out - ref_out).abs().max().item()
+    gt = clip   # synthetic "clean" clip
+    dpsnr = abs(psnr(out, gt) - psnr(ref_out, gt))
+    print(f"tf32 mode: max|d|={err:.3e}  dPSNR={dpsnr:.4f} dB")
+    assert err < 2e-3 and dpsnr < 0.02
+
+
+def test_foreign_caches_roundtrip_like_tiled_inference():
+    """INF:227-237 moves caches .cpu() and back every frame: results must not change."""
+    opt, sd, clip, ref_out, _ = load_case("tiny_t1_live.npz")
+    net = build(opt, sd)
+    k = v = None
+    for j in range(clip.shape[1]):
+        x = torch.stack([clip[:, max(j - 1, 0)], clip[:, j]], 1).cuda()
+        o, k, v = net(x, k, v)
+        k = [None if t is None else t.detach().cpu().to("cuda") for t in k]
+        v = [None if t is None else t.detach().cpu().to("cuda") for t in v]
+        assert (o.cpu() - ref_out[:, j]).abs().max() < 1e-4
+
+
+def test_long_clip_ring_wraparound_matches_oracle():
+    """More frames than ring slots: compaction must be invisible (config-4 style history stress)."""
+    opt, sd, clip, _, _ = load_case("tiny_t1_live.npz")
+    g = torch.Generator().manual_seed(5)
+    clip = torch.rand(1, 14, 3, 32, 64, generator=g)
+    want, _, _ = Oracle(ArchSpec.from_opt(opt), sd).run_clip(clip)
+    net = build(opt, sd)
+    got, _, _ = run_clip(net, clip.cuda())
+    err = (got.cpu() - want).abs().amax(dim=(0, 2, 3, 4))
+    print("wraparound per-frame err", err.tolist())
+    assert err.max() < 1e-4
+
+
+def test_batch_two_and_odd_size():
+    opt, sd, _, _, _ = load_case("tiny_t1_live.npz")
+    g = torch.Generator().manual_seed(6)
+    clip = torch.rand(2, 3, 3, 40, 70, generator=g)      # padded to 64x96 internally
+    want, _, _ = Oracle(ArchSpec.from_opt(opt), sd).run_clip(clip)
+    got, _, _ = run_clip(build(opt, sd), clip.cuda())
+    assert got.shape == want.shape
+    assert (got.cpu() - want).abs().max() < 1e-4
+
+
+def test_cpu_input_raises():
+    opt, sd, clip, _, _ = load_case("tiny_t1_live.npz")
+    net = build(opt, sd)
+    with pytest.raises(RuntimeError):
+        net(torch.stack([clip[:, 0], clip[:, 0]], 1))

@@ -196,6 +196,7 @@ class LatentCacheBlock(nn.Module):               # T1:867-917
         super().__init__()
         self.num_blocks = num_blocks
         self.dim, self.num_heads, self.num_frames_tocache = dim, num_heads, num_frames_tocache
+        self.Scale_patchsize = 1
         if num_blocks < 2:
             print("LatentCacheBlock should have more than 2 layers")
             raise SystemExit()

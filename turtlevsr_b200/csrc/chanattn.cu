@@ -1,0 +1,250 @@
+// Transposed (channel) attention, three steps (see include/turtle_b200.h):
+//   gram    : per-head q^T k over pixels + squared column norms, split over pixels (deterministic partials)
+//   softmax : reduce partials, fold the L2 normalisation in as diagonal scaling, temperature, softmax
+//   fold    : M = W_out . blockdiag(P)  so that the apply step is one GEMM over the value rows
+#include "common.cuh"
+
+namespace {
+
+constexpr int GT = 32;   // pixels per smem tile
+
+template <int CH>
+__global__ void __launch_bounds__(256) gram64_kernel(const float *__restrict__ q, int ldq, int q_hs,
+                                                     const float *__restrict__ k, int ldk, int k_hs, int64_t P,
+                                                     int heads, int64_t chunk, float *__restrict__ gpart,
+                                                     float *__restrict__ sqq, float *__restrict__ sqk) {
+    static_assert(CH == 64, "fast path is for 64-channel heads");
+    __shared__ __align__(16) float qs[GT][CH];
+    __shared__ __align__(16) float ks[GT][CH];
+    const int tid = threadIdx.x, h = blockIdx.y, s = blockIdx.x;
+    const int ti = tid >> 4, tj = tid & 15;
+    const int64_t p0 = (int64_t)s * chunk, p1 = min(P, p0 + chunk);
+    const float *qb = q + (int64_t)h * q_hs, *kb = k + (int64_t)h * k_hs;
+    float acc[4][4] = {};
+    float nq[4] = {}, nk[4] = {};
+    const int lr = tid >> 4, lc = (tid & 15) * 4;   // loader: rows lr and lr+16, float4 column lc
+    float4 rq[2], rk[2];
+    auto gload = [&](int64_t base) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            int64_t p = base + lr + 16 * i;
+            if (p < p1) {
+                rq[i] = ldg_stream(qb + p * ldq + lc);
+                rk[i] = ldg_stream(kb + p * ldk + lc);
+            } else {
+                rq[i] = make_float4(0, 0, 0, 0);
+                rk[i] = make_float4(0, 0, 0, 0);
+            }
+        }
+    };
+    if (p0 < p1) gload(p0);
+    for (int64_t base = p0; base < p1; base += GT) {
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            *reinterpret_cast<float4 *>(&qs[lr + 16 * i][lc]) = rq[i];
+            *reinterpret_cast<float4 *>(&ks[lr + 16 * i][lc]) = rk[i];
+        }
+        __syncthreads();
+        if (base + GT < p1) gload(base + GT);
+#pragma unroll 8
+        for (int p = 0; p < GT; ++p) {
+            float4 a = *reinterpret_cast<const float4 *>(&qs[p][ti * 4]);
+            float4 b = *reinterpret_cast<const float4 *>(&ks[p][tj * 4]);
+            float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+            if (tj == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) nq[i] = fmaf(av[i], av[i], nq[i]);
+            }
+            if (ti == 0) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) nk[j] = fmaf(bv[j], bv[j], nk[j]);
+            }
+        }
+    }
+    float *gp = gpart + (((int64_t)s * heads + h) * CH) * CH;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4 *>(gp + (ti * 4 + i) * CH + tj * 4) =
+            make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    int C = heads * CH;
+    if (tj == 0)
+        *reinterpret_cast<float4 *>(sqq + (int64_t)s * C + h * CH + ti * 4) = make_float4(nq[0], nq[1], nq[2], nq[3]);
+    if (ti == 0)
+        *reinterpret_cast<float4 *>(sqk + (int64_t)s * C + h * CH + tj * 4) = make_float4(nk[0], nk[1], nk[2], nk[3]);
+}
+
+// any ch <= 64 (multiple of 4): used by reduced-size test configs
+__global__ void __launch_bounds__(256) gram_generic_kernel(const float *__restrict__ q, int ldq, int q_hs,
+                                                           const float *__restrict__ k, int ldk, int k_hs, int64_t P,
+                                                           int heads, int ch, int64_t chunk, float *__restrict__ gpart,
+                                                           float *__restrict__ sqq, float *__restrict__ sqk) {
+    __shared__ float qs[GT][64];
+    __shared__ float ks[GT][64];
+    const int tid = threadIdx.x, h = blockIdx.y, s = blockIdx.x;
+    const int64_t p0 = (int64_t)s * chunk, p1 = min(P, p0 + chunk);
+    const float *qb = q + (int64_t)h * q_hs, *kb = k + (int64_t)h * k_hs;
+    float acc[16] = {};
+    float nq = 0.f, nk = 0.f;
+    const int nout = ch * ch;
+    for (int64_t base = p0; base < p1; base += GT) {
+        __syncthreads();
+        for (int e = tid; e < GT * ch; e += 256) {
+            int r = e / ch, c = e - r * ch;
+            int64_t p = base + r;
+            qs[r][c] = p < p1 ? __ldg(qb + p * ldq + c) : 0.f;
+            ks[r][c] = p < p1 ? __ldg(kb + p * ldk + c) : 0.f;
+        }
+        __syncthreads();
+        for (int p = 0; p < GT; ++p) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                int o = tid + 256 * r;
+                if (o < nout) acc[r] = fmaf(qs[p][o / ch], ks[p][o % ch], acc[r]);
+            }
+            if (tid < ch) {
+                nq = fmaf(qs[p][tid], qs[p][tid], nq);
+                nk = fmaf(ks[p][tid], ks[p][tid], nk);
+            }
+        }
+    }
+    float *gp = gpart + ((int64_t)s * heads + h) * nout;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        int o = tid + 256 * r;
+        if (o < nout) gp[o] = acc[r];
+    }
+    if (tid < ch) {
+        int C = heads * ch;
+        sqq[(int64_t)s * C + h * ch + tid] = nq;
+        sqk[(int64_t)s * C + h * ch + tid] = nk;
+    }
+}
+
+__global__ void __launch_bounds__(128) chan_softmax_kernel(const float *__restrict__ gpart,
+                                                           const float *__restrict__ sqq,
+                                                           const float *__restrict__ sqk,
+                                                           const int32_t *__restrict__ prenorm,
+                                                           const float *__restrict__ temperature, int nseg,
+                                                           int nsplit, int heads, int ch, float *__restrict__ Pout,
+                                                           float *__restrict__ inv_knorm) {
+    __shared__ float red[4];
+    __shared__ float bc;
+    const int i = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+    const int C = heads * ch, ncol = nseg * ch;
+    const int64_t seg_stride = (int64_t)nsplit * heads * ch * ch;
+    float nq = 0.f;
+    for (int s = 0; s < nsplit; ++s) nq += sqq[(int64_t)s * C + h * ch + i];
+    const float inv_q = 1.0f / fmaxf(sqrtf(nq), 1e-12f);
+    const float tau = temperature[h];
+    float logit[4];   // ncol <= 512 -> up to 4 columns per thread
+    float mx = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        int c = tid + 128 * r;
+        logit[r] = -INFINITY;
+        if (c < ncol) {
+            int seg = c / ch, j = c - seg * ch;
+            float g = 0.f;
+            const float *gp = gpart + seg * seg_stride + ((int64_t)h * ch + i) * ch + j;
+            for (int s = 0; s < nsplit; ++s) g += gp[(int64_t)s * heads * ch * ch];
+            float inv_k = 1.0f;
+            if (!prenorm[seg]) {
+                float nk = 0.f;
+                const float *kp = sqk + (int64_t)seg * nsplit * C + h * ch + j;
+                for (int s = 0; s < nsplit; ++s) nk += kp[(int64_t)s * C];
+                inv_k = 1.0f / fmaxf(sqrtf(nk), 1e-12f);
+            }
+            if (i == 0 && inv_knorm) inv_knorm[(int64_t)seg * C + h * ch + j] = inv_k;
+            logit[r] = g * inv_q * inv_k * tau;
+            mx = fmaxf(mx, logit[r]);
+        }
+    }
+    mx = warp_max(mx);
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    if (tid == 0) bc = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    __syncthreads();
+    mx = bc;
+    float e[4], sum = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        int c = tid + 128 * r;
+        e[r] = c < ncol ? expf(logit[r] - mx) : 0.f;
+        sum += e[r];
+    }
+    sum = warp_sum(sum);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = sum;
+    __syncthreads();
+    if (tid == 0) bc = (red[0] + red[1]) + (red[2] + red[3]);
+    __syncthreads();
+    sum = bc;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        int c = tid + 128 * r;
+        if (c < ncol) Pout[((int64_t)h * ch + i) * ncol + c] = e[r] / sum;
+    }
+}
+
+__global__ void chan_fold_kernel(const float *__restrict__ Pm, const float *__restrict__ Wo, int nseg, int heads,
+                                 int ch, float *__restrict__ M) {
+    const int C = heads * ch, ncolP = nseg * ch, K = nseg * C;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)C * K) return;
+    int col = (int)(idx % K), o = (int)(idx / K);
+    int seg = col / C, r = col - seg * C, h = r / ch, j = r - h * ch;
+    const float *wp = Wo + (int64_t)o * C + h * ch;
+    const float *pp = Pm + ((int64_t)h * ch) * ncolP + seg * ch + j;
+    float acc = 0.f;
+    for (int i = 0; i < ch; ++i) acc = fmaf(__ldg(wp + i), __ldg(pp + (int64_t)i * ncolP), acc);
+    M[idx] = acc;
+}
+
+}  // namespace
+
+int turtle_chan_gram_tc(const float *q, int ldq, int q_hs, const float *k, int ldk, int k_hs, int64_t P, int heads,
+                        int ch, int nsplit, float *gpart, float *sqq, float *sqk, void *stream);
+
+extern "C" int turtle_chan_gram(const float *q, int ldq, int q_hs, const float *k, int ldk, int k_hs, int64_t P,
+                                int heads, int ch, int nsplit, float *gpart, float *sqq, float *sqk, int mode,
+                                void *stream) {
+    if (!q || !k || !gpart || !sqq || !sqk || heads < 1 || ch < 4 || ch > 64 || (ch & 3) || nsplit < 1 || P < 1)
+        return TURTLE_EINVAL;
+    int64_t chunk = cdiv64(cdiv64(P, nsplit), GT) * GT;
+    dim3 grid(nsplit, heads);
+    (void)mode;
+    if (ch == 64 && !(ldq & 3) && !(ldk & 3) && !(q_hs & 3) && !(k_hs & 3) &&
+        !(((uintptr_t)q | (uintptr_t)k) & 15))
+        gram64_kernel<64><<<grid, 256, 0, as_stream(stream)>>>(q, ldq, q_hs, k, ldk, k_hs, P, heads, chunk, gpart, sqq,
+                                                              sqk);
+    else
+        gram_generic_kernel<<<grid, 256, 0, as_stream(stream)>>>(q, ldq, q_hs, k, ldk, k_hs, P, heads, ch, chunk, gpart,
+                                                                sqq, sqk);
+    TURTLE_CHECK_LAUNCH();
+    return TURTLE_OK;
+}
+
+extern "C" int turtle_chan_softmax(const float *gpart, const float *sqq, const float *sqk, const int32_t *seg_prenorm,
+                                   const float *temperature, int nseg, int nsplit, int heads, int ch, float *Pout,
+                                   float *inv_knorm, void *stream) {
+    if (!gpart || !sqq || !sqk || !seg_prenorm || !temperature || !Pout || nseg < 1 || nseg * ch > 512)
+        return TURTLE_EINVAL;
+    dim3 grid(ch, heads);
+    chan_softmax_kernel<<<grid, 128, 0, as_stream(stream)>>>(gpart, sqq, sqk, seg_prenorm, temperature, nseg, nsplit,
+                                                            heads, ch, Pout, inv_knorm);
+    TURTLE_CHECK_LAUNCH();
+    return TURTLE_OK;
+}
+
+extern "C" int turtle_chan_fold(const float *Pm, const float *Wo, int nseg, int heads, int ch, float *M, void *stream) {
+    if (!Pm || !Wo || !M) return TURTLE_EINVAL;
+    int64_t total = (int64_t)heads * ch * nseg * heads * ch;
+    chan_fold_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, as_stream(stream)>>>(Pm, Wo, nseg, heads, ch, M);
+    TURTLE_CHECK_LAUNCH();
+    return TURTLE_OK;
+}

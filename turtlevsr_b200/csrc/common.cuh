@@ -1,0 +1,44 @@
+// Shared device/host helpers for libturtle_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/turtle_b200.h"
+
+#define TURTLE_CHECK_LAUNCH()                                   \
+    do {                                                        \
+        cudaError_t e__ = cudaGetLastError();                   \
+        if (e__ != cudaSuccess) return TURTLE_ELAUNCH;          \
+    } while (0)
+
+static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float gelu_erf(float x) {
+    // F.gelu default: 0.5*x*(1+erf(x/sqrt(2)))
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// streaming 128-bit global accesses (read-once / write-once data should not pollute L1)
+__device__ __forceinline__ float4 ldg_stream(const float *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream(float *p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}

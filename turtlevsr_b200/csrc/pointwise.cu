@@ -1,0 +1,400 @@
+// Memory-bound per-pixel kernels: frame pack, first/last 3x3 conv, channel LayerNorm,
+// depthwise 3x3 (+GELU / gate / SAB patch layout), column scaling, T0 position code.
+// All activations fp32 channels-last.  See include/turtle_b200.h for the contracts.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// pack_frame
+// ------------------------------------------------------------------------------------------
+__global__ void pack_frame_kernel(const float *__restrict__ src, int64_t bstride, float *__restrict__ dst, int B,
+                                  int C, int Hs, int Ws, int Hp, int Wp, int up) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = (int64_t)B * Hp * Wp;
+    if (idx >= total) return;
+    int x = (int)(idx % Wp);
+    int y = (int)((idx / Wp) % Hp);
+    int b = (int)(idx / ((int64_t)Wp * Hp));
+    const float *s = src + (int64_t)b * bstride;
+    float *d = dst + idx * C;
+    int Ho = Hs * up, Wo = Ws * up;
+    if (y >= Ho || x >= Wo) {
+        for (int c = 0; c < C; ++c) d[c] = 0.f;
+        return;
+    }
+    if (up == 1) {
+        for (int c = 0; c < C; ++c) d[c] = __ldg(s + ((int64_t)c * Hs + y) * Ws + x);
+        return;
+    }
+    // bilinear, align_corners=False, scale = 1/up (ATen area_pixel_compute_source_index)
+    float inv = 1.0f / (float)up;
+    float sy = fmaxf(inv * ((float)y + 0.5f) - 0.5f, 0.f);
+    float sx = fmaxf(inv * ((float)x + 0.5f) - 0.5f, 0.f);
+    int y0 = (int)sy, x0 = (int)sx;
+    int y1 = min(y0 + 1, Hs - 1), x1 = min(x0 + 1, Ws - 1);
+    float ly = sy - (float)y0, lx = sx - (float)x0;
+    float hy = 1.f - ly, hx = 1.f - lx;
+    for (int c = 0; c < C; ++c) {
+        const float *pc = s + (int64_t)c * Hs * Ws;
+        float p00 = __ldg(pc + (int64_t)y0 * Ws + x0), p01 = __ldg(pc + (int64_t)y0 * Ws + x1);
+        float p10 = __ldg(pc + (int64_t)y1 * Ws + x0), p11 = __ldg(pc + (int64_t)y1 * Ws + x1);
+        d[c] = hy * (hx * p00 + lx * p01) + ly * (hx * p10 + lx * p11);
+    }
+}
+
+extern "C" int turtle_pack_frame(const float *src, int64_t src_bstride, float *dst, int B, int C, int Hs, int Ws,
+                                 int Hp, int Wp, int upscale, void *stream) {
+    if (!src || !dst || B < 1 || C < 1 || (upscale != 1 && upscale != 4) || Hp < Hs * upscale ||
+        Wp < Ws * upscale)
+        return TURTLE_EINVAL;
+    int64_t total = (int64_t)B * Hp * Wp;
+    pack_frame_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, as_stream(stream)>>>(src, src_bstride, dst, B, C, Hs,
+                                                                                  Ws, Hp, Wp, upscale);
+    TURTLE_CHECK_LAUNCH();
+    return TURTLE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// first conv: tiny Cin -> Cout.  thread = (pixel, 4 output channels)
+// ------------------------------------------------------------------------------------------
+__global__ void conv3x3_first_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                     const float *__restrict__ bias, float *__restrict__ y, int B, int H, int W,
+                                     int Cin, int Cout) {
+    extern __shared__ float ws[];   // [9][Cin][Cout]
+    for (int i = threadIdx.x; i < 9 * Cin * Cout; i += blockDim.x) {
+        int co = i % Cout, ci = (i / Cout) % Cin, tap = i / (Cout * Cin);
+        ws[i] = w[((int64_t)co * Cin + ci) * 9 + tap];
+    }
+    __syncthreads();
+    int groups = Cout >> 2;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = (int64_t)B * H * W * groups;
+    if (idx >= total) return;
+    int g = (int)(idx % groups);
+    int64_t p = idx / groups;
+    int px = (int)(p % W), py = (int)((p / W) % H);
+    int64_t b = p / ((int64_t)W * H);
+    float4 acc = bias ? *reinterpret_cast<const float4 *>(bias + g * 4) : make_float4(0, 0, 0, 0);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        int yy = py + ky - 1;
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            int xx = px + kx - 1;
+            if (xx < 0 || xx >= W) continue;
+            const float *xp = x + ((b * H + yy) * W + xx) * Cin;
+            const float *wp = ws + (ky * 3 + kx) * Cin * Cout + g * 4;
+            for (int ci = 0; ci < Cin; ++ci) {
+                float v = __ldg(xp + ci);
+                float4 wv = *reinterpret_cast<const float4 *>(wp + ci * Cout);
+                acc.x = fmaf(v, wv.x, acc.x);
+                acc.y = fmaf(v, wv.y, acc.y);
+                acc.z = fmaf(v, wv.z, acc.z);
+                acc.w = fmaf(v, wv.w, acc.w);
+            }
+        }
+    }
+    stg_stream(y + p * Cout + g * 4, acc);
+}
+
+extern "C" int turtle_conv3x3_first(const float *x, const float *w, const float *bias, float *y, int B, int H,
+                                    int W, int Cin, int Cout, void *stream) {
+    if (!x || !w || !y || Cin < 1 || Cin > 16 || Cout < 4 || (Cout & 3)) return TURTLE_EINVAL;
+    size_t smem = (size_t)9 * Cin * Cout * sizeof(float);
+    if (smem > 48 * 1024) return TURTLE_EINVAL;
+    int64_t total = (int64_t)B * H * W * (Cout >> 2);
+    conv3x3_first_kernel<<<(unsigned)cdiv64(total, 256), 256, smem, as_stream(stream)>>>(x, w, bias, y, B, H, W,
+                                                                                        Cin, Cout);
+    TURTLE_CHECK_LAUNCH();
+    return TURTLE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// last conv: Cin -> Cout<=4, + bias + current frame, cropped, NCHW out.  thread = output pixel
+// ------------------------------------------------------------------------------------------
+__global__ void conv3x3_last_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                    const float *__restrict__ bias, const float *__restrict__ cur, int cur_ld,
+                                    int cur_coff, float *__restrict__ out, int B, int H, int W, int Cin, int Cout,
+                                    int Hc, int Wc) {
+    extern __shared__ float ws[];   // [Cout][9][Cin]
+    for (int i = threadIdx.x; i < Cout * 9 * Cin; i += blockDim.x) {
+        int ci = i % Cin, tap = (i / Cin) % 9, co = i / (9 * Cin);
+        ws[i] = w[((int64_t)co * Cin + ci) * 9 + tap];
+    }
+    __syncthreads();
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = (int64_t)B * Hc * Wc;
+    if (idx >= total) return;
+    int px = (int)(idx % Wc), py = (int)((idx / Wc) % Hc);
+    int64_t b = idx / ((int64_t)Wc * Hc);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int ky = 0; ky < 3; ++ky) {
+        int yy = py + ky - 1;
+        if (yy < 0 || yy >= H) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+            int xx = px + kx - 1;
+            if (xx < 0 || xx >= W) continue;
+            const float4 *xp = reinterpret_cast<const float4 *>(x + ((b * H + yy) * W + xx) * Cin);
+            int tap = ky * 3 + kx;
+            for (int c4 = 0; c4 < (Cin >> 2); ++c4) {
+                float4 v = __ldg(xp + c4);
+#pragma unroll
+                for (int co = 0; co < 4; ++co) {
+                    if (co < Cout) {
+                        float4 wv = *reinterpret_cast<const float4 *>(ws + (co * 9 + tap) * Cin + c4 * 4);
+                        acc[co] = fmaf(v.x, wv.x, acc[co]);
+                        acc[co] = fmaf(v.y, wv.y, acc[co]);
+                        acc[co] = fmaf(v.z, wv.z, acc[co]);
+                        acc[co] = fmaf(v.w, wv.w, acc[co]);
+                    }
+                }
+            }
+        }
+    }
+    const float *cp = cur + ((b * H + py) * W + px) * cur_ld + cur_coff;
+    for (int co = 0; co < Cout; ++co) {
+        float v = acc[co] + (bias ? bias[co] : 0.f) + __ldg(cp + co);
+        out[((b * Cout + co) * Hc + py) * (int64_t)Wc + px] = v;
+    }
+}
+
+extern "C" int turtle_conv3x3_last(const float *x, const float *w, const float *bias, const float *cur, int cur_ld,
+                                   int cur_coff, float *out, int B, int H, int W, int Cin, int Cout, int Hc, int Wc,
+                                   void *stream) {
+    if (!x || !w || !cur || !out || Cout < 1 || Cout > 4 || (Cin & 3) || Hc > H || Wc > W) return TURTLE_EINVAL;
+    size_t smem = (size_t)Cout * 9 * Cin * sizeof(float);
+    if (smem > 48 * 1024) return TURTLE_EINVAL;
+    int64_t total = (int64_t)B * Hc * Wc;
+    conv3x3_last_kernel<<<(unsigned)cdiv64(total, 128), 128, smem, as_stream(stream)>>>(
+        x, w, bias, cur, cur_ld, cur_coff, out, B, H, W, Cin, Cout, Hc, Wc);
+    TURTLE_CHECK_LAUNCH();
+    return TURTLE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// channel LayerNorm: one warp per pixel, values held in registers (two-pass, like the reference)
+// ------------------------------------------------------------------------------------------
+template <bool VEC4>
+__global__ void layernorm_kernel(const float *__restrict__ x, int ldx, const float *__restrict__ w,
+                                 const float *__restrict__ b, float *__restrict__ y, int ldy, int64_t P, int C) {
+    int lane = threadIdx.x & 31;
+    int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (p >= P) return;
+    const float *xp = x + p * ldx;
+    float *yp = y + p * ldy;
+    float v[16];
+    float s = 0.f;
+    if (VEC4) {
+        int n4 = C >> 7;   // float4 per lane
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < n4) {
+                float4 t = ldg_stream(xp + i * 128 + lane * 4);
+                v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+                s += (t.x + t.y) + (t.z + t.w);
+            }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            int c = lane + 32 * i;
+            v[i] = c < C ? __ldg(xp + c) : 0.f;
+            s += v[i];
+        }
+    }
+    float mu = warp_sum(s) / (float)C;
+    float q = 0.f;
+    if (VEC4) {
+        int n = C >> 5;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+            if (i < n) { float d = v[i] - mu; q = fmaf(d, d, q); }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            int c = lane + 32 * i;
+            if (c < C) { float d = v[i] - mu; q = fmaf(d, d, q); }
+        }
+    }
+    float den = sqrtf(warp_sum(q) / (float)C + 1e-5f);
+    float sub = b ? mu : 0.f;   // BiasFree variant keeps the mean in the numerator (T1:79-81)
+    if (VEC4) {
+        int n4 = C >> 7;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < n4) {
+                int c = i * 128 + lane * 4;
+                float4 wv = *reinterpret_cast<const float4 *>(w + c);
+                float4 bv = b ? *reinterpret_cast<const float4 *>(b + c) : make_float4(0, 0, 0, 0);
+                float4 o;
+                o.x = (v[4 * i] - sub) / den * wv.x + bv.x;
+                o.y = (v[4 * i + 1] - sub) / den * wv.y + bv.y;
+                o.z = (v[4 * i + 2] - sub) / den * wv.z + bv.z;
+                o.w = (v[4 * i + 3] - sub) / den * wv.w + bv.w;
+                *reinterpret_cast<float4 *>(yp + c) = o;
+            }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            int c = lane + 32 * i;
+            if (c < C) yp[c] = (v[i] - sub) / den * w[c] + (b ? b[c] : 0.f);
+        }
+    }
+}
+
+extern "C" int turtle_layernorm(const float *x, int ldx, const float *w, const float *b, float *y, int ldy,
+                                int64_t P, int C, void *stream) {
+    if (!x || !w || !y || C < 1 || C > 512 || P < 1) return TURTLE_EINVAL;
+    unsigned grid = (unsigned)cdiv64(P, 8);
+    bool vec = (C % 128 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((((uintptr_t)x | (uintptr_t)y) & 15) == 0);
+    if (vec)
+        layernorm_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(x, ldx, w, b, y, ldy, P, C);
+    else
+        layernorm_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(x, ldx, w, b, y, ldy, P, C);
+    TURTLE_CHECK_LAUNCH();
+    return TURTLE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// depthwise 3x3.  thread = (pixel, 4 channels); weights tap-major [9][C]
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fma4(float4 &a, const float4 &x, const float4 &w) {
+    a.x = fmaf(x.x, w.x, a.x);
+    a.y = fmaf(x.y, w.y, a.y);
+    a.z = fmaf(x.z, w.z, a.z);
+    a.w = fmaf(x.w, w.w, a.w);
+}
+
+template <int FUSE>
+__global__ void dwconv3x3_kernel(const float *__restrict__ x, int ldx, const float *__restrict__ w9,
+                                 const float *__restrict__ bias, float *__restrict__ y, int ldy, int NB, int H,
+                                 int W, int C, int layout, int ws) {
+    const int Cout = FUSE == 2 ? (C >> 1) : C;
+    const int groups = Cout >> 2;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = (int64_t)NB * H * W * groups;
+    if (idx >= total) return;
+    int g = (int)(idx % groups);
+    int64_t p = idx / groups;
+    int px = (int)(p % W), py = (int)((p / W) % H);
+    int64_t nb = p / ((int64_t)W * H);
+    int c0 = g * 4;
+    float4 a = bias ? *reinterpret_cast<const float4 *>(bias + c0) : make_float4(0, 0, 0, 0);
+    float4 a2 = make_float4(0, 0, 0, 0);
+    if (FUSE == 2 && bias) a2 = *reinterpret_cast<const float4 *>(bias + c0 + Cout);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        int yy = py + ky - 1;
+        if (yy < 0 || yy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            int xx = px + kx - 1;
+            if (xx < 0 || xx >= W) continue;
+            const float *xp = x + ((nb * H + yy) * W + xx) * ldx + c0;
+            const float *wp = w9 + (ky * 3 + kx) * C + c0;
+            fma4(a, __ldg(reinterpret_cast<const float4 *>(xp)), __ldg(reinterpret_cast<const float4 *>(wp)));
+            if (FUSE == 2)
+                fma4(a2, __ldg(reinterpret_cast<const float4 *>(xp + Cout)),
+                     __ldg(reinterpret_cast<const float4 *>(wp + Cout)));
+        }
+    }
+    if (FUSE == 1) {
+        a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w);
+    } else if (FUSE == 2) {
+        a.x = gelu_erf(a.x) * a2.x; a.y = gelu_erf(a.y) * a2.y;
+        a.z = gelu_erf(a.z) * a2.z; a.w = gelu_erf(a.w) * a2.w;
+    }
+    if (layout == 0) {
+        stg_stream(y + p * ldy + c0, a);
+    } else {
+        int Hg = H / ws, Wg = W / ws;
+        int64_t n = (int64_t)(py % Hg) * Wg + (px % Wg);
+        int64_t e = ((int64_t)(py / Hg) * ws + (px / Wg)) * Cout + c0;
+        stg_stream(y + ((nb * Hg * Wg + n) * ws * ws) * Cout + e, a);
+    }
+}
+
+extern "C" int turtle_dwconv3x3(const float *x, int ldx, const float *w, const float *bias, float *y, int ldy,
+                                int NB, int H, int W, int C, int fuse, int layout, int ws, void *stream) {
+    if (!x || !w || !y || NB < 1 || C < 4 || fuse < 0 || fuse > 2 || (ldx & 3)) return TURTLE_EINVAL;
+    int Cout = fuse == 2 ? C / 2 : C;
+    if ((Cout & 3) || (fuse == 2 && (C & 7))) return TURTLE_EINVAL;
+    if (layout == 0 && (ldy & 3)) return TURTLE_EINVAL;
+    if (layout == 1 && (ws < 1 || H % ws || W % ws)) return TURTLE_EINVAL;
+    if ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)w) & 15) != 0) return TURTLE_EINVAL;
+    int64_t total = (int64_t)NB * H * W * (Cout >> 2);
+    unsigned grid = (unsigned)cdiv64(total, 256);
+    cudaStream_t s = as_stream(stream);
+    if (fuse == 0)
+        dwconv3x3_kernel<0><<<grid, 256, 0, s>>>(x, ldx, w, bias, y, ldy, NB, H, W, C, layout, ws);
+    else if (fuse == 1)
+        dwconv3x3_kernel<1><<<grid, 256, 0, s>>>(x, ldx, w, bias, y, ldy, NB, H, W, C, layout, ws);
+    else
+        dwconv3x3_kernel<2><<<grid, 256, 0, s>>>(x, ldx, w, bias, y, ldy, NB, H, W, C, layout, ws);
+    TURTLE_CHECK_LAUNCH();
+    return TURTLE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// scale_cols
+// ------------------------------------------------------------------------------------------
+__global__ void scale_cols_kernel(const float *__restrict__ x, int ldx, int x_hs, const float *__restrict__ s,
+                                  float *__restrict__ y, int ldy, int y_hs, int64_t P, int heads, int ch) {
+    int per = heads * (ch >> 2);
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P * per) return;
+    int r = (int)(idx % per);
+    int64_t p = idx / per;
+    int h = r / (ch >> 2), j = (r % (ch >> 2)) * 4;
+    float4 v = *reinterpret_cast<const float4 *>(x + p * ldx + (int64_t)h * x_hs + j);
+    if (s) {
+        float4 sv = *reinterpret_cast<const float4 *>(s + h * ch + j);
+        v.x *= sv.x; v.y *= sv.y; v.z *= sv.z; v.w *= sv.w;
+    }
+    *reinterpret_cast<float4 *>(y + p * ldy + (int64_t)h * y_hs + j) = v;
+}
+
+extern "C" int turtle_scale_cols(const float *x, int ldx, int x_hs, const float *s, float *y, int ldy, int y_hs,
+                                 int64_t P, int heads, int ch, void *stream) {
+    if (!x || !y || (ch & 3) || (ldx & 3) || (ldy & 3) || (x_hs & 3) || (y_hs & 3)) return TURTLE_EINVAL;
+    int64_t total = P * heads * (ch >> 2);
+    scale_cols_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, as_stream(stream)>>>(x, ldx, x_hs, s, y, ldy, y_hs, P,
+                                                                                  heads, ch);
+    TURTLE_CHECK_LAUNCH();
+    return TURTLE_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// T0 positional code (T0:412-439), analytic
+// ------------------------------------------------------------------------------------------
+__global__ void add_posenc_kernel(const float *__restrict__ x, float *__restrict__ y, int B, int H, int W, int C) {
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t total = (int64_t)B * H * W * C;
+    if (idx >= total) return;
+    int c = (int)(idx % C);
+    int64_t p = idx / C;
+    int px = (int)(p % W), py = (int)((p / W) % H);
+    int half = C >> 1;
+    int cc = c < half ? c : c - half;
+    float pos = c < half ? (float)px : (float)py;
+    float coef = (float)(-(9.210340371976184 /* ln 1e4 */ / (double)half));
+    float div = expf((float)(cc & ~1) * coef);
+    float ang = pos * div;
+    float pe = (cc & 1) ? cosf(ang) : sinf(ang);
+    y[idx] = x[idx] + pe;
+}
+
+extern "C" int turtle_add_posenc(const float *x, float *y, int B, int H, int W, int C, void *stream) {
+    if (!x || !y || (C & 3)) return TURTLE_EINVAL;
+    int64_t total = (int64_t)B * H * W * C;
+    add_posenc_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, as_stream(stream)>>>(x, y, B, H, W, C);
+    TURTLE_CHECK_LAUNCH();
+    return TURTLE_OK;
+}
+
+extern "C" int turtle_abi_version(void) { return 1; }
+extern "C" const char *turtle_build_info(void) {
+    return "libturtle_b200 sm_100a, CUDA "
+#define TURTLE_STR2(x) #x
+#define TURTLE_STR(x) TURTLE_STR2(x)
+        TURTLE_STR(__CUDACC_VER_MAJOR__) "." TURTLE_STR(__CUDACC_VER_MINOR__);
+}

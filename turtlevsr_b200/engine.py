@@ -1,0 +1,489 @@
+"""FrameEngine: the per-frame kernel schedule of the Turtle hot path.
+
+One ``forward`` = one frame (T1:1045-1132).  Everything between the caller's NCHW frame and the
+NCHW output runs in the hand-written kernels of libturtle_b200.so through the C ABI; torch is used
+for device memory (workspace, parameters, history rings) and the stream only.  Activations are
+fp32 channels-last.  There is no fallback path: CPU tensors or a missing library raise.
+
+Schedule per block (each arrow is one kernel):
+
+  ReducedAttn  LN -> 1x1(+b) -> dw3x3(+b)+GELU -> 1x1(+b)*beta+x
+  FFW          LN -> 1x1(+b)+GELU -> 1x1(+b)*gamma+x
+  GFFW         LN -> 1x1 -> dw3x3+gate -> 1x1+x
+  Channel/FHR  LN -> 1x1 -> dw3x3 -> gram (per key segment) -> softmax -> fold W_o -> apply GEMM + x
+               (FHR also pushes k-hat, v of the frame into its ring)
+  CHM          LN -> SAB[ 1x1,dw (qk) ; 1x1,dw->ring (v) ; 1x1,window-reduce->ring (k) ; same (q) ;
+                          select ; aggregate ; 1x1 ] -> 1x1,dw (kv over F frames) -> router as FHR
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional
+
+import torch
+
+from . import capi
+from .capi import GemmArgs, call
+from .history import FhrRing, SabRing, resolve_ring
+
+_NULL = None
+
+
+def _ptr(t: Optional[torch.Tensor], off: int = 0):
+    return None if t is None else t.data_ptr() + 4 * off
+
+
+class _Workspace:
+    """Named, grow-only device scratch; steady-state frames allocate nothing."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs: Dict[str, torch.Tensor] = {}
+
+    def get(self, name: str, *shape, dtype=torch.float32) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= int(s)
+        b = self.bufs.get(name)
+        if b is None or b.numel() < n or b.dtype != dtype:
+            b = torch.empty(max(n, 1), device=self.device, dtype=dtype)
+            self.bufs[name] = b
+        return b[:n].view(*shape)
+
+
+class FrameEngine:
+    def __init__(self, model):
+        self.model = model
+        self.packed: Dict[str, torch.Tensor] = {}
+        self.ws: Optional[_Workspace] = None
+        self.last_trace: Optional[dict] = None      # filled when model.record_trace is truthy
+        # host-logic tests (CPU, no kernels): record the launch list instead of executing it
+        self.dry_run = bool(getattr(model, "_dry_run", False))
+        self.launch_log: List[str] = []
+        if not self.dry_run:
+            capi.load()                              # fail loudly now if the CUDA library is unavailable
+
+    def _call(self, name, *args):
+        if self.dry_run:
+            self.launch_log.append(name)
+            return
+        call(name, *args)
+
+    def invalidate(self):
+        self.packed.clear()
+
+    # ------------------------------------------------------------------------------------
+    # parameters
+    # ------------------------------------------------------------------------------------
+    def _param(self, name: str) -> Optional[torch.Tensor]:
+        t = self._sd.get(name)
+        return t
+
+    def _w(self, name: str, kind: str = "raw") -> Optional[torch.Tensor]:
+        """Device weight in the layout the kernels want (packed once, cached)."""
+        key = f"{kind}:{name}"
+        t = self.packed.get(key)
+        if t is not None:
+            return t
+        p = self._sd.get(name)
+        if p is None:
+            return None
+        p = p.detach()
+        if p.dtype != torch.float32:
+            p = p.float()
+        if kind == "raw":                 # 1x1 conv [Cout,Cin,1,1], vectors, beta/gamma, temperature
+            t = p.contiguous()
+        elif kind == "dw":                # [C,1,k,k] -> tap-major [k*k, C]
+            t = p.reshape(p.shape[0], -1).t().contiguous()
+        elif kind == "dw_lo" or kind == "dw_hi":     # halves of a depthwise weight (T0 q/k patches)
+            h = p.shape[0] // 2
+            q = p[:h] if kind == "dw_lo" else p[h:]
+            t = q.reshape(h, -1).t().contiguous()
+        elif kind == "conv3":             # [Cout,Cin,3,3] -> [Cout, 9*Cin] tap-major
+            t = p.permute(0, 2, 3, 1).reshape(p.shape[0], -1).contiguous()
+        else:
+            raise ValueError(kind)
+        self.packed[key] = t
+        return t
+
+    # ------------------------------------------------------------------------------------
+    # kernel wrappers
+    # ------------------------------------------------------------------------------------
+    def gemm(self, segs, segw, Wt, out, ldo, P, Cout, bias=None, scale=None, act=0, res=None, ldres=0,
+             im2col=0, geom=None, store=0):
+        """segs: list of (ptr:int, lda:int)."""
+        a = GemmArgs()
+        a.mode = self.mode
+        a.im2col = im2col
+        a.P = P
+        if geom is not None:
+            a.B, a.H, a.W = geom
+        a.Cout = Cout
+        a.nseg = len(segs)
+        a.segw = segw
+        for i, (p, ld) in enumerate(segs):
+            a.A[i] = p
+            a.lda[i] = ld
+        a.Wt = _ptr(Wt) if isinstance(Wt, torch.Tensor) else Wt
+        a.bias = _ptr(bias)
+        a.scale = _ptr(scale)
+        a.act = act
+        a.res = res
+        a.ldres = ldres
+        a.out = out
+        a.ldo = ldo
+        a.store = store
+        self._call("turtle_gemm", C.byref(a), self.stream)
+
+    def conv1x1(self, x, ldx, Cin, wname, out, ldo, P, Cout, **kw):
+        self.gemm([(x, ldx)], Cin, self._w(wname), out, ldo, P, Cout, **kw)
+
+    def layernorm(self, x: torch.Tensor, pre: str, C_: int, P: int) -> torch.Tensor:
+        y = self.ws.get("xn", P, C_)
+        self._call("turtle_layernorm", _ptr(x), C_, _ptr(self._w(pre + "body.weight")), _ptr(self._w(pre + "body.bias")),
+             _ptr(y), C_, P, C_, self.stream)
+        return y
+
+    def dwconv(self, x, ldx, wname, bname, y, ldy, NB, H, W, Cc, fuse=0, layout=0, ws=1, wkind="dw"):
+        self._call("turtle_dwconv3x3", x, ldx, _ptr(self._w(wname, wkind)), _ptr(self._w(bname)) if bname else None, y, ldy,
+             NB, H, W, Cc, fuse, layout, ws, self.stream)
+
+    # ------------------------------------------------------------------------------------
+    # feed-forwards (x updated in place)
+    # ------------------------------------------------------------------------------------
+    def gated_ffw(self, pre, xn, x, P, c, H, W, B):
+        hid2 = self._sd[pre + "project_in.weight"].shape[0]
+        hid = hid2 // 2
+        t = self.ws.get("wide", P, hid2)
+        self.conv1x1(_ptr(xn), c, c, pre + "project_in.weight", _ptr(t), hid2, P, hid2,
+                     bias=self._w(pre + "project_in.bias"))
+        g = self.ws.get("dw", P, hid)
+        self.dwconv(_ptr(t), hid2, pre + "dwconv.weight", pre + "dwconv.bias", _ptr(g), hid, B, H, W, hid2, fuse=2)
+        self.conv1x1(_ptr(g), hid, hid, pre + "project_out.weight", _ptr(x), c, P, c,
+                     bias=self._w(pre + "project_out.bias"), res=_ptr(x), ldres=c)
+
+    def plain_ffw(self, pre, xn, x, P, c):
+        t = self.ws.get("wide", P, 2 * c)
+        self.conv1x1(_ptr(xn), c, c, pre + "conv4.weight", _ptr(t), 2 * c, P, 2 * c, bias=self._w(pre + "conv4.bias"),
+                     act=capi.ACT_GELU)
+        self.conv1x1(_ptr(t), 2 * c, 2 * c, pre + "conv5.weight", _ptr(x), c, P, c, bias=self._w(pre + "conv5.bias"),
+                     scale=self._w(pre + "gamma"), res=_ptr(x), ldres=c)
+
+    # ------------------------------------------------------------------------------------
+    # attentions (x updated in place: x += attn(xn))
+    # ------------------------------------------------------------------------------------
+    def reduced_attn(self, pre, xn, x, P, c, H, W, B):
+        t = self.ws.get("wide", P, 2 * c)
+        self.conv1x1(_ptr(xn), c, c, pre + "conv1.weight", _ptr(t), 2 * c, P, 2 * c, bias=self._w(pre + "conv1.bias"))
+        u = self.ws.get("dw", P, 2 * c)
+        self.dwconv(_ptr(t), 2 * c, pre + "conv2.weight", pre + "conv2.bias", _ptr(u), 2 * c, B, H, W, 2 * c, fuse=1)
+        self.conv1x1(_ptr(u), 2 * c, 2 * c, pre + "conv3.weight", _ptr(x), c, P, c, bias=self._w(pre + "conv3.bias"),
+                     scale=self._w(pre + "beta"), res=_ptr(x), ldres=c)
+
+    def channel_attn(self, pre, xn, x, B, H, W, c, heads, hist_segs=None, ring: Optional[FhrRing] = None,
+                     ring_slot: int = -1):
+        """ChannelAttention / FrameHistoryRouter.
+
+        hist_segs: per batch element a list of key/value history segments (oldest first), each
+        ``dict(k=ptr, ldk=, khs=, v=ptr, ldv=, vhs=, prenorm=bool)``.  The frame's own q/k/v are
+        appended as the last segment.  With ``ring`` the normalised key rows and value rows of the
+        frame are pushed into slot ``ring_slot`` (T1:286)."""
+        Pimg = H * W
+        P = B * Pimg
+        ch = c // heads
+        qkv = self.ws.get("wide", P, 3 * c)
+        self.conv1x1(_ptr(xn), c, c, pre + "qkv.weight", _ptr(qkv), 3 * c, P, 3 * c, bias=self._w(pre + "qkv.bias"))
+        qd = self.ws.get("dw", P, 3 * c)
+        self.dwconv(_ptr(qkv), 3 * c, pre + "qkv_dwconv.weight", pre + "qkv_dwconv.bias", _ptr(qd), 3 * c, B, H, W,
+                    3 * c)
+        nsplit = max(1, min((Pimg + 255) // 256, max(1, 296 // heads)))
+        temp = self._w(pre + "temperature")
+        Wo = self._w(pre + "project_out.weight")
+        for b in range(B):
+            segs = list(hist_segs[b]) if hist_segs is not None else []
+            base = b * Pimg * 3 * c
+            segs.append(dict(k=_ptr(qd, base + c), ldk=3 * c, khs=ch, v=_ptr(qd, base + 2 * c), ldv=3 * c, vhs=ch,
+                             prenorm=False))
+            S = len(segs)
+            gpart = self.ws.get("gram", S, nsplit, heads, ch, ch)
+            sqq = self.ws.get("sqq", S, nsplit, c)
+            sqk = self.ws.get("sqk", S, nsplit, c)
+            for s, sg in enumerate(segs):
+                self._call("turtle_chan_gram", _ptr(qd, base), 3 * c, ch, sg["k"], sg["ldk"], sg["khs"], Pimg, heads, ch,
+                     nsplit, _ptr(gpart[s]), _ptr(sqq[s]), _ptr(sqk[s]), self.mode, self.stream)
+            flags = self._flags([1 if sg["prenorm"] else 0 for sg in segs])
+            Pm = self.ws.get("attnP", heads, ch, S * ch)
+            inv = self.ws.get("invk", S, c)
+            self._call("turtle_chan_softmax", _ptr(gpart), _ptr(sqq), _ptr(sqk), _ptr(flags), _ptr(temp), S, nsplit, heads,
+                 ch, _ptr(Pm), _ptr(inv), self.stream)
+            M = self.ws.get("attnM", c, S * c)
+            self._call("turtle_chan_fold", _ptr(Pm), _ptr(Wo), S, heads, ch, _ptr(M), self.stream)
+            vsegs = [(sg["v"] + 4 * h * sg["vhs"], sg["ldv"]) for sg in segs for h in range(heads)]
+            xb = _ptr(x, b * Pimg * c)
+            self.gemm(vsegs, ch, M, xb, c, Pimg, c, bias=self._w(pre + "project_out.bias"), res=xb, ldres=c)
+            if ring is not None:
+                self._call("turtle_scale_cols", _ptr(qd, base + c), 3 * c, ch, _ptr(inv[S - 1]),
+                     ring.slot_ptr(ring.kbuf, b, ring_slot), ring.ld, ring.head_stride, Pimg, heads, ch, self.stream)
+                self._call("turtle_scale_cols", _ptr(qd, base + 2 * c), 3 * c, ch, None,
+                     ring.slot_ptr(ring.vbuf, b, ring_slot), ring.ld, ring.head_stride, Pimg, heads, ch, self.stream)
+        if self.trace is not None:
+            self.trace.setdefault(pre, []).append(dict(qkv_dw=qd.clone()))
+
+    def _flags(self, vals: List[int]) -> torch.Tensor:
+        key = "flags:" + "".join(map(str, vals))
+        t = self.packed.get(key)
+        if t is None:
+            t = torch.tensor(vals, dtype=torch.int32, device=self.device)
+            self.packed[key] = t
+        return t
+
+    def fhr(self, pre, xn, x, B, H, W, c, heads, keep, k_in, v_in):
+        """FrameHistoryRouter with its ring (latent blocks 0 and -1, T1:243-286)."""
+        Pimg, ch = H * W, c // heads
+        ring = resolve_ring(k_in, v_in)
+        if ring is None:
+            if k_in is not None and v_in is not None:
+                ring = FhrRing.adopt(k_in, v_in, keep, ch, self.device)
+            else:
+                ring = FhrRing(B, Pimg, heads, ch, keep, self.device)
+        slot = ring.begin_push()
+        hist = []
+        for b in range(B):
+            segs = []
+            for t in range(ring.first_live, ring.pos + 1):
+                segs.append(dict(k=ring.slot_ptr(ring.kbuf, b, t), ldk=ring.ld, khs=ring.head_stride,
+                                 v=ring.slot_ptr(ring.vbuf, b, t), ldv=ring.ld, vhs=ring.head_stride, prenorm=True))
+            hist.append(segs)
+        self.channel_attn(pre, xn, x, B, H, W, c, heads, hist_segs=hist, ring=ring, ring_slot=slot)
+        # the reference returns cat(history, new)[-K:]; the window after commit is exactly that
+        ring.commit()
+        return ring.views()
+
+    def chm(self, pre, xn, x, B, H, W, c, heads, scale_patch, keep, k_in, v_in):
+        """CausalHistoryModel (T1:627-662) = StateAlignBlock (T1:548-610 / T0:459-533) + router."""
+        t0 = self.model.variant == "t0"
+        sa = pre + "spatial_aligner."
+        ws_ = 2 * scale_patch
+        Pimg = H * W
+        P = B * Pimg
+        Hg, Wg = H // ws_, W // ws_
+        N = Hg * Wg
+        Dk = ws_ * ws_ * c if t0 else 2 * c
+        Dv = ws_ * ws_ * c
+        ring = resolve_ring(k_in, v_in)
+        if ring is None:
+            if k_in is not None and v_in is not None:
+                ring = SabRing.adopt(k_in, v_in, keep, self.device)
+            else:
+                ring = SabRing(B, N, Dk, Dv, keep, self.device)
+        slot = ring.begin_push()
+        first = ring.first_live
+        F_ = ring.count + 1
+
+        # --- q/k/v feature maps -----------------------------------------------------------
+        src = xn
+        if t0:
+            src = self.ws.get("xpe", P, c)
+            self._call("turtle_add_posenc", _ptr(xn), _ptr(src), B, H, W, c, self.stream)
+        qk = self.ws.get("wide", P, 2 * c)
+        self.conv1x1(_ptr(src), c, c, sa + "qk.weight", _ptr(qk), 2 * c, P, 2 * c)
+        qkd = self.ws.get("dw", P, 2 * c)
+        vt = self.ws.get("sab_v", P, c)
+        self.conv1x1(_ptr(xn), c, c, sa + "v.weight", _ptr(vt), c, P, c)
+        qn = self.ws.get("sab_qn", B, N, Dk)
+        if not t0:
+            self.dwconv(_ptr(qk), 2 * c, sa + "qk_dwconv.weight", None, _ptr(qkd), 2 * c, B, H, W, 2 * c)
+            red = self.ws.get("wide", P, 2 * c)            # qk no longer needed
+            # k: 1x1 c->2c on the k half, then window reduce + normalise straight into the ring slot
+            self.conv1x1(_ptr(qkd, c), 2 * c, c, sa + "k2.weight", _ptr(red), 2 * c, P, 2 * c)
+            self._call("turtle_sab_window_reduce", _ptr(red), 2 * c, _ptr(self._w(sa + "k2_dwconv.weight", "dw")),
+                 _ptr(ring.kbuf[:, slot]), ring.kbuf.stride(0), B, H, W, 2 * c, ws_, self.stream)
+            self.conv1x1(_ptr(qkd), 2 * c, c, sa + "q2.weight", _ptr(red), 2 * c, P, 2 * c)
+            self._call("turtle_sab_window_reduce", _ptr(red), 2 * c, _ptr(self._w(sa + "q2_dwconv.weight", "dw")),
+                 _ptr(qn), N * Dk, B, H, W, 2 * c, ws_, self.stream)
+        for b in range(B):
+            # v: depthwise 3x3 written directly as dilated patch rows into the ring slot
+            self.dwconv(_ptr(vt, b * Pimg * c), c, sa + "v_dwconv.weight", None, _ptr(ring.vbuf[b, slot]), c, 1, H, W, c,
+                        layout=1, ws=ws_)
+            if t0:
+                self.dwconv(_ptr(qk, b * Pimg * 2 * c), 2 * c, sa + "qk_dwconv.weight", None, _ptr(qn[b]), c, 1, H, W,
+                            c, layout=1, ws=ws_, wkind="dw_lo")
+                self.dwconv(_ptr(qk, b * Pimg * 2 * c + c), 2 * c, sa + "qk_dwconv.weight", None,
+                            _ptr(ring.kbuf[b, slot]), c, 1, H, W, c, layout=1, ws=ws_, wkind="dw_hi")
+                self._call("turtle_sab_patch_normalize", _ptr(qn[b]), N, Dk, self.stream)
+                self._call("turtle_sab_patch_normalize", _ptr(ring.kbuf[b, slot]), N, Dk, self.stream)
+
+        # --- selection + aggregation over the F live frames ------------------------------------
+        agg = self.ws.get("sab_agg", B, F_, Pimg, c)
+        idx = self.ws.get("sab_idx", B, F_, N, capi.SAB_SLOTS, dtype=torch.int32)
+        wgt = self.ws.get("sab_wgt", B, F_, N, capi.SAB_SLOTS)
+        temp = self._w(sa + "temperature")
+        for b in range(B):
+            kf = _ptr(ring.kbuf[b, first])
+            vf = _ptr(ring.vbuf[b, first])
+            if not t0:
+                self._call("turtle_sab_select", _ptr(qn[b]), kf, N * Dk, F_, Hg, Wg, Dk, _ptr(temp), 0, _ptr(idx[b]),
+                     _ptr(wgt[b]), self.mode, self.stream)
+            self._call("turtle_sab_aggregate", _ptr(idx[b]), _ptr(wgt[b]), vf, N * Dv, _ptr(agg[b]), F_, Hg, Wg, ws_, c,
+                 1 if t0 else 0, self.stream)
+        if self.trace is not None:
+            self.trace.setdefault(sa, []).append(dict(idx=idx.clone(), wgt=wgt.clone(), qn=qn.clone()))
+        xs = self.ws.get("sab_xs", B, F_, Pimg, c)
+        self.conv1x1(_ptr(agg), c, c, sa + "project_out.weight", _ptr(xs), c, B * F_ * Pimg, c)
+        ring.commit()
+        k_out, v_out = ring.views()
+
+        # --- router over the aligned history (T1:649-660) ---------------------------------------
+        kv = self.ws.get("chm_kv", B * F_ * Pimg, 2 * c)
+        self.conv1x1(_ptr(xs), c, c, pre + "kv.weight", _ptr(kv), 2 * c, B * F_ * Pimg, 2 * c)
+        kvd = self.ws.get("chm_kvd", B, F_, Pimg, 2 * c)
+        self.dwconv(_ptr(kv), 2 * c, pre + "kv_dwconv.weight", None, _ptr(kvd), 2 * c, B * F_, H, W, 2 * c)
+        ch = c // heads
+        hist = []
+        for b in range(B):
+            segs = []
+            for f in range(F_):
+                base = (b * F_ + f) * Pimg * 2 * c
+                segs.append(dict(k=_ptr(kvd, base), ldk=2 * c, khs=ch, v=_ptr(kvd, base + c), ldv=2 * c, vhs=ch,
+                                 prenorm=False))
+            hist.append(segs)
+        self.channel_attn(pre + "ChanAttn.", xn, x, B, H, W, c, heads, hist_segs=hist)
+        return k_out, v_out
+
+    # ------------------------------------------------------------------------------------
+    # block / level
+    # ------------------------------------------------------------------------------------
+    def block(self, pre, blk, x, B, H, W, c, lvl, k_in=None, v_in=None):
+        P = B * H * W
+        kc = vc = None
+        at = blk.attention_type
+        if at != "NoAttn":
+            xn = self.layernorm(x, pre + "norm1.", c, P)
+            a = pre + "attn."
+            if at == "Channel":
+                self.channel_attn(a, xn, x, B, H, W, c, lvl.num_heads)
+            elif at == "ReducedAttn":
+                self.reduced_attn(a, xn, x, P, c, H, W, B)
+            elif at == "FHR":
+                kc, vc = self.fhr(a, xn, x, B, H, W, c, lvl.num_heads, lvl.num_frames_tocache, k_in, v_in)
+            elif at == "CHM":
+                kc, vc = self.chm(a, xn, x, B, H, W, c, lvl.num_heads, lvl.Scale_patchsize, lvl.num_frames_tocache,
+                                  k_in, v_in)
+        xn = self.layernorm(x, pre + "norm2.", c, P)
+        if blk.FFW_type == "GFFW":
+            self.gated_ffw(pre + "ffn.", xn, x, P, c, H, W, B)
+        else:
+            self.plain_ffw(pre + "ffn.", xn, x, P, c)
+        return kc, vc
+
+    def level(self, name, x, B, H, W, k_in=None, v_in=None):
+        lvl = getattr(self.model, name)
+        n = len(lvl.transformer_blocks)
+        kc = vc = None
+        for i, blk in enumerate(lvl.transformer_blocks):
+            last = i == n - 1
+            kc, vc = self.block(f"{name}.transformer_blocks.{i}.", blk, x, B, H, W, lvl.dim, lvl,
+                                k_in if last else None, v_in if last else None)
+        return kc, vc
+
+    def latent(self, x, B, H, W, k1, v1, k2, v2):
+        lvl = self.model.latent
+        n = len(lvl.transformer_blocks)
+        out = [None] * 4
+        for i, blk in enumerate(lvl.transformer_blocks):
+            pre = f"latent.transformer_blocks.{i}."
+            if i == 0:
+                out[0], out[1] = self.block(pre, blk, x, B, H, W, lvl.dim, lvl, k1, v1)
+            elif i == n - 1:
+                out[2], out[3] = self.block(pre, blk, x, B, H, W, lvl.dim, lvl, k2, v2)
+            else:
+                self.block(pre, blk, x, B, H, W, lvl.dim, lvl)
+        return out
+
+    def conv3x3(self, x, Cin, wname, out, ldo, B, H, W, Cout, store):
+        self.gemm([(_ptr(x), Cin)], Cin, self._w(wname, "conv3"), _ptr(out), ldo, B * H * W, Cout, im2col=1,
+                  geom=(B, H, W), store=store)
+
+    # ------------------------------------------------------------------------------------
+    # whole frame
+    # ------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, inp: torch.Tensor, k_cached=None, v_cached=None):
+        m = self.model
+        if not inp.is_cuda and not self.dry_run:
+            raise RuntimeError("turtlevsr_b200 runs on CUDA tensors only (no CPU fallback)")
+        if inp.dim() != 5 or inp.shape[1] != 2:
+            raise ValueError("expected input of shape [B, 2, C, H, W]")
+        self.device = inp.device
+        first_param = next(m.parameters())
+        if first_param.device != inp.device:
+            raise RuntimeError(f"model is on {first_param.device}, input on {inp.device}")
+        if self.ws is None or self.ws.device != inp.device:
+            self.ws = _Workspace(inp.device)
+            self.packed.clear()
+        self._sd = dict(m.named_parameters())
+        self.mode = capi.TF32 if m.precision == "tf32" else capi.FP32
+        self.trace = {} if getattr(m, "record_trace", False) else None
+        inp = inp.float().contiguous()
+        B, _, Cc, Hs, Ws = inp.shape
+        up = 4 if m.variant == "super" else 1
+        H, W = Hs * up, Ws * up
+        Hp, Wp = H + (-H) % 32, W + (-W) % 32
+        if k_cached is None:
+            k_cached, v_cached = [None] * 8, [None] * 8
+        dim = m.dim
+        import contextlib
+        with (contextlib.nullcontext() if self.dry_run else torch.cuda.device(inp.device)):
+            self.stream = 0 if self.dry_run else torch.cuda.current_stream().cuda_stream
+            ws = self.ws
+            if m.use_both_input:
+                Ci, src, bstride = 2 * Cc, _ptr(inp), 2 * Cc * Hs * Ws
+            else:
+                Ci, src, bstride = Cc, _ptr(inp, Cc * Hs * Ws), 2 * Cc * Hs * Ws
+            img = ws.get("img", B, Hp, Wp, Ci)
+            self._call("turtle_pack_frame", src, bstride, _ptr(img), B, Ci, Hs, Ws, Hp, Wp, up, self.stream)
+
+            ks: List[Optional[torch.Tensor]] = []
+            vs: List[Optional[torch.Tensor]] = []
+            e1 = ws.get("e1", B * Hp * Wp, dim)
+            self._call("turtle_conv3x3_first", _ptr(img), _ptr(self._w("input_projection.weight")),
+                 _ptr(self._w("input_projection.bias")), _ptr(e1), B, Hp, Wp, Ci, dim, self.stream)
+            kc, vc = self.level("encoder_level1", e1, B, Hp, Wp, k_cached[0], v_cached[0]); ks.append(kc); vs.append(vc)
+            H2, W2 = Hp // 2, Wp // 2
+            e2 = ws.get("e2", B * H2 * W2, dim * 2)
+            self.conv3x3(e1, dim, "down1_2.body.0.weight", e2, dim * 2, B, Hp, Wp, dim // 2, capi.STORE_UNSHUFFLE2)
+            kc, vc = self.level("encoder_level2", e2, B, H2, W2, k_cached[1], v_cached[1]); ks.append(kc); vs.append(vc)
+            H3, W3 = H2 // 2, W2 // 2
+            e3 = ws.get("e3", B * H3 * W3, dim * 4)
+            self.conv3x3(e2, dim * 2, "down2_3.body.0.weight", e3, dim * 4, B, H2, W2, dim, capi.STORE_UNSHUFFLE2)
+            kc, vc = self.level("encoder_level3", e3, B, H3, W3, k_cached[2], v_cached[2]); ks.append(kc); vs.append(vc)
+            H4, W4 = H3 // 2, W3 // 2
+            x4 = ws.get("x4", B * H4 * W4, dim * 8)
+            self.conv3x3(e3, dim * 4, "down3_4.body.0.weight", x4, dim * 8, B, H3, W3, dim * 2, capi.STORE_UNSHUFFLE2)
+            k4, v4, k5, v5 = self.latent(x4, B, H4, W4, k_cached[3], v_cached[3], k_cached[4], v_cached[4])
+            ks += [k4, k5]; vs += [v4, v5]
+
+            def up_merge(xlow, Hl, Wl, Cl, upname, skip, redname, outname):
+                # Upsample: 3x3 Cl->2Cl + PixelShuffle(2) => [2Hl,2Wl,Cl/2]; cat(skip) ; 1x1 Cl->Cl/2
+                Ch = Cl // 2
+                u = ws.get("up", B * 4 * Hl * Wl, Ch)
+                self.conv3x3(xlow, Cl, upname + ".body.0.weight", u, Ch, B, Hl, Wl, 2 * Cl, capi.STORE_SHUFFLE2)
+                d = ws.get(outname, B * 4 * Hl * Wl, Ch)
+                self.gemm([(_ptr(u), Ch), (_ptr(skip), Ch)], Ch, self._w(redname + ".weight"), _ptr(d), Ch,
+                          B * 4 * Hl * Wl, Ch, bias=self._w(redname + ".bias"))
+                return d
+
+            d3 = up_merge(x4, H4, W4, dim * 8, "up4_3", e3, "reduce_chan_level3", "d3")
+            kc, vc = self.level("decoder_level3", d3, B, H3, W3, k_cached[5], v_cached[5]); ks.append(kc); vs.append(vc)
+            d2 = up_merge(d3, H3, W3, dim * 4, "up3_2", e2, "reduce_chan_level2", "d2")
+            kc, vc = self.level("decoder_level2", d2, B, H2, W2, k_cached[6], v_cached[6]); ks.append(kc); vs.append(vc)
+            d1 = up_merge(d2, H2, W2, dim * 2, "up2_1", e1, "reduce_chan_level1", "d1")
+            kc, vc = self.level("decoder_level1", d1, B, Hp, Wp, k_cached[7], v_cached[7]); ks.append(kc); vs.append(vc)
+            self.level("refinement", d1, B, Hp, Wp)
+
+            out = torch.empty(B, m.out_channels, H, W, device=inp.device, dtype=torch.float32)
+            self._call("turtle_conv3x3_last", _ptr(d1), _ptr(self._w("ending.weight")), _ptr(self._w("ending.bias")),
+                 _ptr(img), Ci, Ci - Cc, _ptr(out), B, Hp, Wp, dim, m.out_channels, H, W, self.stream)
+        if self.trace is not None:
+            self.last_trace = self.trace
+        return out, ks, vs

@@ -1,0 +1,158 @@
+"""HBM-resident history rings for the five history-carrying blocks.
+
+The reference threads its history through the caller as tensors that are ``torch.cat``-ed and
+sliced every frame (T1:272-273,286; T1:581-582,610) -- the whole history is re-copied per frame.
+Here each history lives in a device buffer with ``M`` frame slots; a new frame is written into
+the next slot by the producing kernel itself, and the tensors handed back to the caller are
+*views* of the buffer in exactly the reference shapes:
+
+  SAB caches  k [B, Fc, 1, N, 2c]      v [B, Fc, 1, N, ws*ws*c]        (T1:610)
+  FHR caches  k [B, head, Fc*c/head, hw]   v likewise                   (T1:286)
+
+The window slides through the buffer; when it reaches the end, the (<=K) live frames are moved to
+the front once (amortised cost 1/(M-K) frame copies per frame).  A tensor passed back by the
+caller is recognised as "our current window" by its storage pointer, offset, shape and strides;
+anything else (``.cpu().to(device)`` round trips of the tiled loop INF:227-237, clones, slices) is
+imported by copy into a fresh ring, so the list API stays fully general.
+
+Caveat (documented in DESIGN.md): a window view handed out earlier aliases ring memory and goes
+stale once the ring compacts; callers that need to keep an old history must ``.clone()`` it.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional, Tuple
+
+import torch
+
+RING_SLOTS = int(os.environ.get("TURTLE_RING_SLOTS", "8"))
+
+
+class _RingBase:
+    def __init__(self, keep: int, slots: int):
+        self.keep = keep                     # K = num_frames_tocache of the owning block
+        self.slots = max(slots, 2 * keep + 2)
+        self.pos = -1                        # newest committed slot
+        self.count = 0                       # committed frames in the window (<= keep)
+        # signature of the window last handed out (no tensor refs: the views own the ring, not
+        # the other way round, so dropping the caches frees the ring without a GC cycle)
+        self._sig = None
+
+    # -- protocol ---------------------------------------------------------------------
+    def begin_push(self) -> int:
+        """Slot the producing kernels must write the new frame into (compacts first if needed)."""
+        if self.pos + 1 >= self.slots:
+            self._compact()
+        return self.pos + 1
+
+    def commit(self) -> None:
+        self.pos += 1
+        self.count = min(self.count + 1, self.keep)
+
+    @property
+    def first_live(self) -> int:
+        """Oldest slot that takes part in the current frame's attention (before commit)."""
+        return self.pos - self.count + 1
+
+    def matches(self, k: torch.Tensor, v: torch.Tensor) -> bool:
+        return self._sig is not None and self._sig == (_sig(k), _sig(v))
+
+    def _publish(self, k: torch.Tensor, v: torch.Tensor):
+        k._turtle_ring = v._turtle_ring = self
+        self._sig = (_sig(k), _sig(v))
+        return k, v
+
+
+def _sig(t: torch.Tensor):
+    return (t.device, t.dtype, t.data_ptr(), tuple(t.shape), tuple(t.stride()))
+
+
+class SabRing(_RingBase):
+    """History of a StateAlignBlock: k rows [N,Dk] and v patch rows [N,Dv] per frame."""
+
+    def __init__(self, B, N, Dk, Dv, keep, device, slots=RING_SLOTS):
+        super().__init__(keep, slots)
+        self.B, self.N, self.Dk, self.Dv = B, N, Dk, Dv
+        self.kbuf = torch.empty(B, self.slots, N, Dk, device=device, dtype=torch.float32)
+        self.vbuf = torch.empty(B, self.slots, N, Dv, device=device, dtype=torch.float32)
+
+    def _compact(self):
+        c, a = self.count, self.first_live
+        if c:
+            self.kbuf[:, :c].copy_(self.kbuf[:, a:a + c])
+            self.vbuf[:, :c].copy_(self.vbuf[:, a:a + c])
+        self.pos = c - 1
+
+    def views(self):
+        a, b = self.first_live, self.pos + 1
+        k = self.kbuf[:, a:b].unsqueeze(2)
+        v = self.vbuf[:, a:b].unsqueeze(2)
+        return self._publish(k, v)
+
+    @classmethod
+    def adopt(cls, k: torch.Tensor, v: torch.Tensor, keep: int, device):
+        """Import caller-owned cache tensors [B,Fc,1,N,D*] by copy."""
+        B, Fc, _, N, Dk = k.shape
+        Dv = v.shape[-1]
+        r = cls(B, N, Dk, Dv, keep, device)
+        Fc = min(Fc, keep)
+        r.kbuf[:, :Fc].copy_(k[:, -Fc:, 0].to(device=device, dtype=torch.float32))
+        r.vbuf[:, :Fc].copy_(v[:, -Fc:, 0].to(device=device, dtype=torch.float32))
+        r.pos, r.count = Fc - 1, Fc
+        return r
+
+
+class FhrRing(_RingBase):
+    """History of a FrameHistoryRouter: per frame, normalised key rows and raw value rows, each a
+    channels-last map [P, C].  Stored as [B, P, heads, M*ch] so that the reference-shaped window
+    [B, heads, Fc*ch, P] is a plain strided view (frames are contiguous inside a head)."""
+
+    def __init__(self, B, P, heads, ch, keep, device, slots=RING_SLOTS):
+        super().__init__(keep, slots)
+        self.B, self.P, self.heads, self.ch = B, P, heads, ch
+        self.kbuf = torch.empty(B, P, heads, self.slots * ch, device=device, dtype=torch.float32)
+        self.vbuf = torch.empty(B, P, heads, self.slots * ch, device=device, dtype=torch.float32)
+
+    @property
+    def ld(self) -> int:                     # row pitch of one pixel
+        return self.heads * self.slots * self.ch
+
+    @property
+    def head_stride(self) -> int:
+        return self.slots * self.ch
+
+    def _compact(self):
+        c, a, ch = self.count, self.first_live, self.ch
+        if c:
+            self.kbuf[..., :c * ch].copy_(self.kbuf[..., a * ch:(a + c) * ch].clone())
+            self.vbuf[..., :c * ch].copy_(self.vbuf[..., a * ch:(a + c) * ch].clone())
+        self.pos = c - 1
+
+    def slot_ptr(self, buf: torch.Tensor, b: int, slot: int) -> int:
+        return buf.data_ptr() + 4 * (b * self.P * self.ld + slot * self.ch)
+
+    def views(self):
+        a, b, ch = self.first_live, self.pos + 1, self.ch
+        k = self.kbuf[..., a * ch:b * ch].permute(0, 2, 3, 1)
+        v = self.vbuf[..., a * ch:b * ch].permute(0, 2, 3, 1)
+        return self._publish(k, v)
+
+    @classmethod
+    def adopt(cls, k: torch.Tensor, v: torch.Tensor, keep: int, ch: int, device):
+        B, heads, rows, P = k.shape
+        r = cls(B, P, heads, ch, keep, device)
+        Fc = min(rows // ch, keep)
+        r.kbuf[..., :Fc * ch].copy_(k[:, :, -Fc * ch:].permute(0, 3, 1, 2).to(device=device, dtype=torch.float32))
+        r.vbuf[..., :Fc * ch].copy_(v[:, :, -Fc * ch:].permute(0, 3, 1, 2).to(device=device, dtype=torch.float32))
+        r.pos, r.count = Fc - 1, Fc
+        return r
+
+
+def resolve_ring(k, v):
+    """Ring behind caller-supplied cache tensors if they are exactly its current window."""
+    if k is None or v is None:
+        return None
+    ring = getattr(k, "_turtle_ring", None)
+    if ring is not None and ring is getattr(v, "_turtle_ring", None) and ring.matches(k, v):
+        return ring
+    return None
