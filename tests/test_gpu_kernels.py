@@ -13,6 +13,7 @@ from turtlevsr_b200.capi import call  # noqa: E402
 from gpu_util import dp, gemm, nchw, nhwc, stream  # noqa: E402
 
 TOL = 2e-5
+TF32_REL = 3e-3      # tcgen05 kind::tf32 keeps 10 mantissa bits of each operand (K up to 512 here)
 
 
 def rnd(*s, seed=0):
@@ -43,7 +44,7 @@ def test_gemm_epilogue(Cin, Cout, P, mode):
     gemm([(A, 0, Cin)], Cin, Wt, P, Cout, mode=mode, bias=bias, scale=scale, act=capi.ACT_GELU, res=res, out=out,
          ldo=Cout)
     want = F.gelu(A.cpu() @ Wt.cpu().t() + bias.cpu()) * scale.cpu() + res.cpu()
-    tol = TOL if mode == capi.FP32 else 3e-3
+    tol = TOL if mode == capi.FP32 else TF32_REL * want.abs().max()
     assert (out.cpu() - want).abs().max() < tol
 
 
@@ -55,7 +56,7 @@ def test_gemm_segments_inplace_residual(mode):
     x = rnd(P, 128, seed=10).cuda()
     want = x.cpu() + torch.cat([b.cpu()[:, ch:2 * ch] for b in bufs], 1) @ Wt.cpu().t()
     gemm([(b, ch, 3 * ch) for b in bufs], ch, Wt, P, 128, mode=mode, res=x, out=x, ldo=128)
-    tol = TOL if mode == capi.FP32 else 3e-3
+    tol = TOL if mode == capi.FP32 else TF32_REL * want.abs().max()
     assert (x.cpu() - want).abs().max() < tol
 
 
@@ -78,7 +79,7 @@ def test_conv3x3_im2col(store, mode):
     wp = w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous().cuda()
     gemm([(nhwc(x), 0, Cin)], Cin, wp, B * H * W, Cout, mode=mode, im2col=1, geom=(B, H, W), store=store, out=out,
          ldo=Co)
-    tol = TOL if mode == capi.FP32 else 3e-3
+    tol = TOL if mode == capi.FP32 else TF32_REL * want.abs().max()
     assert (nchw(out) - want).abs().max() < tol
 
 

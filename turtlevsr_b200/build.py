@@ -72,7 +72,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 with open(os.path.join(OBJDIR, os.path.basename(src)[:-3] + ".ptxas.txt"), "w") as f:
                     f.write(r.stderr)
     if jobs or not os.path.exists(LIB) or force:
-        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-lcuda"]
+        cmd = [nvcc, "-shared", "-o", LIB, *objs]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

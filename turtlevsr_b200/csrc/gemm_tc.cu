@@ -1,3 +1,450 @@
-// placeholder until the tcgen05 kernel lands: every shape reports "not supported"
+// Tensor-core contraction for sm_100a:  out[p,o] = epi( sum_k A(p,k) W[o,k] )
+//
+//   tcgen05.mma kind::tf32, cta_group::1, M = 128 pixels (TMEM lanes) x N <= 256 output channels
+//   (TMEM columns), fp32 accumulate in TMEM.  Operands are fp32 in HBM (channels-last activations
+//   are K-major for A, [Cout,K] weights are K-major for B) and are staged by TMA
+//   (cp.async.bulk.tensor, 128B swizzle) into a multi-stage shared-memory ring guarded by mbarriers;
+//   one elected thread issues the MMAs, tcgen05.commit releases stages / publishes the accumulator,
+//   and all four warps run the epilogue (tcgen05.ld 32x32b -> bias/GELU/scale/residual -> stores).
+//   Two CTAs fit per SM (<=256 TMEM columns and ~100 KB smem each), so one CTA's epilogue overlaps
+//   the other's main loop.
+//
+//   Grid = (n-groups, pixel tiles): CTAs that share an A tile are adjacent so the re-read hits L2.
+//   K is walked in 32-float (128 B) blocks: 4 MMAs of K=8 per block, descriptor start address
+//   advanced by 32 B inside the swizzle atom.
+//
+//   im2col mode (dense 3x3 convs): the pixel tile is a BHxBW patch of one image and each of the 9
+//   taps is one TMA box of a 4-D tensor map shifted by (dy,dx); out-of-bounds elements are
+//   zero-filled by the TMA unit, which is exactly the conv's zero padding.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
-int turtle_gemm_tc(const TurtleGemmArgs *, void *) { return TURTLE_ENOTSUP; }
+
+namespace {
+
+constexpr int TM = 128;        // pixels per tile (UMMA M)
+constexpr int TK = 32;         // floats per k-block (128 B swizzle atom)
+constexpr int MAX_TC_SEG = 8;
+constexpr int A_STAGE_BYTES = TM * TK * 4;   // 16 KB
+
+struct alignas(64) TcParams {
+    CUtensorMap mapA[MAX_TC_SEG];
+    CUtensorMap mapW;
+    int nseg, kb_per_seg;      // k-blocks per segment (im2col: per tap, nseg = 9)
+    int nkb;                   // total k-blocks
+    int im2col, BW, BH;        // im2col pixel-patch geometry (BW*BH = 128)
+    int B, H, W;
+    int tiles_x, tiles_y;      // im2col: patches per image
+    long long P;
+    int Cout, NG, ngroups;     // NG = columns per n-group (uniform, divides Cout)
+    int stages;
+    const float *bias, *scale, *res;
+    int act, ldres;
+    float *out;
+    int ldo, store;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, int c3,
+                                            uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+            "r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, version 1):
+//   start address >>4 | LBO (ignored for swizzled K-major, canonical value 1) | SBO = 1024 B between
+//   8-row groups | layout_type 2 = SWIZZLE_128B
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+template <int TMEM_COLS>
+__global__ void __launch_bounds__(128) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], accum_bar;
+    __shared__ uint32_t tmem_base_sh;
+
+    // dynamic smem is only guaranteed 16 B aligned: round up to the 1024 B the 128B swizzle needs
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ng = blockIdx.x % p.ngroups;           // n-group (fastest: CTAs sharing an A tile are adjacent)
+    const int tile = blockIdx.x / p.ngroups;
+    const int n0 = ng * p.NG;
+    const int N = min(p.NG, p.Cout - n0);            // multiple of 16
+    const uint32_t b_stage_bytes = (uint32_t)p.NG * TK * 4;
+    const uint32_t stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+
+    // tile origin
+    long long m0 = 0;
+    int tb = 0, ty0 = 0, tx0 = 0;
+    if (p.im2col) {
+        int t = tile;
+        tx0 = (t % p.tiles_x) * p.BW;
+        ty0 = ((t / p.tiles_x) % p.tiles_y) * p.BH;
+        tb = t / (p.tiles_x * p.tiles_y);
+    } else {
+        m0 = (long long)tile * TM;
+    }
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        mbar_init(smem_u32(&accum_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)),
+                     "n"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_sh;
+
+    if (warp == 0 && lane == 0) {
+        // ------------------------------ TMA producer ------------------------------
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            const uint32_t sa = smem0 + stage * stage_bytes;
+            const uint32_t sb = sa + A_STAGE_BYTES;
+            mbar_expect_tx(fb, A_STAGE_BYTES + (uint32_t)N * TK * 4);
+            const int seg = kb / p.kb_per_seg, kk = (kb - seg * p.kb_per_seg) * TK;
+            if (p.im2col) {
+                const int dy = seg / 3 - 1, dx = seg % 3 - 1;
+                tma_load_4d(sa, &p.mapA[0], kk, tx0 + dx, ty0 + dy, tb, fb);
+            } else {
+                tma_load_2d(sa, &p.mapA[seg], kk, (int)m0, fb);
+            }
+            // weights: N rows of this n-group; boxes of <=256 rows
+            tma_load_2d(sb, &p.mapW, kb * TK, n0, fb);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ------------------------------ MMA issuer ------------------------------
+        // instruction descriptor: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), both K-major, N>>3 @17, M>>4 @24
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = 0; kb < p.nkb; ++kb) {
+            mbar_wait(smem_u32(&full_bar[stage]), phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = smem0 + stage * stage_bytes;
+            const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+            for (int k = 0; k < TK / 8; ++k) {
+                umma_tf32(tmem_base, make_desc(sa + k * 32), make_desc(sb + k * 32), idesc, (kb | k) ? 1u : 0u);
+            }
+            umma_commit(smem_u32(&empty_bar[stage]));       // frees the stage once these MMAs retire
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(&accum_bar));                   // accumulator complete
+    }
+    __syncwarp();
+
+    // ------------------------------ epilogue (all 4 warps) ------------------------------
+    mbar_wait(smem_u32(&accum_bar), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = warp * 32 + lane;                // TMEM lane == pixel within the tile
+    long long pix;                                   // linear pixel index into [B,H,W]
+    bool live;
+    int py = 0, px = 0;
+    if (p.im2col) {
+        py = ty0 + row / p.BW;
+        px = tx0 + row % p.BW;
+        live = py < p.H && px < p.W;
+        pix = ((long long)tb * p.H + py) * p.W + px;
+    } else {
+        pix = m0 + row;
+        live = pix < p.P;
+    }
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        float v[16];
+        __syncwarp();                                // tcgen05.ld is warp-collective (.sync.aligned)
+        tmem_ld16(trow + c0, v);
+        const int o0 = n0 + c0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (!live) break;
+            float4 t = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            const int o = o0 + 4 * q;
+            if (p.bias) {
+                float4 b = __ldg(reinterpret_cast<const float4 *>(p.bias + o));
+                t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
+            }
+            if (p.act == TURTLE_ACT_GELU) {
+                t.x = gelu_erf(t.x); t.y = gelu_erf(t.y); t.z = gelu_erf(t.z); t.w = gelu_erf(t.w);
+            }
+            if (p.scale) {
+                float4 s = __ldg(reinterpret_cast<const float4 *>(p.scale + o));
+                t.x *= s.x; t.y *= s.y; t.z *= s.z; t.w *= s.w;
+            }
+            if (p.res) {
+                float4 r = *reinterpret_cast<const float4 *>(p.res + pix * p.ldres + o);
+                t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
+            }
+            if (p.store == TURTLE_STORE_PLAIN) {
+                *reinterpret_cast<float4 *>(p.out + pix * p.ldo + o) = t;
+            } else if (p.store == TURTLE_STORE_UNSHUFFLE2) {
+                const int Ho = p.H >> 1, Wo = p.W >> 1;
+                float *op = p.out + (((long long)tb * Ho + (py >> 1)) * Wo + (px >> 1)) * p.ldo + ((py & 1) * 2 + (px & 1));
+                op[(o + 0) * 4] = t.x; op[(o + 1) * 4] = t.y; op[(o + 2) * 4] = t.z; op[(o + 3) * 4] = t.w;
+            } else {
+                const int Wo = p.W << 1;
+                float *op = p.out + (((long long)tb * (p.H << 1) + 2 * py) * Wo + 2 * px) * p.ldo + (o >> 2);
+                op[0] = t.x;
+                op[p.ldo] = t.y;
+                op[(long long)Wo * p.ldo] = t.z;
+                op[(long long)Wo * p.ldo + p.ldo] = t.w;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor-map cache + launch
+// ---------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled get_encode() {
+    static PFN_cuTensorMapEncodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(f);
+    });
+    return fn;
+}
+
+struct MapKey {
+    const void *ptr;
+    uint64_t d0, d1, d2, d3, s1, s2, s3;
+    uint32_t b0, b1, b2, b3, rank;
+    bool operator==(const MapKey &o) const {
+        return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && d3 == o.d3 && s1 == o.s1 && s2 == o.s2 &&
+               s3 == o.s3 && b0 == o.b0 && b1 == o.b1 && b2 == o.b2 && b3 == o.b3 && rank == o.rank;
+    }
+};
+struct MapKeyHash {
+    size_t operator()(const MapKey &k) const {
+        uint64_t h = (uint64_t)(uintptr_t)k.ptr * 0x9E3779B97F4A7C15ull;
+        auto mix = [&](uint64_t v) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); };
+        mix(k.d0); mix(k.d1); mix(k.d2); mix(k.d3); mix(k.s1); mix(k.s2); mix(k.s3);
+        mix(((uint64_t)k.b0 << 32) | k.b1); mix(((uint64_t)k.b2 << 32) | k.b3); mix(k.rank);
+        return (size_t)h;
+    }
+};
+
+std::mutex g_map_mu;
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// dims / strides innermost first; strides in bytes for dims 1..rank-1
+bool get_map(CUtensorMap *out, const void *ptr, int rank, const uint64_t *dims, const uint64_t *strides,
+             const uint32_t *box) {
+    MapKey k{};
+    k.ptr = ptr;
+    k.rank = (uint32_t)rank;
+    k.d0 = dims[0]; k.d1 = dims[1]; k.d2 = rank > 2 ? dims[2] : 0; k.d3 = rank > 3 ? dims[3] : 0;
+    k.s1 = strides[0]; k.s2 = rank > 2 ? strides[1] : 0; k.s3 = rank > 3 ? strides[2] : 0;
+    k.b0 = box[0]; k.b1 = box[1]; k.b2 = rank > 2 ? box[2] : 0; k.b3 = rank > 3 ? box[3] : 0;
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    auto it = g_maps.find(k);
+    if (it != g_maps.end()) {
+        *out = it->second;
+        return true;
+    }
+    PFN_cuTensorMapEncodeTiled enc = get_encode();
+    if (!enc) return false;
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUtensorMap m;
+    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(ptr),
+                     reinterpret_cast<const cuuint64_t *>(dims), reinterpret_cast<const cuuint64_t *>(strides),
+                     reinterpret_cast<const cuuint32_t *>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    if (g_maps.size() > 65536) g_maps.clear();
+    g_maps.emplace(k, m);
+    *out = m;
+    return true;
+}
+
+template <int COLS>
+int launch(const TcParams &p, dim3 grid, size_t smem, cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        if (cudaFuncSetAttribute(gemm_tc_kernel<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) !=
+            cudaSuccess)
+            return TURTLE_ELAUNCH;
+        configured = true;
+    }
+    gemm_tc_kernel<COLS><<<grid, 128, smem, s>>>(p);
+    return cudaGetLastError() == cudaSuccess ? TURTLE_OK : TURTLE_ELAUNCH;
+}
+
+}  // namespace
+
+int turtle_gemm_tc(const TurtleGemmArgs *a, void *stream) {
+    const int Cout = a->Cout;
+    if (Cout % 16 || Cout < 16) return TURTLE_ENOTSUP;
+    if (a->segw % TK) return TURTLE_ENOTSUP;
+    if (((uintptr_t)a->Wt & 15) || ((uintptr_t)a->out & 15)) return TURTLE_ENOTSUP;
+
+    TcParams p{};
+    p.P = a->P;
+    p.Cout = Cout;
+    p.bias = a->bias; p.scale = a->scale; p.res = a->res;
+    p.act = a->act; p.ldres = a->ldres;
+    p.out = a->out; p.ldo = a->ldo; p.store = a->store;
+    p.B = a->B; p.H = a->H; p.W = a->W;
+    p.im2col = a->im2col;
+
+    // uniform n-groups: the largest multiple of 16 that is <= 256 and divides Cout
+    int NG = 256;
+    while (NG >= 16 && Cout % NG) NG -= 16;
+    if (NG < 16) return TURTLE_ENOTSUP;
+    const int ngroups = Cout / NG;
+    p.NG = NG;
+    p.ngroups = ngroups;
+    const int K = a->im2col ? 9 * a->segw : a->nseg * a->segw;
+
+    dim3 grid;
+    if (a->im2col) {
+        if (a->lda[0] != a->segw) return TURTLE_ENOTSUP;          // dense [B,H,W,Cin] only
+        int BW = 32;
+        while (BW > 1 && (a->W % BW)) BW >>= 1;
+        if (BW < 4) return TURTLE_ENOTSUP;
+        p.BW = BW; p.BH = TM / BW;
+        p.tiles_x = a->W / BW;
+        p.tiles_y = (a->H + p.BH - 1) / p.BH;
+        p.nseg = 9;
+        p.kb_per_seg = a->segw / TK;
+        uint64_t dims[4] = {(uint64_t)a->segw, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->B};
+        uint64_t str[3] = {(uint64_t)a->segw * 4, (uint64_t)a->segw * 4 * a->W, (uint64_t)a->segw * 4 * a->W * a->H};
+        uint32_t box[4] = {TK, (uint32_t)BW, (uint32_t)p.BH, 1};
+        if (!get_map(&p.mapA[0], a->A[0], 4, dims, str, box)) return TURTLE_ENOTSUP;
+        grid = dim3((unsigned)((long long)ngroups * p.tiles_x * p.tiles_y * a->B));
+    } else {
+        // merge adjacent segments that are contiguous column blocks of one matrix (e.g. per-head slices)
+        const float *ptr[TURTLE_MAX_SEG];
+        int lda[TURTLE_MAX_SEG];
+        int n = a->nseg, w = a->segw;
+        for (int i = 0; i < n; ++i) { ptr[i] = a->A[i]; lda[i] = a->lda[i]; }
+        for (int g = n; g >= 2; --g) {            // largest uniform group size that merges everywhere
+            if (n % g) continue;
+            bool ok = true;
+            for (int i = 0; i < n && ok; i += g)
+                for (int j = 1; j < g && ok; ++j)
+                    ok = ptr[i + j] == ptr[i] + (size_t)j * w && lda[i + j] == lda[i];
+            if (ok) {
+                for (int i = 0; i < n / g; ++i) { ptr[i] = ptr[i * g]; lda[i] = lda[i * g]; }
+                n /= g; w *= g;
+                break;
+            }
+        }
+        if (n > MAX_TC_SEG) return TURTLE_ENOTSUP;
+        p.nseg = n;
+        p.kb_per_seg = w / TK;
+        for (int i = 0; i < n; ++i) {
+            uint64_t dims[2] = {(uint64_t)w, (uint64_t)a->P};
+            uint64_t str[1] = {(uint64_t)lda[i] * 4};
+            uint32_t box[2] = {TK, TM};
+            if (!get_map(&p.mapA[i], ptr[i], 2, dims, str, box)) return TURTLE_ENOTSUP;
+        }
+        grid = dim3((unsigned)((long long)ngroups * ((a->P + TM - 1) / TM)));
+    }
+    p.nkb = K / TK;
+    {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)Cout};
+        uint64_t str[1] = {(uint64_t)K * 4};
+        uint32_t box[2] = {TK, (uint32_t)p.NG};
+        if (!get_map(&p.mapW, a->Wt, 2, dims, str, box)) return TURTLE_ENOTSUP;
+    }
+    const size_t stage_bytes = A_STAGE_BYTES + (size_t)p.NG * TK * 4;
+    int stages = (int)((100 * 1024) / stage_bytes);
+    if (stages > 6) stages = 6;
+    if (stages > p.nkb) stages = p.nkb;
+    if (stages < 1) return TURTLE_ENOTSUP;
+    p.stages = stages;
+    const size_t smem = stages * stage_bytes + 1024;
+    cudaStream_t s = as_stream(stream);
+    if (p.NG <= 32) return launch<32>(p, grid, smem, s);
+    if (p.NG <= 64) return launch<64>(p, grid, smem, s);
+    if (p.NG <= 128) return launch<128>(p, grid, smem, s);
+    return launch<256>(p, grid, smem, s);
+}

@@ -63,11 +63,39 @@ class FrameEngine:
         if not self.dry_run:
             capi.load()                              # fail loudly now if the CUDA library is unavailable
 
+        # per-kernel device timing (bench roofline leg): name -> [ms, launches, alg. bytes, flops]
+        self.profile: Optional[dict] = None
+        self._meta = (0, 0)
+
     def _call(self, name, *args):
         if self.dry_run:
             self.launch_log.append(name)
             return
+        if self.profile is None:
+            call(name, *args)
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
         call(name, *args)
+        e1.record()
+        self.profile.setdefault("_events", []).append((name, e0, e1, self._meta))
+        self._meta = (0, 0)
+
+    def profile_begin(self):
+        self.profile = {}
+
+    def profile_end(self) -> dict:
+        """-> {kernel: dict(ms, launches, bytes, flops)} summed over the profiled frames."""
+        torch.cuda.synchronize()
+        out: Dict[str, dict] = {}
+        for name, e0, e1, (by, fl) in self.profile.get("_events", []):
+            d = out.setdefault(name, dict(ms=0.0, launches=0, bytes=0, flops=0))
+            d["ms"] += e0.elapsed_time(e1)
+            d["launches"] += 1
+            d["bytes"] += by
+            d["flops"] += fl
+        self.profile = None
+        return out
 
     def invalidate(self):
         self.packed.clear()
@@ -133,18 +161,40 @@ class FrameEngine:
         a.out = out
         a.ldo = ldo
         a.store = store
-        self._call("turtle_gemm", C.byref(a), self.stream)
+        if self.profile is not None:
+            K = (9 if im2col else len(segs)) * segw
+            self._meta = (4 * (P * K + Cout * K + P * Cout * (2 if res else 1)), 2 * P * K * Cout)
+        name = "turtle_gemm"
+        if self.profile is not None:
+            name = "turtle_gemm[conv3x3]" if im2col else "turtle_gemm[1x1]"
+        self._call_gemm(name, a)
+
+    def _call_gemm(self, tag, a):
+        if self.dry_run:
+            self.launch_log.append("turtle_gemm")
+            return
+        if self.profile is None:
+            call("turtle_gemm", C.byref(a), self.stream)
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        call("turtle_gemm", C.byref(a), self.stream)
+        e1.record()
+        self.profile.setdefault("_events", []).append((tag, e0, e1, self._meta))
+        self._meta = (0, 0)
 
     def conv1x1(self, x, ldx, Cin, wname, out, ldo, P, Cout, **kw):
         self.gemm([(x, ldx)], Cin, self._w(wname), out, ldo, P, Cout, **kw)
 
     def layernorm(self, x: torch.Tensor, pre: str, C_: int, P: int) -> torch.Tensor:
         y = self.ws.get("xn", P, C_)
+        self._meta = (8 * P * C_, 0)
         self._call("turtle_layernorm", _ptr(x), C_, _ptr(self._w(pre + "body.weight")), _ptr(self._w(pre + "body.bias")),
              _ptr(y), C_, P, C_, self.stream)
         return y
 
     def dwconv(self, x, ldx, wname, bname, y, ldy, NB, H, W, Cc, fuse=0, layout=0, ws=1, wkind="dw"):
+        self._meta = (4 * NB * H * W * (Cc + (Cc // 2 if fuse == 2 else Cc)), 2 * 9 * NB * H * W * Cc)
         self._call("turtle_dwconv3x3", x, ldx, _ptr(self._w(wname, wkind)), _ptr(self._w(bname)) if bname else None, y, ldy,
              NB, H, W, Cc, fuse, layout, ws, self.stream)
 
@@ -209,6 +259,7 @@ class FrameEngine:
             sqq = self.ws.get("sqq", S, nsplit, c)
             sqk = self.ws.get("sqk", S, nsplit, c)
             for s, sg in enumerate(segs):
+                self._meta = (8 * Pimg * c, 2 * Pimg * c * ch)
                 self._call("turtle_chan_gram", _ptr(qd, base), 3 * c, ch, sg["k"], sg["ldk"], sg["khs"], Pimg, heads, ch,
                      nsplit, _ptr(gpart[s]), _ptr(sqq[s]), _ptr(sqk[s]), self.mode, self.stream)
             flags = self._flags([1 if sg["prenorm"] else 0 for sg in segs])
@@ -322,8 +373,10 @@ class FrameEngine:
             kf = _ptr(ring.kbuf[b, first])
             vf = _ptr(ring.vbuf[b, first])
             if not t0:
+                self._meta = (4 * (N * Dk * (F_ + 1) + 2 * F_ * N * capi.SAB_SLOTS), 2 * F_ * N * N * Dk)
                 self._call("turtle_sab_select", _ptr(qn[b]), kf, N * Dk, F_, Hg, Wg, Dk, _ptr(temp), 0, _ptr(idx[b]),
                      _ptr(wgt[b]), self.mode, self.stream)
+            self._meta = (4 * (2 * F_ * N * Dv + 2 * F_ * N * capi.SAB_SLOTS), 2 * F_ * N * 46 * Dv)
             self._call("turtle_sab_aggregate", _ptr(idx[b]), _ptr(wgt[b]), vf, N * Dv, _ptr(agg[b]), F_, Hg, Wg, ws_, c,
                  1 if t0 else 0, self.stream)
         if self.trace is not None:
