@@ -34,6 +34,8 @@ constexpr int A_STAGE_BYTES = TM * TK * 4;   // 16 KB
 struct alignas(64) TcParams {
     CUtensorMap mapA[MAX_TC_SEG];
     CUtensorMap mapW;
+    CUtensorMap mapOut, mapRes;   // TMA epilogue (plain stores): [P, Cout] boxes of 128 rows x 32 columns
+    int tma_epi;
     int nseg, kb_per_seg;      // k-blocks per segment (im2col: per tap, nseg = 9)
     int nkb;                   // total k-blocks
     int im2col, BW, BH;        // im2col pixel-patch geometry (BW*BH = 128)
@@ -121,10 +123,31 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
+
 template <int TMEM_COLS>
 __global__ void __launch_bounds__(128) gemm_tc_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], accum_bar;
+    __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], accum_bar, res_bar[2];
     __shared__ uint32_t tmem_base_sh;
 
     // dynamic smem is only guaranteed 16 B aligned: round up to the 1024 B the 128B swizzle needs
@@ -155,6 +178,8 @@ __global__ void __launch_bounds__(128) gemm_tc_kernel(const __grid_constant__ Tc
             mbar_init(smem_u32(&empty_bar[s]), 1);
         }
         mbar_init(smem_u32(&accum_bar), 1);
+        mbar_init(smem_u32(&res_bar[0]), 1);
+        mbar_init(smem_u32(&res_bar[1]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -228,6 +253,62 @@ __global__ void __launch_bounds__(128) gemm_tc_kernel(const __grid_constant__ Tc
         live = pix < p.P;
     }
     const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    if (p.tma_epi) {
+        // Coalesced epilogue: 128x32 chunks go through the (now idle) pipeline smem in the 128B-swizzled
+        // layout and leave with one TMA store each; the residual chunk arrives the same way.
+        for (int j = 0; j < N / 32; ++j) {
+            const int b = j & 1;
+            const uint32_t buf = smem0 + b * (TM * 128);
+            const uint32_t rb = smem_u32(&res_bar[b]);
+            if (threadIdx.x == 0) {
+                if (j >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // store j-2 drained buf
+                if (p.res) {
+                    mbar_expect_tx(rb, TM * 128);
+                    tma_load_2d(buf, &p.mapRes, n0 + j * 32, (int)m0, rb);
+                }
+            }
+            __syncthreads();
+            float v[32];
+            tmem_ld32(trow + j * 32, v);
+            const int o0 = n0 + j * 32;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int o = o0 + 4 * q;
+                if (p.bias) {
+                    float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + o));
+                    v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
+                }
+                if (p.act == TURTLE_ACT_GELU) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) v[4 * q + e] = gelu_erf(v[4 * q + e]);
+                }
+                if (p.scale) {
+                    float4 sc = __ldg(reinterpret_cast<const float4 *>(p.scale + o));
+                    v[4 * q] *= sc.x; v[4 * q + 1] *= sc.y; v[4 * q + 2] *= sc.z; v[4 * q + 3] *= sc.w;
+                }
+            }
+            if (p.res) mbar_wait(rb, (j >> 1) & 1);
+            const uint32_t rowaddr = buf + row * 128;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const uint32_t addr = rowaddr + (((uint32_t)q ^ ((uint32_t)row & 7u)) << 4);
+                float4 t = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                if (p.res) {
+                    float4 r;
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+                    t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
+                }
+                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                tma_store_2d(&p.mapOut, buf, n0 + j * 32, (int)m0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        }
+        if (threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    } else
     for (int c0 = 0; c0 < N; c0 += 16) {
         float v[16];
         __syncwarp();                                // tcgen05.ld is warp-collective (.sync.aligned)
@@ -295,9 +376,9 @@ PFN_cuTensorMapEncodeTiled get_encode() {
 struct MapKey {
     const void *ptr;
     uint64_t d0, d1, d2, d3, s1, s2, s3;
-    uint32_t b0, b1, b2, b3, rank;
+    uint32_t b0, b1, b2, b3, rank, swz;
     bool operator==(const MapKey &o) const {
-        return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && d3 == o.d3 && s1 == o.s1 && s2 == o.s2 &&
+        return swz == o.swz && ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && d3 == o.d3 && s1 == o.s1 && s2 == o.s2 &&
                s3 == o.s3 && b0 == o.b0 && b1 == o.b1 && b2 == o.b2 && b3 == o.b3 && rank == o.rank;
     }
 };
@@ -306,7 +387,7 @@ struct MapKeyHash {
         uint64_t h = (uint64_t)(uintptr_t)k.ptr * 0x9E3779B97F4A7C15ull;
         auto mix = [&](uint64_t v) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); };
         mix(k.d0); mix(k.d1); mix(k.d2); mix(k.d3); mix(k.s1); mix(k.s2); mix(k.s3);
-        mix(((uint64_t)k.b0 << 32) | k.b1); mix(((uint64_t)k.b2 << 32) | k.b3); mix(k.rank);
+        mix(((uint64_t)k.b0 << 32) | k.b1); mix(((uint64_t)k.b2 << 32) | k.b3); mix(k.rank); mix(k.swz);
         return (size_t)h;
     }
 };
@@ -315,11 +396,14 @@ std::mutex g_map_mu;
 std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
 // dims / strides innermost first; strides in bytes for dims 1..rank-1
-bool get_map(CUtensorMap *out, const void *ptr, int rank, const uint64_t *dims, const uint64_t *strides,
-             const uint32_t *box) {
+}  // namespace
+
+bool turtle_get_tmap(CUtensorMap *out, const void *ptr, int rank, const uint64_t *dims, const uint64_t *strides,
+                     const uint32_t *box, int swizzle128) {
     MapKey k{};
     k.ptr = ptr;
     k.rank = (uint32_t)rank;
+    k.swz = (uint32_t)swizzle128;
     k.d0 = dims[0]; k.d1 = dims[1]; k.d2 = rank > 2 ? dims[2] : 0; k.d3 = rank > 3 ? dims[3] : 0;
     k.s1 = strides[0]; k.s2 = rank > 2 ? strides[1] : 0; k.s3 = rank > 3 ? strides[2] : 0;
     k.b0 = box[0]; k.b1 = box[1]; k.b2 = rank > 2 ? box[2] : 0; k.b3 = rank > 3 ? box[3] : 0;
@@ -336,12 +420,19 @@ bool get_map(CUtensorMap *out, const void *ptr, int rank, const uint64_t *dims, 
     CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(ptr),
                      reinterpret_cast<const cuuint64_t *>(dims), reinterpret_cast<const cuuint64_t *>(strides),
                      reinterpret_cast<const cuuint32_t *>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return false;
     if (g_maps.size() > 65536) g_maps.clear();
     g_maps.emplace(k, m);
     *out = m;
     return true;
+}
+
+namespace {
+inline bool get_map(CUtensorMap *out, const void *ptr, int rank, const uint64_t *dims, const uint64_t *strides,
+                    const uint32_t *box) {
+    return turtle_get_tmap(out, ptr, rank, dims, strides, box, 1);
 }
 
 template <int COLS>
@@ -436,11 +527,24 @@ int turtle_gemm_tc(const TurtleGemmArgs *a, void *stream) {
         if (!get_map(&p.mapW, a->Wt, 2, dims, str, box)) return TURTLE_ENOTSUP;
     }
     const size_t stage_bytes = A_STAGE_BYTES + (size_t)p.NG * TK * 4;
+    p.tma_epi = 0;
     int stages = (int)((100 * 1024) / stage_bytes);
     if (stages > 6) stages = 6;
     if (stages > p.nkb) stages = p.nkb;
     if (stages < 1) return TURTLE_ENOTSUP;
     p.stages = stages;
+    if (!a->im2col && a->store == TURTLE_STORE_PLAIN && p.NG % 32 == 0 && stages * stage_bytes >= 2 * TM * 128 &&
+        !(a->ldo & 3) && (!a->res || (!(a->ldres & 3) && !((uintptr_t)a->res & 15)))) {
+        uint64_t dims[2] = {(uint64_t)Cout, (uint64_t)a->P};
+        uint32_t box[2] = {32, TM};
+        uint64_t so[1] = {(uint64_t)a->ldo * 4};
+        bool ok = get_map(&p.mapOut, a->out, 2, dims, so, box);
+        if (ok && a->res) {
+            uint64_t sr[1] = {(uint64_t)a->ldres * 4};
+            ok = get_map(&p.mapRes, a->res, 2, dims, sr, box);
+        }
+        p.tma_epi = ok ? 1 : 0;
+    }
     const size_t smem = stages * stage_bytes + 1024;
     cudaStream_t s = as_stream(stream);
     if (p.NG <= 32) return launch<32>(p, grid, smem, s);

@@ -241,15 +241,92 @@ __global__ void layernorm_kernel(const float *__restrict__ x, int ldx, const flo
     }
 }
 
+// Vectorised variant: a pixel is owned by G lanes holding NV float4 each (C = 4*NV*G); every lane
+// group keeps U pixels in flight so that enough bytes are outstanding to cover HBM latency.
+template <int NV, int G, int U>
+__global__ void __launch_bounds__(256) layernorm_vec_kernel(const float *__restrict__ x, int ldx,
+                                                            const float *__restrict__ w, const float *__restrict__ b,
+                                                            float *__restrict__ y, int ldy, int64_t P) {
+    constexpr int C = 4 * NV * G;
+    constexpr int GPW = 32 / G;                       // pixel groups per warp
+    const int lane = threadIdx.x & 31, gl = lane % G, gi = lane / G;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t p0 = (warp * GPW + gi) * U;
+    float4 v[U][NV];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int64_t p = p0 + u;
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+            v[u][i] = p < P ? ldg_stream(x + p * ldx + (i * G + gl) * 4) : make_float4(0, 0, 0, 0);
+    }
+    float4 wv[NV], bv[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        wv[i] = __ldg(reinterpret_cast<const float4 *>(w + (i * G + gl) * 4));
+        bv[i] = b ? __ldg(reinterpret_cast<const float4 *>(b + (i * G + gl) * 4)) : make_float4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) s += (v[u][i].x + v[u][i].y) + (v[u][i].z + v[u][i].w);
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mu = s / (float)C;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            float d0 = v[u][i].x - mu, d1 = v[u][i].y - mu, d2 = v[u][i].z - mu, d3 = v[u][i].w - mu;
+            q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); q = fmaf(d2, d2, q); q = fmaf(d3, d3, q);
+        }
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float den = sqrtf(q / (float)C + 1e-5f);
+        const float sub = b ? mu : 0.f;
+        const int64_t p = p0 + u;
+        if (p < P) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                float4 o;
+                o.x = (v[u][i].x - sub) / den * wv[i].x + bv[i].x;
+                o.y = (v[u][i].y - sub) / den * wv[i].y + bv[i].y;
+                o.z = (v[u][i].z - sub) / den * wv[i].z + bv[i].z;
+                o.w = (v[u][i].w - sub) / den * wv[i].w + bv[i].w;
+                *reinterpret_cast<float4 *>(y + p * ldy + (i * G + gl) * 4) = o;
+            }
+        }
+    }
+}
+
+template <int NV, int G, int U>
+static void launch_ln_vec(const float *x, int ldx, const float *w, const float *b, float *y, int ldy, int64_t P,
+                          cudaStream_t s) {
+    const int64_t per_warp = (32 / G) * U;
+    const int64_t warps = cdiv64(P, per_warp);
+    layernorm_vec_kernel<NV, G, U><<<(unsigned)cdiv64(warps, 8), 256, 0, s>>>(x, ldx, w, b, y, ldy, P);
+}
+
 extern "C" int turtle_layernorm(const float *x, int ldx, const float *w, const float *b, float *y, int ldy,
                                 int64_t P, int C, void *stream) {
     if (!x || !w || !y || C < 1 || C > 512 || P < 1) return TURTLE_EINVAL;
+    cudaStream_t s = as_stream(stream);
+    const bool al = (ldx % 4 == 0) && (ldy % 4 == 0) &&
+                    ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)w | (uintptr_t)b) & 15) == 0);
+    if (al && (C == 64 || C == 128 || C == 256 || C == 512)) {
+        if (C == 64) launch_ln_vec<1, 16, 4>(x, ldx, w, b, y, ldy, P, s);
+        else if (C == 128) launch_ln_vec<1, 32, 4>(x, ldx, w, b, y, ldy, P, s);
+        else if (C == 256) launch_ln_vec<2, 32, 4>(x, ldx, w, b, y, ldy, P, s);
+        else launch_ln_vec<4, 32, 2>(x, ldx, w, b, y, ldy, P, s);
+        TURTLE_CHECK_LAUNCH();
+        return TURTLE_OK;
+    }
     unsigned grid = (unsigned)cdiv64(P, 8);
-    bool vec = (C % 128 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && ((((uintptr_t)x | (uintptr_t)y) & 15) == 0);
+    bool vec = (C % 128 == 0) && al;
     if (vec)
-        layernorm_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(x, ldx, w, b, y, ldy, P, C);
+        layernorm_kernel<true><<<grid, 256, 0, s>>>(x, ldx, w, b, y, ldy, P, C);
     else
-        layernorm_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(x, ldx, w, b, y, ldy, P, C);
+        layernorm_kernel<false><<<grid, 256, 0, s>>>(x, ldx, w, b, y, ldy, P, C);
     TURTLE_CHECK_LAUNCH();
     return TURTLE_OK;
 }
@@ -264,54 +341,88 @@ __device__ __forceinline__ void fma4(float4 &a, const float4 &x, const float4 &w
     a.w = fmaf(x.w, w.w, a.w);
 }
 
+// Each thread owns one (x, 4-channel group) column and walks down a strip of RY rows keeping the
+// 3x3 window rows in registers: 3 new float4 loads per output instead of 9, and the x+-1 loads of
+// neighbouring threads hit L1.  L2/HBM sees each input row (RY+2)/RY times.
 template <int FUSE>
-__global__ void dwconv3x3_kernel(const float *__restrict__ x, int ldx, const float *__restrict__ w9,
-                                 const float *__restrict__ bias, float *__restrict__ y, int ldy, int NB, int H,
-                                 int W, int C, int layout, int ws) {
+__global__ void __launch_bounds__(256) dwconv3x3_kernel(const float *__restrict__ x, int ldx,
+                                                        const float *__restrict__ w9,
+                                                        const float *__restrict__ bias, float *__restrict__ y,
+                                                        int ldy, int NB, int H, int W, int C, int layout, int ws,
+                                                        int RY, int nstrips) {
     const int Cout = FUSE == 2 ? (C >> 1) : C;
     const int groups = Cout >> 2;
-    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int64_t total = (int64_t)NB * H * W * groups;
-    if (idx >= total) return;
-    int g = (int)(idx % groups);
-    int64_t p = idx / groups;
-    int px = (int)(p % W), py = (int)((p / W) % H);
-    int64_t nb = p / ((int64_t)W * H);
-    int c0 = g * 4;
-    float4 a = bias ? *reinterpret_cast<const float4 *>(bias + c0) : make_float4(0, 0, 0, 0);
-    float4 a2 = make_float4(0, 0, 0, 0);
-    if (FUSE == 2 && bias) a2 = *reinterpret_cast<const float4 *>(bias + c0 + Cout);
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (int64_t)W * groups) return;
+    const int g = (int)(idx % groups), px = (int)(idx / groups);
+    const int strip = blockIdx.y % nstrips;
+    const int64_t nb = blockIdx.y / nstrips;
+    const int y0 = strip * RY, y1 = min(H, y0 + RY);
+    const int c0 = g * 4;
+    constexpr int NS = FUSE == 2 ? 2 : 1;          // channel sets (gate reads c0 and c0+Cout)
+    float4 wv[NS][9];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-        int yy = py + ky - 1;
-        if (yy < 0 || yy >= H) continue;
+    for (int s = 0; s < NS; ++s)
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-            int xx = px + kx - 1;
-            if (xx < 0 || xx >= W) continue;
-            const float *xp = x + ((nb * H + yy) * W + xx) * ldx + c0;
-            const float *wp = w9 + (ky * 3 + kx) * C + c0;
-            fma4(a, __ldg(reinterpret_cast<const float4 *>(xp)), __ldg(reinterpret_cast<const float4 *>(wp)));
-            if (FUSE == 2)
-                fma4(a2, __ldg(reinterpret_cast<const float4 *>(xp + Cout)),
-                     __ldg(reinterpret_cast<const float4 *>(wp + Cout)));
+        for (int t = 0; t < 9; ++t) wv[s][t] = __ldg(reinterpret_cast<const float4 *>(w9 + t * C + c0 + s * Cout));
+    float4 bv[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+        bv[s] = bias ? __ldg(reinterpret_cast<const float4 *>(bias + c0 + s * Cout)) : make_float4(0, 0, 0, 0);
+
+    float4 r[NS][3][3];
+    const float *xb = x + (nb * H) * (int64_t)W * ldx + c0;
+    auto load_row = [&](int slot, int yy) {
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+            const int xx = px + dx - 1;
+            const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
+            const float *xp = xb + ((int64_t)yy * W + xx) * ldx;
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+                r[s][slot][dx] = ok ? __ldg(reinterpret_cast<const float4 *>(xp + s * Cout)) : make_float4(0, 0, 0, 0);
         }
-    }
-    if (FUSE == 1) {
-        a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w);
-    } else if (FUSE == 2) {
-        a.x = gelu_erf(a.x) * a2.x; a.y = gelu_erf(a.y) * a2.y;
-        a.z = gelu_erf(a.z) * a2.z; a.w = gelu_erf(a.w) * a2.w;
-    }
-    if (layout == 0) {
-        stg_stream(y + p * ldy + c0, a);
-    } else {
-        int Hg = H / ws, Wg = W / ws;
-        int64_t n = (int64_t)(py % Hg) * Wg + (px % Wg);
-        int64_t e = ((int64_t)(py / Hg) * ws + (px / Wg)) * Cout + c0;
-        stg_stream(y + ((nb * Hg * Wg + n) * ws * ws) * Cout + e, a);
+    };
+    load_row(0, y0 - 1);
+    load_row(1, y0);
+    const int Hg = layout ? H / ws : 1, Wg = layout ? W / ws : 1;
+    for (int yy = y0; yy < y1; ++yy) {
+        load_row(2, yy + 1);
+        float4 a[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            a[s] = bv[s];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) fma4(a[s], r[s][ky][kx], wv[s][ky * 3 + kx]);
+        }
+        float4 o = a[0];
+        if (FUSE == 1) {
+            o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w);
+        } else if (FUSE == 2) {
+            o.x = gelu_erf(o.x) * a[NS - 1].x; o.y = gelu_erf(o.y) * a[NS - 1].y;
+            o.z = gelu_erf(o.z) * a[NS - 1].z; o.w = gelu_erf(o.w) * a[NS - 1].w;
+        }
+        if (layout == 0) {
+            stg_stream(y + ((nb * H + yy) * W + px) * ldy + c0, o);
+        } else {
+            int64_t n = (int64_t)(yy % Hg) * Wg + (px % Wg);
+            int64_t e = ((int64_t)(yy / Hg) * ws + (px / Wg)) * Cout + c0;
+            stg_stream(y + ((nb * Hg * Wg + n) * ws * ws) * Cout + e, o);
+        }
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+                r[s][0][dx] = r[s][1][dx];
+                r[s][1][dx] = r[s][2][dx];
+            }
     }
 }
+
+int turtle_dwconv3x3_tma(const float *x, int ldx, const float *w, const float *bias, float *y, int ldy, int NB, int H,
+                         int W, int C, int fuse, int layout, int ws, void *stream);   // dwconv_tma.cu
 
 extern "C" int turtle_dwconv3x3(const float *x, int ldx, const float *w, const float *bias, float *y, int ldy,
                                 int NB, int H, int W, int C, int fuse, int layout, int ws, void *stream) {
@@ -321,15 +432,26 @@ extern "C" int turtle_dwconv3x3(const float *x, int ldx, const float *w, const f
     if (layout == 0 && (ldy & 3)) return TURTLE_EINVAL;
     if (layout == 1 && (ws < 1 || H % ws || W % ws)) return TURTLE_EINVAL;
     if ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)w) & 15) != 0) return TURTLE_EINVAL;
-    int64_t total = (int64_t)NB * H * W * (Cout >> 2);
-    unsigned grid = (unsigned)cdiv64(total, 256);
+    {
+        // TMA halo-staged kernel for 32-channel-aligned maps; the register kernel below covers the rest
+        int r = turtle_dwconv3x3_tma(x, ldx, w, bias, y, ldy, NB, H, W, C, fuse, layout, ws, stream);
+        if (r != TURTLE_ENOTSUP) return r;
+    }
+    int64_t cols = (int64_t)W * (Cout >> 2);
+    unsigned gx = (unsigned)cdiv64(cols, 256);
+    // strip height: tall enough to amortise the 2 halo rows, short enough to fill the chip (>= ~4 waves)
+    int RY = 16;
+    while (RY > 4 && (int64_t)gx * cdiv64(H, RY) * NB < 148 * 8) RY >>= 1;
+    int nstrips = (int)cdiv64(H, RY);
+    if ((int64_t)nstrips * NB > 65535) return TURTLE_EINVAL;
+    dim3 grid(gx, (unsigned)(nstrips * NB));
     cudaStream_t s = as_stream(stream);
     if (fuse == 0)
-        dwconv3x3_kernel<0><<<grid, 256, 0, s>>>(x, ldx, w, bias, y, ldy, NB, H, W, C, layout, ws);
+        dwconv3x3_kernel<0><<<grid, 256, 0, s>>>(x, ldx, w, bias, y, ldy, NB, H, W, C, layout, ws, RY, nstrips);
     else if (fuse == 1)
-        dwconv3x3_kernel<1><<<grid, 256, 0, s>>>(x, ldx, w, bias, y, ldy, NB, H, W, C, layout, ws);
+        dwconv3x3_kernel<1><<<grid, 256, 0, s>>>(x, ldx, w, bias, y, ldy, NB, H, W, C, layout, ws, RY, nstrips);
     else
-        dwconv3x3_kernel<2><<<grid, 256, 0, s>>>(x, ldx, w, bias, y, ldy, NB, H, W, C, layout, ws);
+        dwconv3x3_kernel<2><<<grid, 256, 0, s>>>(x, ldx, w, bias, y, ldy, NB, H, W, C, layout, ws, RY, nstrips);
     TURTLE_CHECK_LAUNCH();
     return TURTLE_OK;
 }
