@@ -19,6 +19,7 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -357,6 +358,285 @@ __global__ void __launch_bounds__(128) gemm_tc_kernel(const __grid_constant__ Tc
     }
 }
 
+// =============================================================================================
+// v2: persistent, warp-specialised, TMEM double-buffered
+//
+//   one CTA per SM, 8 warps:  warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+//   warps 4-7 = epilogue.  The CTA walks work units (pixel tile x n-group, n-group fastest) with a
+//   stride of gridDim.x.  Two 256-column accumulators alternate, so the MMAs of unit i+1 run while
+//   the epilogue warps drain unit i (tcgen05.ld -> bias/GELU/scale -> +residual chunk (TMA-loaded)
+//   -> 128B-swizzled smem staging -> TMA store).  A segments are 3-D tensor maps
+//   {sub-width, sub-blocks, pixels} so head-strided history rows (FHR ring) are addressable too.
+// =============================================================================================
+struct alignas(64) Tc2Params {
+    CUtensorMap mapA[MAX_TC_SEG];
+    CUtensorMap mapW, mapOut, mapRes;
+    int nseg, kb_per_seg, kb_per_sub;
+    int nkb, stages;
+    int im2col, BW, BH, B, H, W, tiles_x, tiles_y;
+    long long P;
+    int Cout, NG, ngroups;
+    long long total_units;
+    int tma_epi;
+    const float *bias, *scale, *res;
+    int act, ldres;
+    float *out;
+    int ldo, store;
+};
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_BUF = 32 * 128;                       // one 32-row x 32-column staging box (4 KB)
+constexpr int EPI_BYTES = EPI_WARPS * 2 * EPI_BUF;      // 64 KB
+
+__global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant__ Tc2Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2], rfull_bar[EPI_WARPS][2];
+    __shared__ uint32_t tmem_base_sh;
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t stage_bytes = A_STAGE_BYTES + (uint32_t)p.NG * TK * 4;
+    const uint32_t epi0 = smem0 + (uint32_t)p.stages * stage_bytes;     // per-warp staging boxes (1024 B aligned)
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(smem_u32(&tfull_bar[s]), 1);
+            mbar_init(smem_u32(&tempty_bar[s]), EPI_WARPS);
+        }
+        for (int w = 0; w < EPI_WARPS; ++w) {
+            mbar_init(smem_u32(&rfull_bar[w][0]), 1);
+            mbar_init(smem_u32(&rfull_bar[w][1]), 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_sh))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_sh;
+    const int NG = p.NG;
+
+    if (warp == 0 && lane == 0) {
+        // ------------------------------ TMA producer ------------------------------
+        int stage = 0;
+        uint32_t phase = 0;
+        for (long long u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+            const int ng = (int)(u % p.ngroups);
+            const long long tile = u / p.ngroups;
+            int tb = 0, ty0 = 0, tx0 = 0;
+            if (p.im2col) {
+                tx0 = (int)(tile % p.tiles_x) * p.BW;
+                ty0 = (int)((tile / p.tiles_x) % p.tiles_y) * p.BH;
+                tb = (int)(tile / ((long long)p.tiles_x * p.tiles_y));
+            }
+            const int m0 = (int)(tile * TM);
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+                const uint32_t fb = smem_u32(&full_bar[stage]);
+                const uint32_t sa = smem0 + stage * stage_bytes;
+                mbar_expect_tx(fb, A_STAGE_BYTES + (uint32_t)NG * TK * 4);
+                const int seg = kb / p.kb_per_seg, r = kb - seg * p.kb_per_seg;
+                if (p.im2col) {
+                    tma_load_4d(sa, &p.mapA[0], r * TK, tx0 + seg % 3 - 1, ty0 + seg / 3 - 1, tb, fb);
+                } else {
+                    const int sub = r / p.kb_per_sub;
+                    tma_load_3d(sa, &p.mapA[seg], (r - sub * p.kb_per_sub) * TK, sub, m0, fb);
+                }
+                tma_load_2d(sa + A_STAGE_BYTES, &p.mapW, kb * TK, ng * NG, fb);
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ------------------------------ MMA issuer ------------------------------
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NG >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (long long u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
+            const int acc = it & 1;
+            mbar_wait(smem_u32(&tempty_bar[acc]), ((it >> 1) & 1) ^ 1);     // epilogue drained this accumulator
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tacc = tmem_base + acc * 256;
+            for (int kb = 0; kb < p.nkb; ++kb) {
+                mbar_wait(smem_u32(&full_bar[stage]), phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem0 + stage * stage_bytes;
+                const uint32_t sb = sa + A_STAGE_BYTES;
+#pragma unroll
+                for (int k = 0; k < TK / 8; ++k)
+                    umma_tf32(tacc, make_desc(sa + k * 32), make_desc(sb + k * 32), idesc, (kb | k) ? 1u : 0u);
+                umma_commit(smem_u32(&empty_bar[stage]));
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(smem_u32(&tfull_bar[acc]));
+        }
+    } else if (warp >= 4) {
+        // ------------------------------ epilogue: 8 warps ------------------------------
+        // warp (4+ew): TMEM lane quarter ew&3 (rows 32*(ew&3)..+31 of the tile), column chunks of
+        // parity ew>>2.  Each warp stages its own 32x32 boxes and issues its own TMA loads/stores,
+        // so the only synchronisation inside the epilogue is __syncwarp.
+        const int ew = warp - 4, quarter = ew & 3, chalf = ew >> 2;
+        const uint32_t mybuf = epi0 + ew * (2 * EPI_BUF);
+        int it = 0;
+        uint32_t gw = 0;                                     // this warp's staging-box use counter
+        for (long long u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
+            const int ng = (int)(u % p.ngroups);
+            const long long tile = u / p.ngroups;
+            const int n0 = ng * NG;
+            const int acc = it & 1;
+            mbar_wait(smem_u32(&tfull_bar[acc]), (it >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256;
+            if (p.tma_epi) {
+                const int m0 = (int)(tile * TM) + quarter * 32;
+                for (int j = chalf; j < NG / 32; j += 2, ++gw) {
+                    const int b = gw & 1;
+                    const uint32_t buf = mybuf + b * EPI_BUF;
+                    const uint32_t rb = smem_u32(&rfull_bar[ew][b]);
+                    if (lane == 0) {
+                        if (gw >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // box b drained
+                        if (p.res) {
+                            mbar_expect_tx(rb, EPI_BUF);
+                            tma_load_2d(buf, &p.mapRes, n0 + j * 32, m0, rb);
+                        }
+                    }
+                    __syncwarp();
+                    float v[32];
+                    tmem_ld32(trow + j * 32, v);
+                    const int o0 = n0 + j * 32;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const int o = o0 + 4 * q;
+                        if (p.bias) {
+                            float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + o));
+                            v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
+                        }
+                        if (p.act == TURTLE_ACT_GELU) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) v[4 * q + e] = gelu_erf(v[4 * q + e]);
+                        }
+                        if (p.scale) {
+                            float4 sc = __ldg(reinterpret_cast<const float4 *>(p.scale + o));
+                            v[4 * q] *= sc.x; v[4 * q + 1] *= sc.y; v[4 * q + 2] *= sc.z; v[4 * q + 3] *= sc.w;
+                        }
+                    }
+                    if (p.res) mbar_wait(rb, (gw >> 1) & 1);
+                    const uint32_t rowaddr = buf + lane * 128;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t addr = rowaddr + (((uint32_t)q ^ ((uint32_t)lane & 7u)) << 4);
+                        float4 t = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        if (p.res) {
+                            float4 r;
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                         : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                                         : "r"(addr));
+                            t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
+                        }
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(t.x), "f"(t.y), "f"(t.z),
+                                     "f"(t.w)
+                                     : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&p.mapOut, buf, n0 + j * 32, m0);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            } else {
+                const int row = quarter * 32 + lane;
+                long long pix;
+                bool live;
+                int py = 0, px = 0, tb = 0;
+                if (p.im2col) {
+                    const int tx0 = (int)(tile % p.tiles_x) * p.BW;
+                    const int ty0 = (int)((tile / p.tiles_x) % p.tiles_y) * p.BH;
+                    tb = (int)(tile / ((long long)p.tiles_x * p.tiles_y));
+                    py = ty0 + row / p.BW;
+                    px = tx0 + row % p.BW;
+                    live = py < p.H && px < p.W;
+                    pix = ((long long)tb * p.H + py) * p.W + px;
+                } else {
+                    pix = tile * TM + row;
+                    live = pix < p.P;
+                }
+                for (int c0 = chalf * 16; c0 < NG; c0 += 32) {
+                    float v[16];
+                    __syncwarp();
+                    tmem_ld16(trow + c0, v);
+                    const int o0 = n0 + c0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (!live) break;
+                        float4 t = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        const int o = o0 + 4 * q;
+                        if (p.bias) {
+                            float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + o));
+                            t.x += bb.x; t.y += bb.y; t.z += bb.z; t.w += bb.w;
+                        }
+                        if (p.act == TURTLE_ACT_GELU) {
+                            t.x = gelu_erf(t.x); t.y = gelu_erf(t.y); t.z = gelu_erf(t.z); t.w = gelu_erf(t.w);
+                        }
+                        if (p.scale) {
+                            float4 sc = __ldg(reinterpret_cast<const float4 *>(p.scale + o));
+                            t.x *= sc.x; t.y *= sc.y; t.z *= sc.z; t.w *= sc.w;
+                        }
+                        if (p.res) {
+                            float4 r = *reinterpret_cast<const float4 *>(p.res + pix * p.ldres + o);
+                            t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
+                        }
+                        if (p.store == TURTLE_STORE_PLAIN) {
+                            *reinterpret_cast<float4 *>(p.out + pix * p.ldo + o) = t;
+                        } else if (p.store == TURTLE_STORE_UNSHUFFLE2) {
+                            const int Ho = p.H >> 1, Wo = p.W >> 1;
+                            float *op = p.out + (((long long)tb * Ho + (py >> 1)) * Wo + (px >> 1)) * p.ldo +
+                                        ((py & 1) * 2 + (px & 1));
+                            op[(o + 0) * 4] = t.x; op[(o + 1) * 4] = t.y; op[(o + 2) * 4] = t.z; op[(o + 3) * 4] = t.w;
+                        } else {
+                            const int Wo = p.W << 1;
+                            float *op = p.out + (((long long)tb * (p.H << 1) + 2 * py) * Wo + 2 * px) * p.ldo + (o >> 2);
+                            op[0] = t.x;
+                            op[p.ldo] = t.y;
+                            op[(long long)Wo * p.ldo] = t.z;
+                            op[(long long)Wo * p.ldo + p.ldo] = t.w;
+                        }
+                    }
+                }
+            }
+            // every tcgen05.ld of this warp has completed (wait::ld): hand the accumulator back
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side: tensor-map cache + launch
 // ---------------------------------------------------------------------------------------------
@@ -450,7 +730,131 @@ int launch(const TcParams &p, dim3 grid, size_t smem, cudaStream_t s) {
 
 }  // namespace
 
+namespace {
+
+int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
+    const int Cout = a->Cout;
+    Tc2Params p{};
+    p.P = a->P;
+    p.Cout = Cout;
+    p.bias = a->bias; p.scale = a->scale; p.res = a->res;
+    p.act = a->act; p.ldres = a->ldres;
+    p.out = a->out; p.ldo = a->ldo; p.store = a->store;
+    p.B = a->B; p.H = a->H; p.W = a->W;
+    p.im2col = a->im2col;
+    int NG = 256;
+    while (NG >= 16 && Cout % NG) NG -= 16;
+    if (NG < 16) return TURTLE_ENOTSUP;
+    p.NG = NG;
+    p.ngroups = Cout / NG;
+    const int K = a->im2col ? 9 * a->segw : a->nseg * a->segw;
+    long long tiles;
+    if (a->im2col) {
+        if (a->lda[0] != a->segw) return TURTLE_ENOTSUP;
+        int BW = 32;
+        while (BW > 1 && (a->W % BW)) BW >>= 1;
+        if (BW < 4) return TURTLE_ENOTSUP;
+        p.BW = BW; p.BH = TM / BW;
+        p.tiles_x = a->W / BW;
+        p.tiles_y = (a->H + p.BH - 1) / p.BH;
+        p.nseg = 9;
+        p.kb_per_seg = a->segw / TK;
+        p.kb_per_sub = p.kb_per_seg;
+        uint64_t dims[4] = {(uint64_t)a->segw, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->B};
+        uint64_t str[3] = {(uint64_t)a->segw * 4, (uint64_t)a->segw * 4 * a->W, (uint64_t)a->segw * 4 * a->W * a->H};
+        uint32_t box[4] = {TK, (uint32_t)BW, (uint32_t)p.BH, 1};
+        if (!get_map(&p.mapA[0], a->A[0], 4, dims, str, box)) return TURTLE_ENOTSUP;
+        tiles = (long long)p.tiles_x * p.tiles_y * a->B;
+    } else {
+        // group the flat segment list into <= 8 runs of equally spaced column blocks (3-D tensor maps)
+        const int n = a->nseg, w = a->segw;
+        int g = 0;
+        for (int cand = n; cand >= 1; --cand) {
+            if (n % cand || n / cand > MAX_TC_SEG) continue;
+            bool ok = true;
+            for (int i = 0; i < n && ok; i += cand) {
+                const long long hs = cand > 1 ? (long long)(a->A[i + 1] - a->A[i]) : w;
+                if (hs < w || (hs & 3)) ok = false;
+                for (int j = 1; j < cand && ok; ++j)
+                    ok = (a->A[i + j] - a->A[i]) == j * hs && a->lda[i + j] == a->lda[i];
+                if (ok && (long long)a->lda[i] < (cand - 1) * hs + w) ok = false;
+            }
+            if (ok) { g = cand; break; }
+        }
+        if (!g) return TURTLE_ENOTSUP;
+        p.nseg = n / g;
+        p.kb_per_sub = w / TK;
+        p.kb_per_seg = g * p.kb_per_sub;
+        for (int i = 0; i < p.nseg; ++i) {
+            const long long hs = g > 1 ? (long long)(a->A[i * g + 1] - a->A[i * g]) : w;
+            uint64_t dims[3] = {(uint64_t)w, (uint64_t)g, (uint64_t)a->P};
+            uint64_t str[2] = {(uint64_t)hs * 4, (uint64_t)a->lda[i * g] * 4};
+            uint32_t box[3] = {TK, 1, TM};
+            if (!get_map(&p.mapA[i], a->A[i * g], 3, dims, str, box)) return TURTLE_ENOTSUP;
+        }
+        tiles = (a->P + TM - 1) / TM;
+    }
+    p.nkb = K / TK;
+    {
+        uint64_t dims[2] = {(uint64_t)K, (uint64_t)Cout};
+        uint64_t str[1] = {(uint64_t)K * 4};
+        uint32_t box[2] = {TK, (uint32_t)NG};
+        if (!get_map(&p.mapW, a->Wt, 2, dims, str, box)) return TURTLE_ENOTSUP;
+    }
+    p.total_units = tiles * p.ngroups;
+    const size_t stage_bytes = A_STAGE_BYTES + (size_t)NG * TK * 4;
+    const size_t max_smem = 232448 - 2048;   // 227 KB opt-in limit minus the kernel's static smem
+    int stages = (int)((max_smem - 1024 - EPI_BYTES) / stage_bytes);
+    if (stages > 8) stages = 8;
+    if (stages < 2) return TURTLE_ENOTSUP;
+    p.stages = stages;
+    p.tma_epi = 0;
+    if (!a->im2col && a->store == TURTLE_STORE_PLAIN && NG % 32 == 0 && !(a->ldo & 3) &&
+        (!a->res || (!(a->ldres & 3) && !((uintptr_t)a->res & 15)))) {
+        uint64_t dims[2] = {(uint64_t)Cout, (uint64_t)a->P};
+        uint32_t box[2] = {32, 32};
+        uint64_t so[1] = {(uint64_t)a->ldo * 4};
+        bool ok = get_map(&p.mapOut, a->out, 2, dims, so, box);
+        if (ok && a->res) {
+            uint64_t sr[1] = {(uint64_t)a->ldres * 4};
+            ok = get_map(&p.mapRes, a->res, 2, dims, sr, box);
+        }
+        p.tma_epi = ok ? 1 : 0;
+    }
+    const size_t smem = stages * stage_bytes + EPI_BYTES + 1024;
+    static bool configured = false;
+    static int nsm = 148;
+    if (!configured) {
+        if (cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess)
+            return TURTLE_ELAUNCH;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+        configured = true;
+    }
+    long long grid = p.total_units < nsm ? p.total_units : nsm;
+    gemm_tc2_kernel<<<(unsigned)grid, 384, smem, as_stream(stream)>>>(p);
+    return cudaGetLastError() == cudaSuccess ? TURTLE_OK : TURTLE_ELAUNCH;
+}
+
+}  // namespace
+
+int turtle_gemm_tc_v1(const TurtleGemmArgs *a, void *stream);
+
 int turtle_gemm_tc(const TurtleGemmArgs *a, void *stream) {
+    const int Cout = a->Cout;
+    if (Cout % 16 || Cout < 16) return TURTLE_ENOTSUP;
+    if (a->segw % TK) return TURTLE_ENOTSUP;
+    if (((uintptr_t)a->Wt & 15) || ((uintptr_t)a->out & 15)) return TURTLE_ENOTSUP;
+    static const bool use_v1 = getenv("TURTLE_GEMM_V1") != nullptr;
+    if (!use_v1) {
+        int r = turtle_gemm_tc2(a, stream);
+        if (r != TURTLE_ENOTSUP) return r;
+    }
+    return turtle_gemm_tc_v1(a, stream);
+}
+
+int turtle_gemm_tc_v1(const TurtleGemmArgs *a, void *stream) {
     const int Cout = a->Cout;
     if (Cout % 16 || Cout < 16) return TURTLE_ENOTSUP;
     if (a->segw % TK) return TURTLE_ENOTSUP;

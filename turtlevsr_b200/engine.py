@@ -65,6 +65,7 @@ class FrameEngine:
 
         # per-kernel device timing (bench roofline leg): name -> [ms, launches, alg. bytes, flops]
         self.profile: Optional[dict] = None
+        self.profile_shapes = False
         self._meta = (0, 0)
 
     def _call(self, name, *args):
@@ -167,6 +168,9 @@ class FrameEngine:
         name = "turtle_gemm"
         if self.profile is not None:
             name = "turtle_gemm[conv3x3]" if im2col else "turtle_gemm[1x1]"
+            if self.profile_shapes:
+                Kt = (9 if im2col else len(segs)) * segw
+                name += f"|{Kt}->{Cout}@{P}" + ("+res" if res else "") + (f"/{len(segs)}seg" if len(segs) > 1 else "")
         self._call_gemm(name, a)
 
     def _call_gemm(self, tag, a):
