@@ -183,6 +183,14 @@ int turtle_sab_patch_normalize(float *rows, int64_t n_rows, int D, void *stream)
 int turtle_sab_select(const float *qn, const float *kn, int64_t k_fstride, int F, int Hg, int Wg, int D,
                       const float *temperature, int halve, int32_t *idx, float *wgt, int mode, void *stream);
 
+/* Same contract on the tensor cores (tcgen05, 3xTF32 split product => fp32-accurate scores, top-5 kept
+ * per TMEM lane in registers).  Needs D % 32 == 0, dense key frames (k_fstride == N*D) and a device
+ * workspace of turtle_sab_select_tc_workspace(F,N,D) bytes; returns TURTLE_ENOTSUP otherwise. */
+long long turtle_sab_select_tc_workspace(int F, int N, int D);
+int turtle_sab_select_tc(const float *qn, const float *kn, int64_t k_fstride, int F, int Hg, int Wg, int D,
+                         const float *temperature, int halve, int32_t *idx, float *wgt, void *workspace,
+                         void *stream);
+
 /* attn @ v with the sparse weights, un-patched straight to NHWC (T1:599-604):
  *   y[f, p1*Hg+iy, p2*Wg+ix, d] = sum_t wgt[f,i,t] * V[f][idx[f,i,t]][(p1*ws+p2)*c + d]
  * v: frame f at v + f*v_fstride, [N, ws*ws*c];  y [F,H,W,c] dense.

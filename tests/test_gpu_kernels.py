@@ -192,8 +192,9 @@ def test_sab_window_reduce(ws, D):
     assert (out.cpu() - want).abs().max() < TOL
 
 
+@pytest.mark.parametrize("tc", [False, True])
 @pytest.mark.parametrize("Hg,Wg,D,F_", [(6, 8, 32, 2), (16, 16, 128, 4), (30, 54, 64, 3), (46, 80, 128, 2)])
-def test_sab_select_and_aggregate(Hg, Wg, D, F_):
+def test_sab_select_and_aggregate(Hg, Wg, D, F_, tc):
     N = Hg * Wg
     q = orc.l2norm_rows(rnd(N, D))
     k = orc.l2norm_rows(rnd(F_, N, D, seed=1))
@@ -201,8 +202,14 @@ def test_sab_select_and_aggregate(Hg, Wg, D, F_):
     Wt, top, S = orc.sab_select_sparse(q, k, tau, Hg, Wg)
     idx = torch.empty(F_, N, capi.SAB_SLOTS, dtype=torch.int32, device="cuda")
     wgt = torch.empty(F_, N, capi.SAB_SLOTS, device="cuda")
-    call("turtle_sab_select", dp(q), dp(k), N * D, F_, Hg, Wg, D,
-         dp(torch.tensor([tau])), 0, idx.data_ptr(), wgt.data_ptr(), 0, stream())
+    if tc:     # tcgen05 3xTF32 correlation, top-5 per TMEM lane
+        nbytes = capi.load().turtle_sab_select_tc_workspace(F_, N, D)
+        wsp = torch.empty(nbytes // 4 + 1, device="cuda")
+        call("turtle_sab_select_tc", dp(q), dp(k), N * D, F_, Hg, Wg, D, dp(torch.tensor([tau])), 0, idx.data_ptr(),
+             wgt.data_ptr(), wsp.data_ptr(), stream())
+    else:
+        call("turtle_sab_select", dp(q), dp(k), N * D, F_, Hg, Wg, D,
+             dp(torch.tensor([tau])), 0, idx.data_ptr(), wgt.data_ptr(), 0, stream())
     idx_c, wgt_c = idx.cpu().long(), wgt.cpu()
     # top-5 sets identical (fp32 FMA order may differ from the CPU matmul only on sub-ulp near-ties)
     same = (idx_c[..., :5].sort(-1).values == top.sort(-1).values).all(-1)

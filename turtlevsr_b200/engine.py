@@ -378,8 +378,14 @@ class FrameEngine:
             vf = _ptr(ring.vbuf[b, first])
             if not t0:
                 self._meta = (4 * (N * Dk * (F_ + 1) + 2 * F_ * N * capi.SAB_SLOTS), 2 * F_ * N * N * Dk)
-                self._call("turtle_sab_select", _ptr(qn[b]), kf, N * Dk, F_, Hg, Wg, Dk, _ptr(temp), 0, _ptr(idx[b]),
-                     _ptr(wgt[b]), self.mode, self.stream)
+                if self.mode == capi.TF32 and Dk % 32 == 0 and N >= 5 and not self.dry_run:
+                    wsb = capi.load().turtle_sab_select_tc_workspace(F_, N, Dk)
+                    wsp = self.ws.get("sab_tcws", (wsb + 3) // 4)
+                    self._call("turtle_sab_select_tc", _ptr(qn[b]), kf, N * Dk, F_, Hg, Wg, Dk, _ptr(temp), 0,
+                               _ptr(idx[b]), _ptr(wgt[b]), _ptr(wsp), self.stream)
+                else:
+                    self._call("turtle_sab_select", _ptr(qn[b]), kf, N * Dk, F_, Hg, Wg, Dk, _ptr(temp), 0,
+                               _ptr(idx[b]), _ptr(wgt[b]), self.mode, self.stream)
             self._meta = (4 * (2 * F_ * N * Dv + 2 * F_ * N * capi.SAB_SLOTS), 2 * F_ * N * 46 * Dv)
             self._call("turtle_sab_aggregate", _ptr(idx[b]), _ptr(wgt[b]), vf, N * Dv, _ptr(agg[b]), F_, Hg, Wg, ws_, c,
                  1 if t0 else 0, self.stream)
