@@ -217,7 +217,10 @@ extern "C" int turtle_chan_gram(const float *q, int ldq, int q_hs, const float *
         return TURTLE_EINVAL;
     int64_t chunk = cdiv64(cdiv64(P, nsplit), GT) * GT;
     dim3 grid(nsplit, heads);
-    (void)mode;
+    if (mode == TURTLE_TF32) {
+        int r = turtle_chan_gram_tc(q, ldq, q_hs, k, ldk, k_hs, P, heads, ch, nsplit, gpart, sqq, sqk, stream);
+        if (r != TURTLE_ENOTSUP) return r;
+    }
     if (ch == 64 && !(ldq & 3) && !(ldk & 3) && !(q_hs & 3) && !(k_hs & 3) &&
         !(((uintptr_t)q | (uintptr_t)k) & 15))
         gram64_kernel<64><<<grid, 256, 0, as_stream(stream)>>>(q, ldq, q_hs, k, ldk, k_hs, P, heads, chunk, gpart, sqq,

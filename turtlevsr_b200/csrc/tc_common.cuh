@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 // cached cuTensorMapEncodeTiled (gemm_tc.cu).  dims/strides innermost first, strides in bytes for dims 1..
+// swizzle128: 0 = none, 1 = SWIZZLE_128B (16 B atoms), 2 = SWIZZLE_128B_ATOM_32B (tf32 MN-major operands)
 bool turtle_get_tmap(CUtensorMap *out, const void *ptr, int rank, const uint64_t *dims, const uint64_t *strides,
                      const uint32_t *box, int swizzle128);
 
