@@ -15,6 +15,9 @@
  *   - every function enqueues work on `stream` (a cudaStream_t passed as void*) and returns
  *     immediately: 0 on success, a negative TURTLE_E* code on bad arguments or launch failure.
  *     Nothing allocates, synchronises or throws; the caller owns all buffers;
+ *   - `round_tf32` (producer kernels) / `round_out` (gemm): in TURTLE_TF32 mode the host asks producers whose
+ *     output feeds a tensor-core contraction to round it to nearest TF32 (cvt.rna), so that the tensor core's
+ *     operand truncation is exact and unbiased; pass 0 in TURTLE_FP32 mode;
  *   - `mode`: TURTLE_FP32 = CUDA-core fp32 FMA (exact mode: bit-exact top-k contract),
  *             TURTLE_TF32 = tcgen05 tensor cores, TF32 operands, fp32 accumulate in TMEM.
  */
@@ -77,7 +80,7 @@ int turtle_conv3x3_last(const float *x, const float *w, const float *bias, const
  *   in the numerator, exactly as T1:79-81)
  * ------------------------------------------------------------------------------------- */
 int turtle_layernorm(const float *x, int ldx, const float *w, const float *b, float *y, int ldy, int64_t P,
-                     int C, void *stream);
+                     int C, int round_tf32, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Contractions over channels: 1x1 convs, the skip-cat + reduce_chan, the folded
@@ -113,6 +116,7 @@ typedef struct TurtleGemmArgs {
     float *out;
     int32_t ldo;
     int32_t store;       /* TURTLE_STORE_* */
+    int32_t round_out;   /* !=0: round the stored values to nearest TF32 (they feed another tensor-core op) */
 } TurtleGemmArgs;
 
 int turtle_gemm(const TurtleGemmArgs *args, void *stream);
@@ -127,7 +131,7 @@ int turtle_gemm(const TurtleGemmArgs *args, void *stream);
  * bias nullable.
  * ------------------------------------------------------------------------------------- */
 int turtle_dwconv3x3(const float *x, int ldx, const float *w, const float *bias, float *y, int ldy, int NB,
-                     int H, int W, int C, int fuse, int layout, int ws, void *stream);
+                     int H, int W, int C, int fuse, int layout, int ws, int round_tf32, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Transposed (channel) attention: ChannelAttention T1:680-702, FrameHistoryRouter T1:243-286,
@@ -151,7 +155,8 @@ int turtle_chan_softmax(const float *gpart, const float *sqq, const float *sqk, 
                         float *inv_knorm /* [nseg, heads*ch], 1/max(|k|,1e-12) (1 for prenormalised) */,
                         void *stream);
 
-int turtle_chan_fold(const float *Pm, const float *Wo, int nseg, int heads, int ch, float *M, void *stream);
+int turtle_chan_fold(const float *Pm, const float *Wo, int nseg, int heads, int ch, float *M, int round_tf32,
+                     void *stream);
 
 /* y[p, h*y_hs + j] = x[p, h*x_hs + j] * s[h*ch + j]  (s==NULL: copy).  Used to push the normalised
  * key rows / raw value rows of a frame into the history ring (T1:272-273, 286). */
@@ -196,7 +201,7 @@ int turtle_sab_select_tc(const float *qn, const float *kn, int64_t k_fstride, in
  * v: frame f at v + f*v_fstride, [N, ws*ws*c];  y [F,H,W,c] dense.
  * passthrough!=0 reproduces T0:523 (`out = v`): y is the un-patched V itself. */
 int turtle_sab_aggregate(const int32_t *idx, const float *wgt, const float *v, int64_t v_fstride, float *y, int F,
-                         int Hg, int Wg, int ws, int c, int passthrough, void *stream);
+                         int Hg, int Wg, int ws, int c, int passthrough, int round_tf32, void *stream);
 
 /* T0 only: x + positionalencoding2d(c,h,w) (T0:412-439, 475-476), evaluated analytically. */
 int turtle_add_posenc(const float *x, float *y, int B, int H, int W, int C, void *stream);

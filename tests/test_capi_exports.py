@@ -35,13 +35,14 @@ def test_abi_version_and_struct_layout():
     hdr = open(os.path.join(ROOT, "include", "turtle_b200.h")).read()
     assert int(re.search(r"#define TURTLE_MAX_SEG (\d+)", hdr).group(1)) == capi.MAX_SEG
     assert int(re.search(r"#define TURTLE_SAB_SLOTS (\d+)", hdr).group(1)) == capi.SAB_SLOTS
-    assert ctypes.sizeof(capi.GemmArgs) == 8 + 8 + 16 + 8 + 8 * 48 + 4 * 48 + 8 * 3 + 8 + 8 + 8 + 8 + 8
+    assert lib.turtle_abi_version() == 2
+    assert ctypes.sizeof(capi.GemmArgs) == 688
 
 
 def test_bad_arguments_are_rejected_without_a_gpu():
     lib = capi.load()
     # NULL pointers / bad shapes return TURTLE_EINVAL before any launch is attempted
-    assert lib.turtle_layernorm(None, 64, None, None, None, 64, 10, 64, None) == -1
-    assert lib.turtle_dwconv3x3(None, 64, None, None, None, 64, 1, 8, 8, 64, 0, 0, 1, None) == -1
+    assert lib.turtle_layernorm(None, 64, None, None, None, 64, 10, 64, 0, None) == -1
+    assert lib.turtle_dwconv3x3(None, 64, None, None, None, 64, 1, 8, 8, 64, 0, 0, 1, 0, None) == -1
     a = capi.GemmArgs()
     assert lib.turtle_gemm(ctypes.byref(a), None) == -1

@@ -29,7 +29,7 @@ def test_layernorm(C_):
     xd = nhwc(x)
     y = torch.empty_like(xd)
     call("turtle_layernorm", xd.data_ptr(), C_, dp(w), dp(b), y.data_ptr(), C_,
-         2 * 12 * 20, C_, stream())
+         2 * 12 * 20, C_, 0, stream())
     assert (nchw(y) - want).abs().max() < TOL
 
 
@@ -97,7 +97,7 @@ def test_dwconv(fuse):
     out = torch.empty(B, H, W, Co, device="cuda")
     w9 = w.reshape(C_, 9).t().contiguous().cuda()
     call("turtle_dwconv3x3", dp(nhwc(x)), C_, w9.data_ptr(), dp(b), out.data_ptr(), Co, B, H, W,
-         C_, fuse, 0, 1, stream())
+         C_, fuse, 0, 1, 0, stream())
     assert (nchw(out) - y).abs().max() < TOL
 
 
@@ -108,7 +108,7 @@ def test_dwconv_patch_layout():
     out = torch.empty(B, (H // ws) * (W // ws), ws * ws * C_, device="cuda")
     w9 = w.reshape(C_, 9).t().contiguous().cuda()
     call("turtle_dwconv3x3", dp(nhwc(x)), C_, w9.data_ptr(), None, out.data_ptr(), C_, B, H, W, C_, 0, 1, ws,
-         stream())
+         0, stream())
     assert (out.cpu() - want).abs().max() < TOL
 
 
@@ -173,7 +173,7 @@ def test_channel_attention_chain(heads, ch, S, mode):
          S, nsplit, heads, ch, Pm.data_ptr(), inv.data_ptr(), stream())
     assert (Pm.cpu().reshape(heads, ch, S * ch) - attn).abs().max() < (1e-5 if mode == capi.FP32 else 2e-4)
     M = torch.empty(c, S * c, device="cuda")
-    call("turtle_chan_fold", Pm.data_ptr(), dp(Wo), S, heads, ch, M.data_ptr(), stream())
+    call("turtle_chan_fold", Pm.data_ptr(), dp(Wo), S, heads, ch, M.data_ptr(), 0, stream())
     xd = x.cuda()
     segs = [(qkv[s], 2 * c + h * ch, 3 * c) for s in range(S) for h in range(heads)]
     gemm(segs, ch, M, P, c, res=xd, out=xd, ldo=c)
@@ -228,7 +228,7 @@ def test_sab_select_and_aggregate(Hg, Wg, D, F_, tc):
     V = rnd(F_, N, ws * ws * c, seed=2)
     y = torch.empty(F_, Hg * ws, Wg * ws, c, device="cuda")
     call("turtle_sab_aggregate", idx.data_ptr(), wgt.data_ptr(), dp(V), N * ws * ws * c, y.data_ptr(), F_,
-         Hg, Wg, ws, c, 0, stream())
+         Hg, Wg, ws, c, 0, 0, stream())
     want = orc.from_dilated_patches(dense @ V, ws, c, Hg * ws, Wg * ws)      # [F,c,H,W]
     assert (y.cpu().permute(0, 3, 1, 2) - want).abs().max() < 1e-5
 

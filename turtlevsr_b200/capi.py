@@ -26,7 +26,7 @@ class GemmArgs(C.Structure):
         ("mode", _i32), ("im2col", _i32), ("P", _i64), ("B", _i32), ("H", _i32), ("W", _i32), ("Cout", _i32),
         ("nseg", _i32), ("segw", _i32), ("A", _fp * MAX_SEG), ("lda", _i32 * MAX_SEG), ("Wt", _fp),
         ("bias", _fp), ("scale", _fp), ("act", _i32), ("res", _fp), ("ldres", _i32), ("out", _fp),
-        ("ldo", _i32), ("store", _i32),
+        ("ldo", _i32), ("store", _i32), ("round_out", _i32),
     ]
 
 
@@ -37,20 +37,21 @@ _SIGS = {
     "turtle_conv3x3_first": ([_fp, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _i32, _fp], C.c_int),
     "turtle_conv3x3_last": ([_fp, _fp, _fp, _fp, _i32, _i32, _fp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _fp],
                             C.c_int),
-    "turtle_layernorm": ([_fp, _i32, _fp, _fp, _fp, _i32, _i64, _i32, _fp], C.c_int),
+    "turtle_layernorm": ([_fp, _i32, _fp, _fp, _fp, _i32, _i64, _i32, _i32, _fp], C.c_int),
     "turtle_gemm": ([C.POINTER(GemmArgs), _fp], C.c_int),
-    "turtle_dwconv3x3": ([_fp, _i32, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _fp], C.c_int),
+    "turtle_dwconv3x3": ([_fp, _i32, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _fp],
+                         C.c_int),
     "turtle_chan_gram": ([_fp, _i32, _i32, _fp, _i32, _i32, _i64, _i32, _i32, _i32, _fp, _fp, _fp, _i32, _fp],
                          C.c_int),
     "turtle_chan_softmax": ([_fp, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _fp, _fp, _fp], C.c_int),
-    "turtle_chan_fold": ([_fp, _fp, _i32, _i32, _i32, _fp, _fp], C.c_int),
+    "turtle_chan_fold": ([_fp, _fp, _i32, _i32, _i32, _fp, _i32, _fp], C.c_int),
     "turtle_scale_cols": ([_fp, _i32, _i32, _fp, _fp, _i32, _i32, _i64, _i32, _i32, _fp], C.c_int),
     "turtle_sab_window_reduce": ([_fp, _i32, _fp, _fp, _i64, _i32, _i32, _i32, _i32, _i32, _fp], C.c_int),
     "turtle_sab_patch_normalize": ([_fp, _i64, _i32, _fp], C.c_int),
     "turtle_sab_select": ([_fp, _fp, _i64, _i32, _i32, _i32, _i32, _fp, _i32, _fp, _fp, _i32, _fp], C.c_int),
     "turtle_sab_select_tc_workspace": ([_i32, _i32, _i32], C.c_longlong),
     "turtle_sab_select_tc": ([_fp, _fp, _i64, _i32, _i32, _i32, _i32, _fp, _i32, _fp, _fp, _fp, _fp], C.c_int),
-    "turtle_sab_aggregate": ([_fp, _fp, _fp, _i64, _fp, _i32, _i32, _i32, _i32, _i32, _i32, _fp], C.c_int),
+    "turtle_sab_aggregate": ([_fp, _fp, _fp, _i64, _fp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _fp], C.c_int),
     "turtle_add_posenc": ([_fp, _fp, _i32, _i32, _i32, _i32, _fp], C.c_int),
 }
 

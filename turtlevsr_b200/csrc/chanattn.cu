@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(128) chan_softmax_kernel(const float *__restri
 }
 
 __global__ void chan_fold_kernel(const float *__restrict__ Pm, const float *__restrict__ Wo, int nseg, int heads,
-                                 int ch, float *__restrict__ M) {
+                                 int ch, float *__restrict__ M, int rnd) {
     const int C = heads * ch, ncolP = nseg * ch, K = nseg * C;
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)C * K) return;
@@ -202,7 +202,7 @@ __global__ void chan_fold_kernel(const float *__restrict__ Pm, const float *__re
     const float *pp = Pm + ((int64_t)h * ch) * ncolP + seg * ch + j;
     float acc = 0.f;
     for (int i = 0; i < ch; ++i) acc = fmaf(__ldg(wp + i), __ldg(pp + (int64_t)i * ncolP), acc);
-    M[idx] = acc;
+    M[idx] = rnd ? rna_tf32(acc) : acc;
 }
 
 }  // namespace
@@ -244,10 +244,11 @@ extern "C" int turtle_chan_softmax(const float *gpart, const float *sqq, const f
     return TURTLE_OK;
 }
 
-extern "C" int turtle_chan_fold(const float *Pm, const float *Wo, int nseg, int heads, int ch, float *M, void *stream) {
+extern "C" int turtle_chan_fold(const float *Pm, const float *Wo, int nseg, int heads, int ch, float *M, int round_tf32,
+                                void *stream) {
     if (!Pm || !Wo || !M) return TURTLE_EINVAL;
     int64_t total = (int64_t)heads * ch * nseg * heads * ch;
-    chan_fold_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, as_stream(stream)>>>(Pm, Wo, nseg, heads, ch, M);
+    chan_fold_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, as_stream(stream)>>>(Pm, Wo, nseg, heads, ch, M, round_tf32);
     TURTLE_CHECK_LAUNCH();
     return TURTLE_OK;
 }

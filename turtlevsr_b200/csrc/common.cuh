@@ -42,3 +42,14 @@ __device__ __forceinline__ void stg_stream(float *p, float4 v) {
                  "f"(v.w)
                  : "memory");
 }
+
+// round-to-nearest TF32 (10 mantissa bits) kept in an fp32 container: producers apply it in tf32 mode so
+// that the tensor core's operand truncation becomes a no-op (removes the truncation bias)
+__device__ __forceinline__ float rna_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ float4 rna_tf32(float4 v) {
+    return make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
+}

@@ -24,7 +24,7 @@ struct alignas(64) DwParams {
     CUtensorMap map;
     const float *w9, *bias;
     float *y;
-    int ldy, NB, H, W, C, Cout, fuse, layout, ws;
+    int ldy, NB, H, W, C, Cout, fuse, layout, ws, rnd;
     int tiles_x, tiles_y, cblocks;
     long long nitems;
 };
@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_tma_kernel(const __grid_constan
                 o.x = gelu_erf(o.x) * g.x; o.y = gelu_erf(o.y) * g.y;
                 o.z = gelu_erf(o.z) * g.z; o.w = gelu_erf(o.w) * g.w;
             }
+            if (p.rnd) o = rna_tf32(o);
             const int py = py0 + i;
             if (py < p.H && px < p.W) {
                 if (p.layout == 0) {
@@ -194,7 +195,7 @@ int launch(const DwParams &p, cudaStream_t s) {
 
 // returns TURTLE_ENOTSUP when the shape does not fit the tiled kernel (caller falls back)
 int turtle_dwconv3x3_tma(const float *x, int ldx, const float *w, const float *bias, float *y, int ldy, int NB, int H,
-                         int W, int C, int fuse, int layout, int ws, void *stream) {
+                         int W, int C, int fuse, int layout, int ws, int rnd, void *stream) {
     const int Cout = fuse == 2 ? C / 2 : C;
     if (Cout % CK) return TURTLE_ENOTSUP;
     DwParams p{};
@@ -203,7 +204,7 @@ int turtle_dwconv3x3_tma(const float *x, int ldx, const float *w, const float *b
     uint32_t box[4] = {CK, HC, HR, 1};
     if (!turtle_get_tmap(&p.map, x, 4, dims, str, box, 0)) return TURTLE_ENOTSUP;
     p.w9 = w; p.bias = bias; p.y = y; p.ldy = ldy;
-    p.NB = NB; p.H = H; p.W = W; p.C = C; p.Cout = Cout; p.fuse = fuse; p.layout = layout; p.ws = ws;
+    p.NB = NB; p.H = H; p.W = W; p.C = C; p.Cout = Cout; p.fuse = fuse; p.layout = layout; p.ws = ws; p.rnd = rnd;
     p.tiles_x = (W + TW - 1) / TW;
     p.tiles_y = (H + TH - 1) / TH;
     p.cblocks = Cout / CK;

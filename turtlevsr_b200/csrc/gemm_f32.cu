@@ -126,6 +126,7 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const __grid_constant__ G
             float4 r = *reinterpret_cast<const float4 *>(g.a.res + p * g.a.ldres + o0);
             v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
         }
+        if (g.a.round_out) v = rna_tf32(v);
         if (g.a.store == TURTLE_STORE_PLAIN) {
             *reinterpret_cast<float4 *>(g.a.out + p * g.a.ldo + o0) = v;
         } else {

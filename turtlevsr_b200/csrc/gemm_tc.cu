@@ -49,7 +49,7 @@ struct alignas(64) TcParams {
     const float *bias, *scale, *res;
     int act, ldres;
     float *out;
-    int ldo, store;
+    int ldo, store, round_out;
 };
 
 template <int TMEM_COLS>
@@ -206,6 +206,7 @@ __global__ void __launch_bounds__(128) gemm_tc_kernel(const __grid_constant__ Tc
                     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
                     t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
                 }
+                if (p.round_out) t = rna_tf32(t);
                 asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -242,6 +243,7 @@ __global__ void __launch_bounds__(128) gemm_tc_kernel(const __grid_constant__ Tc
                 float4 r = *reinterpret_cast<const float4 *>(p.res + pix * p.ldres + o);
                 t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
             }
+            if (p.round_out) t = rna_tf32(t);
             if (p.store == TURTLE_STORE_PLAIN) {
                 *reinterpret_cast<float4 *>(p.out + pix * p.ldo + o) = t;
             } else if (p.store == TURTLE_STORE_UNSHUFFLE2) {
@@ -288,7 +290,7 @@ struct alignas(64) Tc2Params {
     const float *bias, *scale, *res;
     int act, ldres;
     float *out;
-    int ldo, store;
+    int ldo, store, round_out;
 };
 
 constexpr int EPI_WARPS = 8;
@@ -447,6 +449,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
                                          : "r"(addr));
                             t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
                         }
+                        if (p.round_out) t = rna_tf32(t);
                         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(t.x), "f"(t.y), "f"(t.z),
                                      "f"(t.w)
                                      : "memory");
@@ -500,6 +503,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
                             float4 r = *reinterpret_cast<const float4 *>(p.res + pix * p.ldres + o);
                             t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
                         }
+                        if (p.round_out) t = rna_tf32(t);
                         if (p.store == TURTLE_STORE_PLAIN) {
                             *reinterpret_cast<float4 *>(p.out + pix * p.ldo + o) = t;
                         } else if (p.store == TURTLE_STORE_UNSHUFFLE2) {
@@ -637,7 +641,7 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
     p.Cout = Cout;
     p.bias = a->bias; p.scale = a->scale; p.res = a->res;
     p.act = a->act; p.ldres = a->ldres;
-    p.out = a->out; p.ldo = a->ldo; p.store = a->store;
+    p.out = a->out; p.ldo = a->ldo; p.store = a->store; p.round_out = a->round_out;
     p.B = a->B; p.H = a->H; p.W = a->W;
     p.im2col = a->im2col;
     int NG = 256;
@@ -763,7 +767,7 @@ int turtle_gemm_tc_v1(const TurtleGemmArgs *a, void *stream) {
     p.Cout = Cout;
     p.bias = a->bias; p.scale = a->scale; p.res = a->res;
     p.act = a->act; p.ldres = a->ldres;
-    p.out = a->out; p.ldo = a->ldo; p.store = a->store;
+    p.out = a->out; p.ldo = a->ldo; p.store = a->store; p.round_out = a->round_out;
     p.B = a->B; p.H = a->H; p.W = a->W;
     p.im2col = a->im2col;
 

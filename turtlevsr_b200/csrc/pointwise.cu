@@ -176,7 +176,7 @@ extern "C" int turtle_conv3x3_last(const float *x, const float *w, const float *
 // ------------------------------------------------------------------------------------------
 template <bool VEC4>
 __global__ void layernorm_kernel(const float *__restrict__ x, int ldx, const float *__restrict__ w,
-                                 const float *__restrict__ b, float *__restrict__ y, int ldy, int64_t P, int C) {
+                                 const float *__restrict__ b, float *__restrict__ y, int ldy, int64_t P, int C, int rnd) {
     int lane = threadIdx.x & 31;
     int64_t p = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (p >= P) return;
@@ -230,13 +230,16 @@ __global__ void layernorm_kernel(const float *__restrict__ x, int ldx, const flo
                 o.y = (v[4 * i + 1] - sub) / den * wv.y + bv.y;
                 o.z = (v[4 * i + 2] - sub) / den * wv.z + bv.z;
                 o.w = (v[4 * i + 3] - sub) / den * wv.w + bv.w;
-                *reinterpret_cast<float4 *>(yp + c) = o;
+                *reinterpret_cast<float4 *>(yp + c) = rnd ? rna_tf32(o) : o;
             }
     } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             int c = lane + 32 * i;
-            if (c < C) yp[c] = (v[i] - sub) / den * w[c] + (b ? b[c] : 0.f);
+            if (c < C) {
+                float o = (v[i] - sub) / den * w[c] + (b ? b[c] : 0.f);
+                yp[c] = rnd ? rna_tf32(o) : o;
+            }
         }
     }
 }
@@ -246,7 +249,7 @@ __global__ void layernorm_kernel(const float *__restrict__ x, int ldx, const flo
 template <int NV, int G, int U>
 __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float *__restrict__ x, int ldx,
                                                             const float *__restrict__ w, const float *__restrict__ b,
-                                                            float *__restrict__ y, int ldy, int64_t P) {
+                                                            float *__restrict__ y, int ldy, int64_t P, int rnd) {
     constexpr int C = 4 * NV * G;
     constexpr int GPW = 32 / G;                       // pixel groups per warp
     const int lane = threadIdx.x & 31, gl = lane % G, gi = lane / G;
@@ -293,7 +296,7 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float *__restr
                 o.y = (v[u][i].y - sub) / den * wv[i].y + bv[i].y;
                 o.z = (v[u][i].z - sub) / den * wv[i].z + bv[i].z;
                 o.w = (v[u][i].w - sub) / den * wv[i].w + bv[i].w;
-                *reinterpret_cast<float4 *>(y + p * ldy + (i * G + gl) * 4) = o;
+                *reinterpret_cast<float4 *>(y + p * ldy + (i * G + gl) * 4) = rnd ? rna_tf32(o) : o;
             }
         }
     }
@@ -301,32 +304,33 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float *__restr
 
 template <int NV, int G, int U>
 static void launch_ln_vec(const float *x, int ldx, const float *w, const float *b, float *y, int ldy, int64_t P,
-                          cudaStream_t s) {
+                          int rnd, cudaStream_t s) {
     const int64_t per_warp = (32 / G) * U;
     const int64_t warps = cdiv64(P, per_warp);
-    layernorm_vec_kernel<NV, G, U><<<(unsigned)cdiv64(warps, 8), 256, 0, s>>>(x, ldx, w, b, y, ldy, P);
+    layernorm_vec_kernel<NV, G, U><<<(unsigned)cdiv64(warps, 8), 256, 0, s>>>(x, ldx, w, b, y, ldy, P, rnd);
 }
 
 extern "C" int turtle_layernorm(const float *x, int ldx, const float *w, const float *b, float *y, int ldy,
-                                int64_t P, int C, void *stream) {
+                                int64_t P, int C, int round_tf32, void *stream) {
     if (!x || !w || !y || C < 1 || C > 512 || P < 1) return TURTLE_EINVAL;
+    const int rnd = round_tf32;
     cudaStream_t s = as_stream(stream);
     const bool al = (ldx % 4 == 0) && (ldy % 4 == 0) &&
                     ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)w | (uintptr_t)b) & 15) == 0);
     if (al && (C == 64 || C == 128 || C == 256 || C == 512)) {
-        if (C == 64) launch_ln_vec<1, 16, 4>(x, ldx, w, b, y, ldy, P, s);
-        else if (C == 128) launch_ln_vec<1, 32, 4>(x, ldx, w, b, y, ldy, P, s);
-        else if (C == 256) launch_ln_vec<2, 32, 4>(x, ldx, w, b, y, ldy, P, s);
-        else launch_ln_vec<4, 32, 2>(x, ldx, w, b, y, ldy, P, s);
+        if (C == 64) launch_ln_vec<1, 16, 4>(x, ldx, w, b, y, ldy, P, rnd, s);
+        else if (C == 128) launch_ln_vec<1, 32, 4>(x, ldx, w, b, y, ldy, P, rnd, s);
+        else if (C == 256) launch_ln_vec<2, 32, 4>(x, ldx, w, b, y, ldy, P, rnd, s);
+        else launch_ln_vec<4, 32, 2>(x, ldx, w, b, y, ldy, P, rnd, s);
         TURTLE_CHECK_LAUNCH();
         return TURTLE_OK;
     }
     unsigned grid = (unsigned)cdiv64(P, 8);
     bool vec = (C % 128 == 0) && al;
     if (vec)
-        layernorm_kernel<true><<<grid, 256, 0, s>>>(x, ldx, w, b, y, ldy, P, C);
+        layernorm_kernel<true><<<grid, 256, 0, s>>>(x, ldx, w, b, y, ldy, P, C, rnd);
     else
-        layernorm_kernel<false><<<grid, 256, 0, s>>>(x, ldx, w, b, y, ldy, P, C);
+        layernorm_kernel<false><<<grid, 256, 0, s>>>(x, ldx, w, b, y, ldy, P, C, rnd);
     TURTLE_CHECK_LAUNCH();
     return TURTLE_OK;
 }
@@ -349,7 +353,7 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const float *__restrict_
                                                         const float *__restrict__ w9,
                                                         const float *__restrict__ bias, float *__restrict__ y,
                                                         int ldy, int NB, int H, int W, int C, int layout, int ws,
-                                                        int RY, int nstrips) {
+                                                        int RY, int nstrips, int rnd) {
     const int Cout = FUSE == 2 ? (C >> 1) : C;
     const int groups = Cout >> 2;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -404,6 +408,7 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const float *__restrict_
             o.x = gelu_erf(o.x) * a[NS - 1].x; o.y = gelu_erf(o.y) * a[NS - 1].y;
             o.z = gelu_erf(o.z) * a[NS - 1].z; o.w = gelu_erf(o.w) * a[NS - 1].w;
         }
+        if (rnd) o = rna_tf32(o);
         if (layout == 0) {
             stg_stream(y + ((nb * H + yy) * W + px) * ldy + c0, o);
         } else {
@@ -422,10 +427,11 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const float *__restrict_
 }
 
 int turtle_dwconv3x3_tma(const float *x, int ldx, const float *w, const float *bias, float *y, int ldy, int NB, int H,
-                         int W, int C, int fuse, int layout, int ws, void *stream);   // dwconv_tma.cu
+                         int W, int C, int fuse, int layout, int ws, int rnd, void *stream);   // dwconv_tma.cu
 
 extern "C" int turtle_dwconv3x3(const float *x, int ldx, const float *w, const float *bias, float *y, int ldy,
-                                int NB, int H, int W, int C, int fuse, int layout, int ws, void *stream) {
+                                int NB, int H, int W, int C, int fuse, int layout, int ws, int round_tf32, void *stream) {
+    const int rnd = round_tf32;
     if (!x || !w || !y || NB < 1 || C < 4 || fuse < 0 || fuse > 2 || (ldx & 3)) return TURTLE_EINVAL;
     int Cout = fuse == 2 ? C / 2 : C;
     if ((Cout & 3) || (fuse == 2 && (C & 7))) return TURTLE_EINVAL;
@@ -434,7 +440,7 @@ extern "C" int turtle_dwconv3x3(const float *x, int ldx, const float *w, const f
     if ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)w) & 15) != 0) return TURTLE_EINVAL;
     {
         // TMA halo-staged kernel for 32-channel-aligned maps; the register kernel below covers the rest
-        int r = turtle_dwconv3x3_tma(x, ldx, w, bias, y, ldy, NB, H, W, C, fuse, layout, ws, stream);
+        int r = turtle_dwconv3x3_tma(x, ldx, w, bias, y, ldy, NB, H, W, C, fuse, layout, ws, rnd, stream);
         if (r != TURTLE_ENOTSUP) return r;
     }
     int64_t cols = (int64_t)W * (Cout >> 2);
@@ -447,11 +453,11 @@ extern "C" int turtle_dwconv3x3(const float *x, int ldx, const float *w, const f
     dim3 grid(gx, (unsigned)(nstrips * NB));
     cudaStream_t s = as_stream(stream);
     if (fuse == 0)
-        dwconv3x3_kernel<0><<<grid, 256, 0, s>>>(x, ldx, w, bias, y, ldy, NB, H, W, C, layout, ws, RY, nstrips);
+        dwconv3x3_kernel<0><<<grid, 256, 0, s>>>(x, ldx, w, bias, y, ldy, NB, H, W, C, layout, ws, RY, nstrips, rnd);
     else if (fuse == 1)
-        dwconv3x3_kernel<1><<<grid, 256, 0, s>>>(x, ldx, w, bias, y, ldy, NB, H, W, C, layout, ws, RY, nstrips);
+        dwconv3x3_kernel<1><<<grid, 256, 0, s>>>(x, ldx, w, bias, y, ldy, NB, H, W, C, layout, ws, RY, nstrips, rnd);
     else
-        dwconv3x3_kernel<2><<<grid, 256, 0, s>>>(x, ldx, w, bias, y, ldy, NB, H, W, C, layout, ws, RY, nstrips);
+        dwconv3x3_kernel<2><<<grid, 256, 0, s>>>(x, ldx, w, bias, y, ldy, NB, H, W, C, layout, ws, RY, nstrips, rnd);
     TURTLE_CHECK_LAUNCH();
     return TURTLE_OK;
 }
@@ -513,7 +519,7 @@ extern "C" int turtle_add_posenc(const float *x, float *y, int B, int H, int W, 
     return TURTLE_OK;
 }
 
-extern "C" int turtle_abi_version(void) { return 1; }
+extern "C" int turtle_abi_version(void) { return 2; }
 extern "C" const char *turtle_build_info(void) {
     return "libturtle_b200 sm_100a, CUDA "
 #define TURTLE_STR2(x) #x

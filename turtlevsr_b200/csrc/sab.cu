@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(256) sab_aggregate_kernel(const int32_t *__res
                                                             const float *__restrict__ wgt,
                                                             const float *__restrict__ v, int64_t v_fstride,
                                                             float *__restrict__ y, int Hg, int Wg, int ws, int c,
-                                                            int passthrough) {
+                                                            int passthrough, int rnd) {
     __shared__ int sid[TURTLE_SAB_SLOTS];
     __shared__ float sw[TURTLE_SAB_SLOTS];
     __shared__ int cnt;
@@ -303,6 +303,7 @@ __global__ void __launch_bounds__(256) sab_aggregate_kernel(const int32_t *__res
         int pp = (int)(e4 / c4), d = (int)(e4 % c4) * 4;
         int p1 = pp / ws, p2 = pp % ws;
         int yy = p1 * Hg + gi, xx = p2 * Wg + gj;
+        if (rnd) acc = rna_tf32(acc);
         stg_stream(y + (((int64_t)f * H + yy) * W + xx) * c + d, acc);
     }
 }
@@ -339,11 +340,11 @@ extern "C" int turtle_sab_select(const float *qn, const float *kn, int64_t k_fst
 }
 
 extern "C" int turtle_sab_aggregate(const int32_t *idx, const float *wgt, const float *v, int64_t v_fstride, float *y,
-                                    int F, int Hg, int Wg, int ws, int c, int passthrough, void *stream) {
+                                    int F, int Hg, int Wg, int ws, int c, int passthrough, int round_tf32, void *stream) {
     if (!v || !y || F < 1 || (c & 3) || ws < 1) return TURTLE_EINVAL;
     if (!passthrough && (!idx || !wgt)) return TURTLE_EINVAL;
     dim3 grid(Hg * Wg, F);
-    sab_aggregate_kernel<<<grid, 256, 0, as_stream(stream)>>>(idx, wgt, v, v_fstride, y, Hg, Wg, ws, c, passthrough);
+    sab_aggregate_kernel<<<grid, 256, 0, as_stream(stream)>>>(idx, wgt, v, v_fstride, y, Hg, Wg, ws, c, passthrough, round_tf32);
     TURTLE_CHECK_LAUNCH();
     return TURTLE_OK;
 }

@@ -110,7 +110,8 @@ class FrameEngine:
 
     def _w(self, name: str, kind: str = "raw") -> Optional[torch.Tensor]:
         """Device weight in the layout the kernels want (packed once, cached)."""
-        key = f"{kind}:{name}"
+        tf32 = self.mode == capi.TF32 and kind in ("gemm", "conv3")
+        key = f"{kind}{'@tf32' if tf32 else ''}:{name}"
         t = self.packed.get(key)
         if t is not None:
             return t
@@ -120,7 +121,7 @@ class FrameEngine:
         p = p.detach()
         if p.dtype != torch.float32:
             p = p.float()
-        if kind == "raw":                 # 1x1 conv [Cout,Cin,1,1], vectors, beta/gamma, temperature
+        if kind == "raw" or kind == "gemm":   # vectors, beta/gamma, temperature / 1x1 conv [Cout,Cin,1,1]
             t = p.contiguous()
         elif kind == "dw":                # [C,1,k,k] -> tap-major [k*k, C]
             t = p.reshape(p.shape[0], -1).t().contiguous()
@@ -132,6 +133,9 @@ class FrameEngine:
             t = p.permute(0, 2, 3, 1).reshape(p.shape[0], -1).contiguous()
         else:
             raise ValueError(kind)
+        if tf32:
+            # round the tensor-core weights to nearest TF32 once (the MMA would otherwise truncate them)
+            t = ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
         self.packed[key] = t
         return t
 
@@ -139,8 +143,8 @@ class FrameEngine:
     # kernel wrappers
     # ------------------------------------------------------------------------------------
     def gemm(self, segs, segw, Wt, out, ldo, P, Cout, bias=None, scale=None, act=0, res=None, ldres=0,
-             im2col=0, geom=None, store=0):
-        """segs: list of (ptr:int, lda:int)."""
+             im2col=0, geom=None, store=0, round_out=False):
+        """segs: list of (ptr:int, lda:int).  round_out: the result feeds another tensor-core op."""
         a = GemmArgs()
         a.mode = self.mode
         a.im2col = im2col
@@ -162,6 +166,7 @@ class FrameEngine:
         a.out = out
         a.ldo = ldo
         a.store = store
+        a.round_out = 1 if (round_out and self.mode == capi.TF32) else 0
         if self.profile is not None:
             K = (9 if im2col else len(segs)) * segw
             self._meta = (4 * (P * K + Cout * K + P * Cout * (2 if res else 1)), 2 * P * K * Cout)
@@ -188,19 +193,20 @@ class FrameEngine:
         self._meta = (0, 0)
 
     def conv1x1(self, x, ldx, Cin, wname, out, ldo, P, Cout, **kw):
-        self.gemm([(x, ldx)], Cin, self._w(wname), out, ldo, P, Cout, **kw)
+        self.gemm([(x, ldx)], Cin, self._w(wname, "gemm"), out, ldo, P, Cout, **kw)
 
     def layernorm(self, x: torch.Tensor, pre: str, C_: int, P: int) -> torch.Tensor:
         y = self.ws.get("xn", P, C_)
         self._meta = (8 * P * C_, 0)
         self._call("turtle_layernorm", _ptr(x), C_, _ptr(self._w(pre + "body.weight")), _ptr(self._w(pre + "body.bias")),
-             _ptr(y), C_, P, C_, self.stream)
+             _ptr(y), C_, P, C_, self.rnd, self.stream)
         return y
 
-    def dwconv(self, x, ldx, wname, bname, y, ldy, NB, H, W, Cc, fuse=0, layout=0, ws=1, wkind="dw"):
+    def dwconv(self, x, ldx, wname, bname, y, ldy, NB, H, W, Cc, fuse=0, layout=0, ws=1, wkind="dw", rnd=None):
+        rnd = (self.rnd if layout == 0 else 0) if rnd is None else rnd      # ring / patch rows stay unrounded
         self._meta = (4 * NB * H * W * (Cc + (Cc // 2 if fuse == 2 else Cc)), 2 * 9 * NB * H * W * Cc)
         self._call("turtle_dwconv3x3", x, ldx, _ptr(self._w(wname, wkind)), _ptr(self._w(bname)) if bname else None, y, ldy,
-             NB, H, W, Cc, fuse, layout, ws, self.stream)
+             NB, H, W, Cc, fuse, layout, ws, rnd, self.stream)
 
     # ------------------------------------------------------------------------------------
     # feed-forwards (x updated in place)
@@ -219,7 +225,7 @@ class FrameEngine:
     def plain_ffw(self, pre, xn, x, P, c):
         t = self.ws.get("wide", P, 2 * c)
         self.conv1x1(_ptr(xn), c, c, pre + "conv4.weight", _ptr(t), 2 * c, P, 2 * c, bias=self._w(pre + "conv4.bias"),
-                     act=capi.ACT_GELU)
+                     act=capi.ACT_GELU, round_out=True)
         self.conv1x1(_ptr(t), 2 * c, 2 * c, pre + "conv5.weight", _ptr(x), c, P, c, bias=self._w(pre + "conv5.bias"),
                      scale=self._w(pre + "gamma"), res=_ptr(x), ldres=c)
 
@@ -272,7 +278,7 @@ class FrameEngine:
             self._call("turtle_chan_softmax", _ptr(gpart), _ptr(sqq), _ptr(sqk), _ptr(flags), _ptr(temp), S, nsplit, heads,
                  ch, _ptr(Pm), _ptr(inv), self.stream)
             M = self.ws.get("attnM", c, S * c)
-            self._call("turtle_chan_fold", _ptr(Pm), _ptr(Wo), S, heads, ch, _ptr(M), self.stream)
+            self._call("turtle_chan_fold", _ptr(Pm), _ptr(Wo), S, heads, ch, _ptr(M), self.rnd, self.stream)
             vsegs = [(sg["v"] + 4 * h * sg["vhs"], sg["ldv"]) for sg in segs for h in range(heads)]
             xb = _ptr(x, b * Pimg * c)
             self.gemm(vsegs, ch, M, xb, c, Pimg, c, bias=self._w(pre + "project_out.bias"), res=xb, ldres=c)
@@ -388,11 +394,11 @@ class FrameEngine:
                                _ptr(idx[b]), _ptr(wgt[b]), self.mode, self.stream)
             self._meta = (4 * (2 * F_ * N * Dv + 2 * F_ * N * capi.SAB_SLOTS), 2 * F_ * N * 46 * Dv)
             self._call("turtle_sab_aggregate", _ptr(idx[b]), _ptr(wgt[b]), vf, N * Dv, _ptr(agg[b]), F_, Hg, Wg, ws_, c,
-                 1 if t0 else 0, self.stream)
+                 1 if t0 else 0, self.rnd, self.stream)
         if self.trace is not None:
             self.trace.setdefault(sa, []).append(dict(idx=idx.clone(), wgt=wgt.clone(), qn=qn.clone()))
         xs = self.ws.get("sab_xs", B, F_, Pimg, c)
-        self.conv1x1(_ptr(agg), c, c, sa + "project_out.weight", _ptr(xs), c, B * F_ * Pimg, c)
+        self.conv1x1(_ptr(agg), c, c, sa + "project_out.weight", _ptr(xs), c, B * F_ * Pimg, c, round_out=True)
         ring.commit()
         k_out, v_out = ring.views()
 
@@ -463,9 +469,9 @@ class FrameEngine:
                 self.block(pre, blk, x, B, H, W, lvl.dim, lvl)
         return out
 
-    def conv3x3(self, x, Cin, wname, out, ldo, B, H, W, Cout, store):
+    def conv3x3(self, x, Cin, wname, out, ldo, B, H, W, Cout, store, round_out=False):
         self.gemm([(_ptr(x), Cin)], Cin, self._w(wname, "conv3"), _ptr(out), ldo, B * H * W, Cout, im2col=1,
-                  geom=(B, H, W), store=store)
+                  geom=(B, H, W), store=store, round_out=round_out)
 
     # ------------------------------------------------------------------------------------
     # whole frame
@@ -486,6 +492,7 @@ class FrameEngine:
             self.packed.clear()
         self._sd = dict(m.named_parameters())
         self.mode = capi.TF32 if m.precision == "tf32" else capi.FP32
+        self.rnd = 1 if self.mode == capi.TF32 else 0
         self.trace = {} if getattr(m, "record_trace", False) else None
         inp = inp.float().contiguous()
         B, _, Cc, Hs, Ws = inp.shape
@@ -530,9 +537,9 @@ class FrameEngine:
                 # Upsample: 3x3 Cl->2Cl + PixelShuffle(2) => [2Hl,2Wl,Cl/2]; cat(skip) ; 1x1 Cl->Cl/2
                 Ch = Cl // 2
                 u = ws.get("up", B * 4 * Hl * Wl, Ch)
-                self.conv3x3(xlow, Cl, upname + ".body.0.weight", u, Ch, B, Hl, Wl, 2 * Cl, capi.STORE_SHUFFLE2)
+                self.conv3x3(xlow, Cl, upname + ".body.0.weight", u, Ch, B, Hl, Wl, 2 * Cl, capi.STORE_SHUFFLE2, round_out=True)
                 d = ws.get(outname, B * 4 * Hl * Wl, Ch)
-                self.gemm([(_ptr(u), Ch), (_ptr(skip), Ch)], Ch, self._w(redname + ".weight"), _ptr(d), Ch,
+                self.gemm([(_ptr(u), Ch), (_ptr(skip), Ch)], Ch, self._w(redname + ".weight", "gemm"), _ptr(d), Ch,
                           B * 4 * Hl * Wl, Ch, bias=self._w(redname + ".bias"))
                 return d
 
