@@ -138,7 +138,7 @@ def test_pack_frame_first_last(up):
     call("turtle_conv3x3_last", y1.data_ptr(), dp(w2), dp(b2), dst.data_ptr(), 3, 0,
          out.data_ptr(), B, Hp, Wp, 16, 3, H, W, stream())
     ref = (F.conv2d(F.conv2d(want, w1, padding=1), w2, b2, padding=1) + want)[:, :, :H, :W]
-    assert (out.cpu() - ref).abs().max() < 5e-5
+    assert (out.cpu() - ref).abs().max() < 1e-4
 
 
 @pytest.mark.parametrize("mode", [capi.FP32, capi.TF32])

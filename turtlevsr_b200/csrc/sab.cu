@@ -308,6 +308,98 @@ __global__ void __launch_bounds__(256) sab_aggregate_kernel(const int32_t *__res
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// aggregate, 2x2 query quads: the four queries of a quad share most of their local windows, so the
+// block first merges their entry lists into one list of distinct keys with four weights each
+// (10x10 window box around the quad + far top-k keys), then every thread streams each V row chunk ONCE
+// and accumulates into the four outputs: ~20 row reads per output instead of 46.
+// ------------------------------------------------------------------------------------------
+constexpr int QB = 10;                    // window box edge: 2 queries + 4 on each side
+constexpr int QMAX = QB * QB + 4 * 5;     // distinct keys: box slots + far top-k entries
+
+__global__ void __launch_bounds__(256) sab_aggregate_quad_kernel(const int32_t *__restrict__ idx,
+                                                                 const float *__restrict__ wgt,
+                                                                 const float *__restrict__ v, int64_t v_fstride,
+                                                                 float *__restrict__ y, int Hg, int Wg, int ws, int c,
+                                                                 int quads_x, int rnd) {
+    __shared__ float bw[QB * QB][4];      // weight of window-box key for each of the 4 queries
+    __shared__ int ekey[QMAX];
+    __shared__ float4 ew[QMAX];
+    __shared__ int ecount;
+    const int tid = threadIdx.x, f = blockIdx.y;
+    const int qy0 = (blockIdx.x / quads_x) * 2, qx0 = (blockIdx.x % quads_x) * 2;
+    const int wy0 = qy0 - 4, wx0 = qx0 - 4;
+    const int N = Hg * Wg, H = Hg * ws, W = Wg * ws;
+    const int64_t Dv = (int64_t)ws * ws * c;
+    for (int i = tid; i < QB * QB * 4; i += 256) (&bw[0][0])[i] = 0.f;
+    if (tid == 0) ecount = 0;
+    __syncthreads();
+    // scatter the (<=4 x 46) entries: box keys accumulate into bw, far keys are appended
+    if (tid < 4 * 46) {
+        const int q = tid / 46, t = tid % 46;
+        const int qy = qy0 + (q >> 1), qx = qx0 + (q & 1);
+        if (qy < Hg && qx < Wg) {
+            const int64_t base = ((int64_t)f * N + (int64_t)qy * Wg + qx) * TURTLE_SAB_SLOTS;
+            const int id = idx[base + t];
+            const float w = wgt[base + t];
+            if (id >= 0 && w != 0.f) {
+                const int ry = id / Wg - wy0, rx = id % Wg - wx0;
+                if (ry >= 0 && ry < QB && rx >= 0 && rx < QB) {
+                    bw[ry * QB + rx][q] = w;             // a key appears at most once per query
+                } else {
+                    const int e = atomicAdd(&ecount, 1);
+                    ekey[e] = id;
+                    ew[e] = make_float4(q == 0 ? w : 0.f, q == 1 ? w : 0.f, q == 2 ? w : 0.f, q == 3 ? w : 0.f);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // compact the box slots that carry any weight (one warp, ballot-ordered)
+    if (tid < 32) {
+        int base = ecount;
+        for (int s0 = 0; s0 < QB * QB; s0 += 32) {
+            const int sidx = s0 + tid;
+            float4 w4 = make_float4(0, 0, 0, 0);
+            if (sidx < QB * QB) w4 = make_float4(bw[sidx][0], bw[sidx][1], bw[sidx][2], bw[sidx][3]);
+            const bool live = (w4.x != 0.f) | (w4.y != 0.f) | (w4.z != 0.f) | (w4.w != 0.f);
+            const unsigned m = __ballot_sync(0xffffffffu, live);
+            if (live) {
+                const int e = base + __popc(m & ((1u << tid) - 1));
+                ekey[e] = (wy0 + sidx / QB) * Wg + (wx0 + sidx % QB);
+                ew[e] = w4;
+            }
+            base += __popc(m);
+        }
+        if (tid == 0) ecount = base;
+    }
+    __syncthreads();
+    const int m = ecount;
+    const float *vf = v + (int64_t)f * v_fstride;
+    const int c4 = c >> 2;
+    for (int64_t e4 = tid; e4 < (Dv >> 2); e4 += 256) {
+        float4 a0 = make_float4(0, 0, 0, 0), a1 = a0, a2 = a0, a3 = a0;
+#pragma unroll 4
+        for (int t = 0; t < m; ++t) {
+            const float4 x = __ldg(reinterpret_cast<const float4 *>(vf + (int64_t)ekey[t] * Dv) + e4);
+            const float4 w = ew[t];
+            a0.x = fmaf(w.x, x.x, a0.x); a0.y = fmaf(w.x, x.y, a0.y); a0.z = fmaf(w.x, x.z, a0.z); a0.w = fmaf(w.x, x.w, a0.w);
+            a1.x = fmaf(w.y, x.x, a1.x); a1.y = fmaf(w.y, x.y, a1.y); a1.z = fmaf(w.y, x.z, a1.z); a1.w = fmaf(w.y, x.w, a1.w);
+            a2.x = fmaf(w.z, x.x, a2.x); a2.y = fmaf(w.z, x.y, a2.y); a2.z = fmaf(w.z, x.z, a2.z); a2.w = fmaf(w.z, x.w, a2.w);
+            a3.x = fmaf(w.w, x.x, a3.x); a3.y = fmaf(w.w, x.y, a3.y); a3.z = fmaf(w.w, x.z, a3.z); a3.w = fmaf(w.w, x.w, a3.w);
+        }
+        const int pp = (int)(e4 / c4), d = (int)(e4 % c4) * 4;
+        const int p1 = pp / ws, p2 = pp % ws;
+        const float4 acc[4] = {a0, a1, a2, a3};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int qy = qy0 + (q >> 1), qx = qx0 + (q & 1);
+            if (qy < Hg && qx < Wg)
+                stg_stream(y + (((int64_t)f * H + p1 * Hg + qy) * W + p2 * Wg + qx) * c + d, rnd ? rna_tf32(acc[q]) : acc[q]);
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int turtle_sab_window_reduce(const float *t, int ldt, const float *w, float *out, int64_t out_bstride,
@@ -343,6 +435,14 @@ extern "C" int turtle_sab_aggregate(const int32_t *idx, const float *wgt, const 
                                     int F, int Hg, int Wg, int ws, int c, int passthrough, int round_tf32, void *stream) {
     if (!v || !y || F < 1 || (c & 3) || ws < 1) return TURTLE_EINVAL;
     if (!passthrough && (!idx || !wgt)) return TURTLE_EINVAL;
+    if (!passthrough && !(((uintptr_t)v | (uintptr_t)y) & 15) && !(v_fstride & 3)) {
+        const int quads_x = (Wg + 1) / 2, quads_y = (Hg + 1) / 2;
+        dim3 grid(quads_x * quads_y, F);
+        sab_aggregate_quad_kernel<<<grid, 256, 0, as_stream(stream)>>>(idx, wgt, v, v_fstride, y, Hg, Wg, ws, c, quads_x,
+                                                                      round_tf32);
+        TURTLE_CHECK_LAUNCH();
+        return TURTLE_OK;
+    }
     dim3 grid(Hg * Wg, F);
     sab_aggregate_kernel<<<grid, 256, 0, as_stream(stream)>>>(idx, wgt, v, v_fstride, y, Hg, Wg, ws, c, passthrough, round_tf32);
     TURTLE_CHECK_LAUNCH();
