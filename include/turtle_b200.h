@@ -17,7 +17,8 @@
  *     Nothing allocates, synchronises or throws; the caller owns all buffers;
  *   - `round_tf32` (producer kernels) / `round_out` (gemm): in TURTLE_TF32 mode the host asks producers whose
  *     output feeds a tensor-core contraction to round it to nearest TF32 (cvt.rna), so that the tensor core's
- *     operand truncation is exact and unbiased; pass 0 in TURTLE_FP32 mode;
+ *     operand truncation is exact and unbiased; pass 0 in TURTLE_FP32 mode.  The same flag (and TURTLE_TF32 in
+ *     turtle_gemm) selects a 1.5e-7-accurate polynomial erf for the fused GELUs instead of erff;
  *   - `mode`: TURTLE_FP32 = CUDA-core fp32 FMA (exact mode: bit-exact top-k contract),
  *             TURTLE_TF32 = tcgen05 tensor cores, TF32 operands, fp32 accumulate in TMEM.
  */

@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(128) gemm_tc_kernel(const __grid_constant__ Tc
                 }
                 if (p.act == TURTLE_ACT_GELU) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) v[4 * q + e] = gelu_erf(v[4 * q + e]);
+                    for (int e = 0; e < 4; ++e) v[4 * q + e] = gelu_fast(v[4 * q + e]);
                 }
                 if (p.scale) {
                     float4 sc = __ldg(reinterpret_cast<const float4 *>(p.scale + o));
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
                         }
                         if (p.act == TURTLE_ACT_GELU) {
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) v[4 * q + e] = gelu_erf(v[4 * q + e]);
+                            for (int e = 0; e < 4; ++e) v[4 * q + e] = gelu_fast(v[4 * q + e]);
                         }
                         if (p.scale) {
                             float4 sc = __ldg(reinterpret_cast<const float4 *>(p.scale + o));
