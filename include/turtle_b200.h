@@ -118,6 +118,9 @@ typedef struct TurtleGemmArgs {
     int32_t ldo;
     int32_t store;       /* TURTLE_STORE_* */
     int32_t round_out;   /* !=0: round the stored values to nearest TF32 (they feed another tensor-core op) */
+    int32_t a_dtype;     /* 0: A segments and Wt are fp32 (TF32 MMA); 1: they are fp16 (kind::f16 MMA). TURTLE_TF32 only;
+                            lda counts elements of that type, the pointers are carried in the float* slots */
+    int32_t out_dtype;   /* 0: out is fp32; 1: out is fp16 (ldo in halves; no residual, plain store) */
 } TurtleGemmArgs;
 
 int turtle_gemm(const TurtleGemmArgs *args, void *stream);

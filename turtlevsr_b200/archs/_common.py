@@ -282,6 +282,7 @@ class TurtleNet(nn.Module):
         self.padder_size = (2 ** 3) * 4
         # execution state (not part of the state dict)
         self.precision = "fp32"        # "fp32": CUDA-core fp32 everywhere; "tf32": tcgen05 TF32 contractions
+        self.half_intermediates = True  # tf32 mode: FFN-side intermediates stored fp16 (same 10-bit mantissa as TF32)
         self._engine = None
 
     # -- public knobs ------------------------------------------------------------------

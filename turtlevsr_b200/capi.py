@@ -26,7 +26,7 @@ class GemmArgs(C.Structure):
         ("mode", _i32), ("im2col", _i32), ("P", _i64), ("B", _i32), ("H", _i32), ("W", _i32), ("Cout", _i32),
         ("nseg", _i32), ("segw", _i32), ("A", _fp * MAX_SEG), ("lda", _i32 * MAX_SEG), ("Wt", _fp),
         ("bias", _fp), ("scale", _fp), ("act", _i32), ("res", _fp), ("ldres", _i32), ("out", _fp),
-        ("ldo", _i32), ("store", _i32), ("round_out", _i32),
+        ("ldo", _i32), ("store", _i32), ("round_out", _i32), ("a_dtype", _i32), ("out_dtype", _i32),
     ]
 
 

@@ -8,17 +8,18 @@
 // produces a 4-row column of one float4 channel group with a register sliding window (18 LDS.128
 // per 4 outputs) and stores full 128-byte channel runs.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
-bool turtle_get_tmap(CUtensorMap *out, const void *ptr, int rank, const uint64_t *dims, const uint64_t *strides,
-                     const uint32_t *box, int swizzle128);
+bool turtle_get_tmap2(CUtensorMap *out, const void *ptr, int rank, const uint64_t *dims, const uint64_t *strides,
+                      const uint32_t *box, int swizzle128, int dtype);
 
 namespace {
 
 constexpr int TH = 8, TW = 16, CK = 32;
 constexpr int HR = TH + 2, HC = TW + 2;
-constexpr int BOX_BYTES = HR * HC * CK * 4;   // 23040
+constexpr int BOX_BYTES = HR * HC * CK * 4;   // 23040 (fp32); the fp16 variant uses half of it
 
 struct alignas(64) DwParams {
     CUtensorMap map;
@@ -38,9 +39,10 @@ __device__ __forceinline__ void fma4(float4 &a, const float4 &x, const float4 &w
     a.w = fmaf(x.w, w.w, a.w);
 }
 
-template <int FUSE, bool FAST>
+template <int FUSE, bool FAST, bool IO16>
 __global__ void __launch_bounds__(256, 2) dwconv_tma_kernel(const __grid_constant__ DwParams p) {
     constexpr int NS = FUSE == 2 ? 2 : 1;
+    constexpr int BOXB = IO16 ? BOX_BYTES / 2 : BOX_BYTES;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[2];
     const uint32_t smem0 = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -64,13 +66,13 @@ __global__ void __launch_bounds__(256, 2) dwconv_tma_kernel(const __grid_constan
         int cb, tx, ty, nb;
         decode(it, cb, tx, ty, nb);
         const uint32_t bar = smem_u32(&full_bar[buf]);
-        const uint32_t dst = smem0 + buf * (NS * BOX_BYTES);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(NS * BOX_BYTES) : "memory");
+        const uint32_t dst = smem0 + buf * (NS * BOXB);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(NS * BOXB) : "memory");
 #pragma unroll
         for (int s = 0; s < NS; ++s)
             asm volatile(
                 "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
-                    "r"(dst + s * BOX_BYTES),
+                    "r"(dst + s * BOXB),
                 "l"(&p.map), "r"(bar), "r"(cb * CK + s * p.Cout), "r"(tx * TW - 1), "r"(ty * TH - 1), "r"(nb)
                 : "memory");
     };
@@ -106,8 +108,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_tma_kernel(const __grid_constan
         }
         const int px = tx * TW + col;
         const int py0 = ty * TH + half * 4;
-        const float *sbase = reinterpret_cast<const float *>(smem_raw) + ((smem0 - smem_u32(smem_raw)) >> 2) +
-                             buf * (NS * BOX_BYTES / 4);
+        const uint8_t *sbase = smem_raw + (smem0 - smem_u32(smem_raw)) + buf * (NS * BOXB);
         // smem box layout [HR][HC][CK]; output (r, col) reads rows r..r+2, cols col..col+2.
         // One channel set at a time (the gated variant has two) keeps the register window small.
         float4 acc[NS][4];
@@ -119,12 +120,21 @@ __global__ void __launch_bounds__(256, 2) dwconv_tma_kernel(const __grid_constan
                 wv[t] = __ldg(reinterpret_cast<const float4 *>(p.w9 + t * p.C + c0 + s * p.Cout));
             const float4 bv =
                 p.bias ? __ldg(reinterpret_cast<const float4 *>(p.bias + c0 + s * p.Cout)) : make_float4(0, 0, 0, 0);
-            const float *sb = sbase + s * (BOX_BYTES / 4) + c4 * 4;
+            const uint8_t *sb = sbase + s * BOXB;
             float4 r[3][3];
             auto ld_row = [&](int slot, int rr) {
 #pragma unroll
-                for (int dx = 0; dx < 3; ++dx)
-                    r[slot][dx] = *reinterpret_cast<const float4 *>(sb + (rr * HC + col + dx) * CK);
+                for (int dx = 0; dx < 3; ++dx) {
+                    const int e = (rr * HC + col + dx) * CK + c4 * 4;       // element index inside the box
+                    if (IO16) {
+                        const uint2 u = *reinterpret_cast<const uint2 *>(sb + e * 2);
+                        const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&u.x));
+                        const float2 hi = __half22float2(*reinterpret_cast<const __half2 *>(&u.y));
+                        r[slot][dx] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                    } else {
+                        r[slot][dx] = *reinterpret_cast<const float4 *>(sb + e * 4);
+                    }
+                }
             };
             ld_row(0, half * 4);
             ld_row(1, half * 4 + 1);
@@ -154,10 +164,15 @@ __global__ void __launch_bounds__(256, 2) dwconv_tma_kernel(const __grid_constan
                 o.x = gelu_sel<FAST>(o.x) * g.x; o.y = gelu_sel<FAST>(o.y) * g.y;
                 o.z = gelu_sel<FAST>(o.z) * g.z; o.w = gelu_sel<FAST>(o.w) * g.w;
             }
-            if (p.rnd) o = rna_tf32(o);
+            if (!IO16 && p.rnd) o = rna_tf32(o);
             const int py = py0 + i;
             if (py < p.H && px < p.W) {
-                if (p.layout == 0) {
+                if (IO16) {
+                    __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+                    uint2 pk = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+                    *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(p.y) +
+                                               (((long long)nb * p.H + py) * p.W + px) * p.ldy + c0) = pk;
+                } else if (p.layout == 0) {
                     stg_stream(p.y + (((long long)nb * p.H + py) * p.W + px) * p.ldy + c0, o);
                 } else {
                     long long n = (long long)(py % Hg) * Wg + (px % Wg);
@@ -170,14 +185,14 @@ __global__ void __launch_bounds__(256, 2) dwconv_tma_kernel(const __grid_constan
     }
 }
 
-template <int FUSE, bool FAST>
+template <int FUSE, bool FAST, bool IO16>
 int launch(const DwParams &p, cudaStream_t s) {
     constexpr int NS = FUSE == 2 ? 2 : 1;
-    const size_t smem = 2 * NS * BOX_BYTES + 128;
+    const size_t smem = 2 * NS * (IO16 ? BOX_BYTES / 2 : BOX_BYTES) + 128;
     static bool configured = false;
     static int nsm = 148;
     if (!configured) {
-        if (cudaFuncSetAttribute(dwconv_tma_kernel<FUSE, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        if (cudaFuncSetAttribute(dwconv_tma_kernel<FUSE, FAST, IO16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
             cudaSuccess)
             return TURTLE_ELAUNCH;
         int dev = 0;
@@ -188,7 +203,7 @@ int launch(const DwParams &p, cudaStream_t s) {
     const int per_sm = NS == 2 ? 2 : 4;
     long long grid = (long long)nsm * per_sm;
     if (grid > p.nitems) grid = p.nitems;
-    dwconv_tma_kernel<FUSE, FAST><<<(unsigned)grid, 256, smem, s>>>(p);
+    dwconv_tma_kernel<FUSE, FAST, IO16><<<(unsigned)grid, 256, smem, s>>>(p);
     return cudaGetLastError() == cudaSuccess ? TURTLE_OK : TURTLE_ELAUNCH;
 }
 
@@ -199,11 +214,14 @@ int turtle_dwconv3x3_tma(const float *x, int ldx, const float *w, const float *b
                          int W, int C, int fuse, int layout, int ws, int rnd, void *stream) {
     const int Cout = fuse == 2 ? C / 2 : C;
     if (Cout % CK) return TURTLE_ENOTSUP;
+    const bool io16 = rnd == 2;
+    if (io16 && (layout != 0 || fuse == 0)) return TURTLE_ENOTSUP;
+    const uint64_t es = io16 ? 2 : 4;
     DwParams p{};
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
-    uint64_t str[3] = {(uint64_t)ldx * 4, (uint64_t)ldx * 4 * W, (uint64_t)ldx * 4 * W * H};
+    uint64_t str[3] = {(uint64_t)ldx * es, (uint64_t)ldx * es * W, (uint64_t)ldx * es * W * H};
     uint32_t box[4] = {CK, HC, HR, 1};
-    if (!turtle_get_tmap(&p.map, x, 4, dims, str, box, 0)) return TURTLE_ENOTSUP;
+    if (!turtle_get_tmap2(&p.map, x, 4, dims, str, box, 0, io16 ? 1 : 0)) return TURTLE_ENOTSUP;
     p.w9 = w; p.bias = bias; p.y = y; p.ldy = ldy;
     p.NB = NB; p.H = H; p.W = W; p.C = C; p.Cout = Cout; p.fuse = fuse; p.layout = layout; p.ws = ws; p.rnd = rnd;
     p.tiles_x = (W + TW - 1) / TW;
@@ -213,7 +231,8 @@ int turtle_dwconv3x3_tma(const float *x, int ldx, const float *w, const float *b
     cudaStream_t s = as_stream(stream);
     if (p.nitems >= (1LL << 31)) return TURTLE_ENOTSUP;
     // rnd marks the tensor-core (tf32) mode: its 1e-3-class numerics admit the 1.5e-7-accurate fast erf
-    if (fuse == 0) return launch<0, false>(p, s);
-    if (fuse == 1) return rnd ? launch<1, true>(p, s) : launch<1, false>(p, s);
-    return rnd ? launch<2, true>(p, s) : launch<2, false>(p, s);
+    if (io16) return fuse == 1 ? launch<1, true, true>(p, s) : launch<2, true, true>(p, s);
+    if (fuse == 0) return launch<0, false, false>(p, s);
+    if (fuse == 1) return rnd ? launch<1, true, false>(p, s) : launch<1, false, false>(p, s);
+    return rnd ? launch<2, true, false>(p, s) : launch<2, false, false>(p, s);
 }

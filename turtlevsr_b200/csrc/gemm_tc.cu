@@ -18,6 +18,7 @@
 //   zero-filled by the TMA unit, which is exactly the conv's zero padding.
 #include <cuda.h>
 #include <cudaTypedefs.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 #include <mutex>
@@ -297,6 +298,7 @@ constexpr int EPI_WARPS = 8;
 constexpr int EPI_BUF = 32 * 128;                       // one 32-row x 32-column staging box (4 KB)
 constexpr int EPI_BYTES = EPI_WARPS * 2 * EPI_BUF;      // 64 KB
 
+template <bool A16, bool O16>
 __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant__ Tc2Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2], rfull_bar[EPI_WARPS][2];
@@ -351,20 +353,23 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
                 const uint32_t fb = smem_u32(&full_bar[stage]);
                 const uint32_t sa = smem0 + stage * stage_bytes;
                 mbar_expect_tx(fb, A_STAGE_BYTES + (uint32_t)NG * TK * 4);
+                constexpr int KE = A16 ? 64 : 32;       // K elements per 128-byte k-block
                 const int seg = kb / p.kb_per_seg, r = kb - seg * p.kb_per_seg;
                 if (p.im2col) {
-                    tma_load_4d(sa, &p.mapA[0], r * TK, tx0 + seg % 3 - 1, ty0 + seg / 3 - 1, tb, fb);
+                    tma_load_4d(sa, &p.mapA[0], r * KE, tx0 + seg % 3 - 1, ty0 + seg / 3 - 1, tb, fb);
                 } else {
                     const int sub = r / p.kb_per_sub;
-                    tma_load_3d(sa, &p.mapA[seg], (r - sub * p.kb_per_sub) * TK, sub, m0, fb);
+                    tma_load_3d(sa, &p.mapA[seg], (r - sub * p.kb_per_sub) * KE, sub, m0, fb);
                 }
-                tma_load_2d(sa + A_STAGE_BYTES, &p.mapW, kb * TK, ng * NG, fb);
+                tma_load_2d(sa + A_STAGE_BYTES, &p.mapW, kb * KE, ng * NG, fb);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1 && lane == 0) {
         // ------------------------------ MMA issuer ------------------------------
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NG >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+        // D=f32; A,B = tf32 (format 2, K=8 per MMA) or fp16 (format 0, K=16 per MMA); both K-major
+        const uint32_t fmt = A16 ? 0u : 2u;
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NG >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
@@ -379,8 +384,10 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
                 const uint32_t sa = smem0 + stage * stage_bytes;
                 const uint32_t sb = sa + A_STAGE_BYTES;
 #pragma unroll
-                for (int k = 0; k < TK / 8; ++k)
-                    umma_tf32(tacc, make_desc(sa + k * 32), make_desc(sb + k * 32), idesc, (kb | k) ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) {       // 4 x 32 B of K per 128 B swizzle row
+                    if (A16) umma_f16(tacc, make_desc(sa + k * 32), make_desc(sb + k * 32), idesc, (kb | k) ? 1u : 0u);
+                    else umma_tf32(tacc, make_desc(sa + k * 32), make_desc(sb + k * 32), idesc, (kb | k) ? 1u : 0u);
+                }
                 umma_commit(smem_u32(&empty_bar[stage]));
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
@@ -436,6 +443,22 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
                             v[4 * q] *= sc.x; v[4 * q + 1] *= sc.y; v[4 * q + 2] *= sc.z; v[4 * q + 3] *= sc.w;
                         }
                     }
+                    if (O16) {
+                        // fp16 output: 32 rows x 64 B, SWIZZLE_64B (16 B chunk ^= (row>>1)&3)
+                        const uint32_t rowaddr = buf + lane * 64;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const uint32_t addr = rowaddr + (((uint32_t)q ^ (((uint32_t)lane >> 1) & 3u)) << 4);
+                            __half2 h0 = __floats2half2_rn(v[8 * q + 0], v[8 * q + 1]);
+                            __half2 h1 = __floats2half2_rn(v[8 * q + 2], v[8 * q + 3]);
+                            __half2 h2 = __floats2half2_rn(v[8 * q + 4], v[8 * q + 5]);
+                            __half2 h3 = __floats2half2_rn(v[8 * q + 6], v[8 * q + 7]);
+                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(*reinterpret_cast<uint32_t *>(&h0)),
+                                         "r"(*reinterpret_cast<uint32_t *>(&h1)), "r"(*reinterpret_cast<uint32_t *>(&h2)),
+                                         "r"(*reinterpret_cast<uint32_t *>(&h3))
+                                         : "memory");
+                        }
+                    } else {
                     if (p.res) mbar_wait(rb, (gw >> 1) & 1);
                     const uint32_t rowaddr = buf + lane * 128;
 #pragma unroll
@@ -453,6 +476,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
                         asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(t.x), "f"(t.y), "f"(t.z),
                                      "f"(t.w)
                                      : "memory");
+                    }
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
@@ -580,10 +604,15 @@ std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
 bool turtle_get_tmap(CUtensorMap *out, const void *ptr, int rank, const uint64_t *dims, const uint64_t *strides,
                      const uint32_t *box, int swizzle128) {
+    return turtle_get_tmap2(out, ptr, rank, dims, strides, box, swizzle128, 0);
+}
+
+bool turtle_get_tmap2(CUtensorMap *out, const void *ptr, int rank, const uint64_t *dims, const uint64_t *strides,
+                      const uint32_t *box, int swizzle128, int dtype) {
     MapKey k{};
     k.ptr = ptr;
     k.rank = (uint32_t)rank;
-    k.swz = (uint32_t)swizzle128;
+    k.swz = (uint32_t)swizzle128 | ((uint32_t)dtype << 8);
     k.d0 = dims[0]; k.d1 = dims[1]; k.d2 = rank > 2 ? dims[2] : 0; k.d3 = rank > 3 ? dims[3] : 0;
     k.s1 = strides[0]; k.s2 = rank > 2 ? strides[1] : 0; k.s3 = rank > 3 ? strides[2] : 0;
     k.b0 = box[0]; k.b1 = box[1]; k.b2 = rank > 2 ? box[2] : 0; k.b3 = rank > 3 ? box[3] : 0;
@@ -597,10 +626,11 @@ bool turtle_get_tmap(CUtensorMap *out, const void *ptr, int rank, const uint64_t
     if (!enc) return false;
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUtensorMap m;
-    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(ptr),
+    CUresult r = enc(&m, dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(ptr),
                      reinterpret_cast<const cuuint64_t *>(dims), reinterpret_cast<const cuuint64_t *>(strides),
                      reinterpret_cast<const cuuint32_t *>(box), estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     swizzle128 == 2   ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                     swizzle128 == 3   ? CU_TENSOR_MAP_SWIZZLE_64B
+                     : swizzle128 == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
                      : swizzle128 == 1 ? CU_TENSOR_MAP_SWIZZLE_128B
                                        : CU_TENSOR_MAP_SWIZZLE_NONE,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -650,6 +680,11 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
     p.NG = NG;
     p.ngroups = Cout / NG;
     const int K = a->im2col ? 9 * a->segw : a->nseg * a->segw;
+    const bool a16 = a->a_dtype == 1, o16 = a->out_dtype == 1;
+    const int es = a16 ? 2 : 4;                 // operand element size
+    const int KE = 128 / es;                    // K elements per k-block
+    if (a16 && (a->im2col || (a->nseg > 1 && a->segw % KE))) return TURTLE_ENOTSUP;
+    if (o16 && (a->res || a->store != TURTLE_STORE_PLAIN || NG % 32)) return TURTLE_ENOTSUP;
     long long tiles;
     if (a->im2col) {
         if (a->lda[0] != a->segw) return TURTLE_ENOTSUP;
@@ -675,33 +710,35 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
             if (n % cand || n / cand > MAX_TC_SEG) continue;
             bool ok = true;
             for (int i = 0; i < n && ok; i += cand) {
-                const long long hs = cand > 1 ? (long long)(a->A[i + 1] - a->A[i]) : w;
-                if (hs < w || (hs & 3)) ok = false;
+                const char *b0 = (const char *)a->A[i];
+                const long long hs = cand > 1 ? (long long)((const char *)a->A[i + 1] - b0) / es : w;   // in elements
+                if (hs < w || (hs * es) % 16) ok = false;
                 for (int j = 1; j < cand && ok; ++j)
-                    ok = (a->A[i + j] - a->A[i]) == j * hs && a->lda[i + j] == a->lda[i];
+                    ok = ((const char *)a->A[i + j] - b0) == (long long)j * hs * es && a->lda[i + j] == a->lda[i];
                 if (ok && (long long)a->lda[i] < (cand - 1) * hs + w) ok = false;
             }
             if (ok) { g = cand; break; }
         }
         if (!g) return TURTLE_ENOTSUP;
         p.nseg = n / g;
-        p.kb_per_sub = w / TK;
+        p.kb_per_sub = (w + KE - 1) / KE;          // a ragged last k-block is zero-filled by TMA (single segment)
         p.kb_per_seg = g * p.kb_per_sub;
         for (int i = 0; i < p.nseg; ++i) {
-            const long long hs = g > 1 ? (long long)(a->A[i * g + 1] - a->A[i * g]) : w;
+            // NB for fp16 the A pointers are byte addresses of __half data carried in the float* slots
+            const long long hs_bytes = g > 1 ? (long long)((const char *)a->A[i * g + 1] - (const char *)a->A[i * g]) : (long long)w * es;
             uint64_t dims[3] = {(uint64_t)w, (uint64_t)g, (uint64_t)a->P};
-            uint64_t str[2] = {(uint64_t)hs * 4, (uint64_t)a->lda[i * g] * 4};
-            uint32_t box[3] = {TK, 1, TM};
-            if (!get_map(&p.mapA[i], a->A[i * g], 3, dims, str, box)) return TURTLE_ENOTSUP;
+            uint64_t str[2] = {(uint64_t)hs_bytes, (uint64_t)a->lda[i * g] * es};
+            uint32_t box[3] = {(uint32_t)KE, 1, TM};
+            if (!turtle_get_tmap2(&p.mapA[i], a->A[i * g], 3, dims, str, box, 1, a16 ? 1 : 0)) return TURTLE_ENOTSUP;
         }
         tiles = (a->P + TM - 1) / TM;
     }
-    p.nkb = K / TK;
+    p.nkb = a->im2col ? K / TK : p.nseg * p.kb_per_seg;
     {
         uint64_t dims[2] = {(uint64_t)K, (uint64_t)Cout};
-        uint64_t str[1] = {(uint64_t)K * 4};
-        uint32_t box[2] = {TK, (uint32_t)NG};
-        if (!get_map(&p.mapW, a->Wt, 2, dims, str, box)) return TURTLE_ENOTSUP;
+        uint64_t str[1] = {(uint64_t)K * es};
+        uint32_t box[2] = {(uint32_t)KE, (uint32_t)NG};
+        if (!turtle_get_tmap2(&p.mapW, a->Wt, 2, dims, str, box, 1, a16 ? 1 : 0)) return TURTLE_ENOTSUP;
     }
     p.total_units = tiles * p.ngroups;
     const size_t stage_bytes = A_STAGE_BYTES + (size_t)NG * TK * 4;
@@ -711,12 +748,12 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
     if (stages < 2) return TURTLE_ENOTSUP;
     p.stages = stages;
     p.tma_epi = 0;
-    if (!a->im2col && a->store == TURTLE_STORE_PLAIN && NG % 32 == 0 && !(a->ldo & 3) &&
+    if (!a->im2col && a->store == TURTLE_STORE_PLAIN && NG % 32 == 0 && !((a->ldo * (o16 ? 2 : 4)) & 15) &&
         (!a->res || (!(a->ldres & 3) && !((uintptr_t)a->res & 15)))) {
         uint64_t dims[2] = {(uint64_t)Cout, (uint64_t)a->P};
         uint32_t box[2] = {32, 32};
-        uint64_t so[1] = {(uint64_t)a->ldo * 4};
-        bool ok = get_map(&p.mapOut, a->out, 2, dims, so, box);
+        uint64_t so[1] = {(uint64_t)a->ldo * (o16 ? 2 : 4)};
+        bool ok = o16 ? turtle_get_tmap2(&p.mapOut, a->out, 2, dims, so, box, 3, 1) : get_map(&p.mapOut, a->out, 2, dims, so, box);
         if (ok && a->res) {
             uint64_t sr[1] = {(uint64_t)a->ldres * 4};
             ok = get_map(&p.mapRes, a->res, 2, dims, sr, box);
@@ -724,10 +761,14 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
         p.tma_epi = ok ? 1 : 0;
     }
     const size_t smem = stages * stage_bytes + EPI_BYTES + 1024;
+    if (o16 && !p.tma_epi) return TURTLE_ENOTSUP;
     static bool configured = false;
     static int nsm = 148;
     if (!configured) {
-        if (cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(gemm_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess ||
+            cudaFuncSetAttribute(gemm_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess ||
+            cudaFuncSetAttribute(gemm_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess ||
+            cudaFuncSetAttribute(gemm_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess)
             return TURTLE_ELAUNCH;
         int dev = 0;
         cudaGetDevice(&dev);
@@ -735,7 +776,11 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
         configured = true;
     }
     long long grid = p.total_units < nsm ? p.total_units : nsm;
-    gemm_tc2_kernel<<<(unsigned)grid, 384, smem, as_stream(stream)>>>(p);
+    cudaStream_t st = as_stream(stream);
+    if (a16 && o16) gemm_tc2_kernel<true, true><<<(unsigned)grid, 384, smem, st>>>(p);
+    else if (a16) gemm_tc2_kernel<true, false><<<(unsigned)grid, 384, smem, st>>>(p);
+    else if (o16) gemm_tc2_kernel<false, true><<<(unsigned)grid, 384, smem, st>>>(p);
+    else gemm_tc2_kernel<false, false><<<(unsigned)grid, 384, smem, st>>>(p);
     return cudaGetLastError() == cudaSuccess ? TURTLE_OK : TURTLE_ELAUNCH;
 }
 
@@ -746,12 +791,13 @@ int turtle_gemm_tc_v1(const TurtleGemmArgs *a, void *stream);
 int turtle_gemm_tc(const TurtleGemmArgs *a, void *stream) {
     const int Cout = a->Cout;
     if (Cout % 16 || Cout < 16) return TURTLE_ENOTSUP;
-    if (a->segw % TK) return TURTLE_ENOTSUP;
+    if (!a->a_dtype && a->segw % TK) return TURTLE_ENOTSUP;
     if (((uintptr_t)a->Wt & 15) || ((uintptr_t)a->out & 15)) return TURTLE_ENOTSUP;
     static const bool use_v1 = getenv("TURTLE_GEMM_V1") != nullptr;
-    if (!use_v1) {
+    const bool half_io = a->a_dtype || a->out_dtype;
+    if (!use_v1 || half_io) {
         int r = turtle_gemm_tc2(a, stream);
-        if (r != TURTLE_ENOTSUP) return r;
+        if (r != TURTLE_ENOTSUP || half_io) return r;
     }
     return turtle_gemm_tc_v1(a, stream);
 }

@@ -1,6 +1,8 @@
 // Memory-bound per-pixel kernels: frame pack, first/last 3x3 conv, channel LayerNorm,
 // depthwise 3x3 (+GELU / gate / SAB patch layout), column scaling, T0 position code.
 // All activations fp32 channels-last.  See include/turtle_b200.h for the contracts.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -246,7 +248,7 @@ __global__ void layernorm_kernel(const float *__restrict__ x, int ldx, const flo
 
 // Vectorised variant: a pixel is owned by G lanes holding NV float4 each (C = 4*NV*G); every lane
 // group keeps U pixels in flight so that enough bytes are outstanding to cover HBM latency.
-template <int NV, int G, int U>
+template <int NV, int G, int U, bool O16>
 __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float *__restrict__ x, int ldx,
                                                             const float *__restrict__ w, const float *__restrict__ b,
                                                             float *__restrict__ y, int ldy, int64_t P, int rnd) {
@@ -296,7 +298,13 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float *__restr
                 o.y = (v[u][i].y - sub) / den * wv[i].y + bv[i].y;
                 o.z = (v[u][i].z - sub) / den * wv[i].z + bv[i].z;
                 o.w = (v[u][i].w - sub) / den * wv[i].w + bv[i].w;
-                *reinterpret_cast<float4 *>(y + p * ldy + (i * G + gl) * 4) = rnd ? rna_tf32(o) : o;
+                if (O16) {        // y is __half*, ldy in halves
+                    __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+                    uint2 pk = make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+                    *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(y) + p * ldy + (i * G + gl) * 4) = pk;
+                } else {
+                    *reinterpret_cast<float4 *>(y + p * ldy + (i * G + gl) * 4) = rnd ? rna_tf32(o) : o;
+                }
             }
         }
     }
@@ -307,16 +315,21 @@ static void launch_ln_vec(const float *x, int ldx, const float *w, const float *
                           int rnd, cudaStream_t s) {
     const int64_t per_warp = (32 / G) * U;
     const int64_t warps = cdiv64(P, per_warp);
-    layernorm_vec_kernel<NV, G, U><<<(unsigned)cdiv64(warps, 8), 256, 0, s>>>(x, ldx, w, b, y, ldy, P, rnd);
+    if (rnd == 2)
+        layernorm_vec_kernel<NV, G, U, true><<<(unsigned)cdiv64(warps, 8), 256, 0, s>>>(x, ldx, w, b, y, ldy, P, rnd);
+    else
+        layernorm_vec_kernel<NV, G, U, false><<<(unsigned)cdiv64(warps, 8), 256, 0, s>>>(x, ldx, w, b, y, ldy, P, rnd);
 }
 
 extern "C" int turtle_layernorm(const float *x, int ldx, const float *w, const float *b, float *y, int ldy,
                                 int64_t P, int C, int round_tf32, void *stream) {
     if (!x || !w || !y || C < 1 || C > 512 || P < 1) return TURTLE_EINVAL;
-    const int rnd = round_tf32;
+    const int rnd = round_tf32;     // 0: fp32 out, 1: fp32 out rounded to TF32, 2: fp16 out (y is __half*, ldy in halves)
     cudaStream_t s = as_stream(stream);
+    if (rnd == 2 && !(C == 64 || C == 128 || C == 256 || C == 512)) return TURTLE_ENOTSUP;
     const bool al = (ldx % 4 == 0) && (ldy % 4 == 0) &&
                     ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)w | (uintptr_t)b) & 15) == 0);
+    if (rnd == 2 && !al) return TURTLE_ENOTSUP;
     if (al && (C == 64 || C == 128 || C == 256 || C == 512)) {
         if (C == 64) launch_ln_vec<1, 16, 4>(x, ldx, w, b, y, ldy, P, rnd, s);
         else if (C == 128) launch_ln_vec<1, 32, 4>(x, ldx, w, b, y, ldy, P, rnd, s);
@@ -427,11 +440,12 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const float *__restrict_
 }
 
 int turtle_dwconv3x3_tma(const float *x, int ldx, const float *w, const float *bias, float *y, int ldy, int NB, int H,
-                         int W, int C, int fuse, int layout, int ws, int rnd, void *stream);   // dwconv_tma.cu
+                         int W, int C, int fuse, int layout, int ws, int rnd, void *stream);   // dwconv_tma.cu (rnd==2: fp16 in/out)
 
 extern "C" int turtle_dwconv3x3(const float *x, int ldx, const float *w, const float *bias, float *y, int ldy,
                                 int NB, int H, int W, int C, int fuse, int layout, int ws, int round_tf32, void *stream) {
-    const int rnd = round_tf32;
+    const int rnd = round_tf32;     // 2: x and y are fp16 (ldx/ldy in halves); tensor-core mode only
+    if (rnd == 2) return turtle_dwconv3x3_tma(x, ldx, w, bias, y, ldy, NB, H, W, C, fuse, layout, ws, rnd, stream);
     if (!x || !w || !y || NB < 1 || C < 4 || fuse < 0 || fuse > 2 || (ldx & 3)) return TURTLE_EINVAL;
     int Cout = fuse == 2 ? C / 2 : C;
     if ((Cout & 3) || (fuse == 2 && (C & 7))) return TURTLE_EINVAL;

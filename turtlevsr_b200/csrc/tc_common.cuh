@@ -8,6 +8,9 @@
 // swizzle128: 0 = none, 1 = SWIZZLE_128B (16 B atoms), 2 = SWIZZLE_128B_ATOM_32B (tf32 MN-major operands)
 bool turtle_get_tmap(CUtensorMap *out, const void *ptr, int rank, const uint64_t *dims, const uint64_t *strides,
                      const uint32_t *box, int swizzle128);
+// + swizzle128 == 3: SWIZZLE_64B;  dtype: 0 = fp32, 1 = fp16 (strides stay in bytes)
+bool turtle_get_tmap2(CUtensorMap *out, const void *ptr, int rank, const uint64_t *dims, const uint64_t *strides,
+                      const uint32_t *box, int swizzle128, int dtype);
 
 namespace {
 
@@ -65,6 +68,15 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }

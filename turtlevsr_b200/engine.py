@@ -30,7 +30,7 @@ _NULL = None
 
 
 def _ptr(t: Optional[torch.Tensor], off: int = 0):
-    return None if t is None else t.data_ptr() + 4 * off
+    return None if t is None else t.data_ptr() + t.element_size() * off
 
 
 class _Workspace:
@@ -110,6 +110,13 @@ class FrameEngine:
 
     def _w(self, name: str, kind: str = "raw") -> Optional[torch.Tensor]:
         """Device weight in the layout the kernels want (packed once, cached)."""
+        if kind == "gemm16":          # fp16 copy of a 1x1 weight for the kind::f16 tensor-core path
+            key = f"gemm16:{name}"
+            t = self.packed.get(key)
+            if t is None:
+                t = self._sd[name].detach().float().reshape(self._sd[name].shape[0], -1).half().contiguous()
+                self.packed[key] = t
+            return t
         tf32 = self.mode == capi.TF32 and kind in ("gemm", "conv3")
         key = f"{kind}{'@tf32' if tf32 else ''}:{name}"
         t = self.packed.get(key)
@@ -143,7 +150,7 @@ class FrameEngine:
     # kernel wrappers
     # ------------------------------------------------------------------------------------
     def gemm(self, segs, segw, Wt, out, ldo, P, Cout, bias=None, scale=None, act=0, res=None, ldres=0,
-             im2col=0, geom=None, store=0, round_out=False):
+             im2col=0, geom=None, store=0, round_out=False, a16=False, o16=False):
         """segs: list of (ptr:int, lda:int).  round_out: the result feeds another tensor-core op."""
         a = GemmArgs()
         a.mode = self.mode
@@ -166,7 +173,9 @@ class FrameEngine:
         a.out = out
         a.ldo = ldo
         a.store = store
-        a.round_out = 1 if (round_out and self.mode == capi.TF32) else 0
+        a.round_out = 1 if (round_out and self.mode == capi.TF32 and not o16) else 0
+        a.a_dtype = 1 if a16 else 0
+        a.out_dtype = 1 if o16 else 0
         if self.profile is not None:
             K = (9 if im2col else len(segs)) * segw
             self._meta = (4 * (P * K + Cout * K + P * Cout * (2 if res else 1)), 2 * P * K * Cout)
@@ -193,9 +202,21 @@ class FrameEngine:
         self._meta = (0, 0)
 
     def conv1x1(self, x, ldx, Cin, wname, out, ldo, P, Cout, **kw):
-        self.gemm([(x, ldx)], Cin, self._w(wname, "gemm"), out, ldo, P, Cout, **kw)
+        self.gemm([(x, ldx)], Cin, self._w(wname, "gemm16" if kw.get("a16") else "gemm"), out, ldo, P, Cout, **kw)
 
-    def layernorm(self, x: torch.Tensor, pre: str, C_: int, P: int) -> torch.Tensor:
+    def half_path(self, *chans) -> bool:
+        """fp16 storage for the FFN-side intermediates (LN output, wide hidden, gated hidden): tf32 mode only and
+        only for shapes the fp16 kernels cover (32-aligned channel counts, LN widths 64..512)."""
+        return (self.mode == capi.TF32 and self.use_half and not self.dry_run
+                and chans[0] in (64, 128, 256, 512) and all(ch % 32 == 0 for ch in chans))
+
+    def layernorm(self, x: torch.Tensor, pre: str, C_: int, P: int, half: bool = False) -> torch.Tensor:
+        if half:
+            y = self.ws.get("xn16", P, C_, dtype=torch.float16)
+            self._meta = (6 * P * C_, 0)
+            self._call("turtle_layernorm", _ptr(x), C_, _ptr(self._w(pre + "body.weight")),
+                       _ptr(self._w(pre + "body.bias")), _ptr(y), C_, P, C_, 2, self.stream)
+            return y
         y = self.ws.get("xn", P, C_)
         self._meta = (8 * P * C_, 0)
         self._call("turtle_layernorm", _ptr(x), C_, _ptr(self._w(pre + "body.weight")), _ptr(self._w(pre + "body.bias")),
@@ -214,6 +235,17 @@ class FrameEngine:
     def gated_ffw(self, pre, xn, x, P, c, H, W, B):
         hid2 = self._sd[pre + "project_in.weight"].shape[0]
         hid = hid2 // 2
+        if xn.dtype == torch.float16:       # fp16 intermediates, kind::f16 MMAs
+            t = self.ws.get("wide16", P, hid2, dtype=torch.float16)
+            self.conv1x1(_ptr(xn), c, c, pre + "project_in.weight", _ptr(t), hid2, P, hid2,
+                         bias=self._w(pre + "project_in.bias"), a16=True, o16=True)
+            g = self.ws.get("dw16", P, hid, dtype=torch.float16)
+            self._meta = (2 * P * (hid2 + hid), 2 * 9 * P * hid2)
+            self._call("turtle_dwconv3x3", _ptr(t), hid2, _ptr(self._w(pre + "dwconv.weight", "dw")),
+                       _ptr(self._w(pre + "dwconv.bias")), _ptr(g), hid, B, H, W, hid2, 2, 0, 1, 2, self.stream)
+            self.conv1x1(_ptr(g), hid, hid, pre + "project_out.weight", _ptr(x), c, P, c,
+                         bias=self._w(pre + "project_out.bias"), res=_ptr(x), ldres=c, a16=True)
+            return
         t = self.ws.get("wide", P, hid2)
         self.conv1x1(_ptr(xn), c, c, pre + "project_in.weight", _ptr(t), hid2, P, hid2,
                      bias=self._w(pre + "project_in.bias"))
@@ -223,6 +255,13 @@ class FrameEngine:
                      bias=self._w(pre + "project_out.bias"), res=_ptr(x), ldres=c)
 
     def plain_ffw(self, pre, xn, x, P, c):
+        if xn.dtype == torch.float16:
+            t = self.ws.get("wide16", P, 2 * c, dtype=torch.float16)
+            self.conv1x1(_ptr(xn), c, c, pre + "conv4.weight", _ptr(t), 2 * c, P, 2 * c,
+                         bias=self._w(pre + "conv4.bias"), act=capi.ACT_GELU, a16=True, o16=True)
+            self.conv1x1(_ptr(t), 2 * c, 2 * c, pre + "conv5.weight", _ptr(x), c, P, c, bias=self._w(pre + "conv5.bias"),
+                         scale=self._w(pre + "gamma"), res=_ptr(x), ldres=c, a16=True)
+            return
         t = self.ws.get("wide", P, 2 * c)
         self.conv1x1(_ptr(xn), c, c, pre + "conv4.weight", _ptr(t), 2 * c, P, 2 * c, bias=self._w(pre + "conv4.bias"),
                      act=capi.ACT_GELU, round_out=True)
@@ -233,6 +272,17 @@ class FrameEngine:
     # attentions (x updated in place: x += attn(xn))
     # ------------------------------------------------------------------------------------
     def reduced_attn(self, pre, xn, x, P, c, H, W, B):
+        if xn.dtype == torch.float16:
+            t = self.ws.get("wide16", P, 2 * c, dtype=torch.float16)
+            self.conv1x1(_ptr(xn), c, c, pre + "conv1.weight", _ptr(t), 2 * c, P, 2 * c,
+                         bias=self._w(pre + "conv1.bias"), a16=True, o16=True)
+            u = self.ws.get("dw16", P, 2 * c, dtype=torch.float16)
+            self._meta = (2 * P * 4 * c, 2 * 9 * P * 2 * c)
+            self._call("turtle_dwconv3x3", _ptr(t), 2 * c, _ptr(self._w(pre + "conv2.weight", "dw")),
+                       _ptr(self._w(pre + "conv2.bias")), _ptr(u), 2 * c, B, H, W, 2 * c, 1, 0, 1, 2, self.stream)
+            self.conv1x1(_ptr(u), 2 * c, 2 * c, pre + "conv3.weight", _ptr(x), c, P, c, bias=self._w(pre + "conv3.bias"),
+                         scale=self._w(pre + "beta"), res=_ptr(x), ldres=c, a16=True)
+            return
         t = self.ws.get("wide", P, 2 * c)
         self.conv1x1(_ptr(xn), c, c, pre + "conv1.weight", _ptr(t), 2 * c, P, 2 * c, bias=self._w(pre + "conv1.bias"))
         u = self.ws.get("dw", P, 2 * c)
@@ -427,7 +477,7 @@ class FrameEngine:
         kc = vc = None
         at = blk.attention_type
         if at != "NoAttn":
-            xn = self.layernorm(x, pre + "norm1.", c, P)
+            xn = self.layernorm(x, pre + "norm1.", c, P, half=(at == "ReducedAttn" and self.half_path(c, 2 * c)))
             a = pre + "attn."
             if at == "Channel":
                 self.channel_attn(a, xn, x, B, H, W, c, lvl.num_heads)
@@ -438,7 +488,12 @@ class FrameEngine:
             elif at == "CHM":
                 kc, vc = self.chm(a, xn, x, B, H, W, c, lvl.num_heads, lvl.Scale_patchsize, lvl.num_frames_tocache,
                                   k_in, v_in)
-        xn = self.layernorm(x, pre + "norm2.", c, P)
+        if blk.FFW_type == "GFFW":
+            hid2 = self._sd[pre + "ffn.project_in.weight"].shape[0]
+            half = self.half_path(c, hid2 // 2)
+        else:
+            half = self.half_path(c, 2 * c)
+        xn = self.layernorm(x, pre + "norm2.", c, P, half=half)
         if blk.FFW_type == "GFFW":
             self.gated_ffw(pre + "ffn.", xn, x, P, c, H, W, B)
         else:
@@ -493,6 +548,7 @@ class FrameEngine:
         self._sd = dict(m.named_parameters())
         self.mode = capi.TF32 if m.precision == "tf32" else capi.FP32
         self.rnd = 1 if self.mode == capi.TF32 else 0
+        self.use_half = bool(getattr(m, "half_intermediates", True))
         self.trace = {} if getattr(m, "record_trace", False) else None
         inp = inp.float().contiguous()
         B, _, Cc, Hs, Ws = inp.shape
