@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(128) gemm_tc_kernel(const __grid_constant__ Tc
 // =============================================================================================
 struct alignas(64) Tc2Params {
     CUtensorMap mapA[MAX_TC_SEG];
-    CUtensorMap mapW, mapOut, mapRes;
+    CUtensorMap mapW, mapOut, mapRes, mapOut2;   // mapOut2: fp16 out, 64-column (128 B) boxes
     int nseg, kb_per_seg, kb_per_sub;
     int nkb, stages;
     int im2col, BW, BH, B, H, W, tiles_x, tiles_y;
@@ -410,7 +410,62 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
             mbar_wait(smem_u32(&tfull_bar[acc]), (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256;
-            if (p.tma_epi) {
+            if (p.tma_epi && O16) {
+                // fp16 output: contiguous chunk range per warp, two 32-column chunks (= one 128-byte row) per TMA
+                // store where possible -- TMA store cost scales with the number of row segments, not bytes.
+                const int m0 = (int)(tile * TM) + quarter * 32;
+                const int nch = NG / 32, h0 = (nch + 1) / 2;
+                const int jb = chalf ? h0 : 0, je = chalf ? nch : h0;
+                for (int j = jb; j < je; ++gw) {
+                    const int nc = (je - j >= 2) ? 2 : 1;
+                    const int b = gw & 1;
+                    const uint32_t buf = mybuf + b * EPI_BUF;
+                    if (lane == 0 && gw >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+                    for (int ci = 0; ci < nc; ++ci) {
+                        float v[32];
+                        tmem_ld32(trow + (j + ci) * 32, v);
+                        const int o0 = n0 + (j + ci) * 32;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const int o = o0 + 4 * q;
+                            if (p.bias) {
+                                float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + o));
+                                v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
+                            }
+                            if (p.act == TURTLE_ACT_GELU) {
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) v[4 * q + e] = gelu_fast(v[4 * q + e]);
+                            }
+                            if (p.scale) {
+                                float4 sc = __ldg(reinterpret_cast<const float4 *>(p.scale + o));
+                                v[4 * q] *= sc.x; v[4 * q + 1] *= sc.y; v[4 * q + 2] *= sc.z; v[4 * q + 3] *= sc.w;
+                            }
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            // nc == 2: 128-byte rows, SWIZZLE_128B (16 B chunk ^= row & 7); nc == 1: 64-byte rows, SWIZZLE_64B
+                            const uint32_t addr = nc == 2 ? buf + lane * 128 + (((uint32_t)(ci * 4 + q) ^ ((uint32_t)lane & 7u)) << 4)
+                                                          : buf + lane * 64 + (((uint32_t)q ^ (((uint32_t)lane >> 1) & 3u)) << 4);
+                            __half2 h0_ = __floats2half2_rn(v[8 * q + 0], v[8 * q + 1]);
+                            __half2 h1_ = __floats2half2_rn(v[8 * q + 2], v[8 * q + 3]);
+                            __half2 h2_ = __floats2half2_rn(v[8 * q + 4], v[8 * q + 5]);
+                            __half2 h3_ = __floats2half2_rn(v[8 * q + 6], v[8 * q + 7]);
+                            asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(*reinterpret_cast<uint32_t *>(&h0_)),
+                                         "r"(*reinterpret_cast<uint32_t *>(&h1_)), "r"(*reinterpret_cast<uint32_t *>(&h2_)),
+                                         "r"(*reinterpret_cast<uint32_t *>(&h3_))
+                                         : "memory");
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(nc == 2 ? &p.mapOut2 : &p.mapOut, buf, n0 + j * 32, m0);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    j += nc;
+                }
+            } else if (p.tma_epi) {
                 const int m0 = (int)(tile * TM) + quarter * 32;
                 for (int j = chalf; j < NG / 32; j += 2, ++gw) {
                     const int b = gw & 1;
@@ -754,6 +809,10 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
         uint32_t box[2] = {32, 32};
         uint64_t so[1] = {(uint64_t)a->ldo * (o16 ? 2 : 4)};
         bool ok = o16 ? turtle_get_tmap2(&p.mapOut, a->out, 2, dims, so, box, 3, 1) : get_map(&p.mapOut, a->out, 2, dims, so, box);
+        if (ok && o16) {
+            uint32_t box2[2] = {64, 32};
+            ok = turtle_get_tmap2(&p.mapOut2, a->out, 2, dims, so, box2, 1, 1);
+        }
         if (ok && a->res) {
             uint64_t sr[1] = {(uint64_t)a->ldres * 4};
             ok = get_map(&p.mapRes, a->res, 2, dims, sr, box);
