@@ -2,6 +2,8 @@
 //   gram    : per-head q^T k over pixels + squared column norms, split over pixels (deterministic partials)
 //   softmax : reduce partials, fold the L2 normalisation in as diagonal scaling, temperature, softmax
 //   fold    : M = W_out . blockdiag(P)  so that the apply step is one GEMM over the value rows
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -202,13 +204,14 @@ __global__ void chan_fold_kernel(const float *__restrict__ Pm, const float *__re
     const float *pp = Pm + ((int64_t)h * ch) * ncolP + seg * ch + j;
     float acc = 0.f;
     for (int i = 0; i < ch; ++i) acc = fmaf(__ldg(wp + i), __ldg(pp + (int64_t)i * ncolP), acc);
-    M[idx] = rnd ? rna_tf32(acc) : acc;
+    if (rnd == 2) reinterpret_cast<__half *>(M)[idx] = __float2half_rn(acc);     // fp16 weights for kind::f16
+    else M[idx] = rnd ? rna_tf32(acc) : acc;
 }
 
 }  // namespace
 
 int turtle_chan_gram_tc(const float *q, int ldq, int q_hs, const float *k, int ldk, int k_hs, int64_t P, int heads,
-                        int ch, int nsplit, float *gpart, float *sqq, float *sqk, void *stream);
+                        int ch, int nsplit, float *gpart, float *sqq, float *sqk, int h16, void *stream);
 
 extern "C" int turtle_chan_gram(const float *q, int ldq, int q_hs, const float *k, int ldk, int k_hs, int64_t P,
                                 int heads, int ch, int nsplit, float *gpart, float *sqq, float *sqk, int mode,
@@ -217,8 +220,10 @@ extern "C" int turtle_chan_gram(const float *q, int ldq, int q_hs, const float *
         return TURTLE_EINVAL;
     int64_t chunk = cdiv64(cdiv64(P, nsplit), GT) * GT;
     dim3 grid(nsplit, heads);
+    if (mode == 2)      // q,k are fp16 (pitches in halves): tensor-core kernel only
+        return turtle_chan_gram_tc(q, ldq, q_hs, k, ldk, k_hs, P, heads, ch, nsplit, gpart, sqq, sqk, 1, stream);
     if (mode == TURTLE_TF32) {
-        int r = turtle_chan_gram_tc(q, ldq, q_hs, k, ldk, k_hs, P, heads, ch, nsplit, gpart, sqq, sqk, stream);
+        int r = turtle_chan_gram_tc(q, ldq, q_hs, k, ldk, k_hs, P, heads, ch, nsplit, gpart, sqq, sqk, 0, stream);
         if (r != TURTLE_ENOTSUP) return r;
     }
     if (ch == 64 && !(ldq & 3) && !(ldk & 3) && !(q_hs & 3) && !(k_hs & 3) &&

@@ -215,7 +215,7 @@ int turtle_dwconv3x3_tma(const float *x, int ldx, const float *w, const float *b
     const int Cout = fuse == 2 ? C / 2 : C;
     if (Cout % CK) return TURTLE_ENOTSUP;
     const bool io16 = rnd == 2;
-    if (io16 && (layout != 0 || fuse == 0)) return TURTLE_ENOTSUP;
+    if (io16 && layout != 0) return TURTLE_ENOTSUP;
     const uint64_t es = io16 ? 2 : 4;
     DwParams p{};
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
@@ -231,7 +231,7 @@ int turtle_dwconv3x3_tma(const float *x, int ldx, const float *w, const float *b
     cudaStream_t s = as_stream(stream);
     if (p.nitems >= (1LL << 31)) return TURTLE_ENOTSUP;
     // rnd marks the tensor-core (tf32) mode: its 1e-3-class numerics admit the 1.5e-7-accurate fast erf
-    if (io16) return fuse == 1 ? launch<1, true, true>(p, s) : launch<2, true, true>(p, s);
+    if (io16) return fuse == 0 ? launch<0, false, true>(p, s) : fuse == 1 ? launch<1, true, true>(p, s) : launch<2, true, true>(p, s);
     if (fuse == 0) return launch<0, false, false>(p, s);
     if (fuse == 1) return rnd ? launch<1, true, false>(p, s) : launch<1, false, false>(p, s);
     return rnd ? launch<2, true, false>(p, s) : launch<2, false, false>(p, s);

@@ -39,6 +39,18 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo, u
     return d;
 }
 
+// fp16 operands use the ordinary 128B swizzle (layout type 2): atom = 64 halves (MN) x 8 rows (K)
+__device__ __forceinline__ uint64_t make_desc_mn16(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+template <bool H16>
 __global__ void __launch_bounds__(128) gram_tc_kernel(const __grid_constant__ GramParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
@@ -75,16 +87,23 @@ __global__ void __launch_bounds__(128) gram_tc_kernel(const __grid_constant__ Gr
             const uint32_t fb = smem_u32(&full_bar[stage]);
             const uint32_t sa = smem0 + stage * STAGE_BYTES;
             const int px = (int)(p0 + (long long)it * KP);
-            mbar_expect_tx(fb, STAGE_BYTES);
-            tma_load_2d(sa + 0 * BLK_BYTES, &p.mapQ, h * p.q_hs, px, fb);
-            tma_load_2d(sa + 1 * BLK_BYTES, &p.mapQ, h * p.q_hs + 32, px, fb);
-            tma_load_2d(sa + 2 * BLK_BYTES, &p.mapK, h * p.k_hs, px, fb);
-            tma_load_2d(sa + 3 * BLK_BYTES, &p.mapK, h * p.k_hs + 32, px, fb);
+            if (H16) {          // one 64-channel (128 B) box each for q_h and k_h
+                mbar_expect_tx(fb, 2 * BLK_BYTES);
+                tma_load_2d(sa + 0 * BLK_BYTES, &p.mapQ, h * p.q_hs, px, fb);
+                tma_load_2d(sa + 1 * BLK_BYTES, &p.mapK, h * p.k_hs, px, fb);
+            } else {
+                mbar_expect_tx(fb, STAGE_BYTES);
+                tma_load_2d(sa + 0 * BLK_BYTES, &p.mapQ, h * p.q_hs, px, fb);
+                tma_load_2d(sa + 1 * BLK_BYTES, &p.mapQ, h * p.q_hs + 32, px, fb);
+                tma_load_2d(sa + 2 * BLK_BYTES, &p.mapK, h * p.k_hs, px, fb);
+                tma_load_2d(sa + 3 * BLK_BYTES, &p.mapK, h * p.k_hs + 32, px, fb);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
     } else if (warp == 1 && lane == 0) {
-        // D=f32, A=B=tf32, A and B MN-major (bits 15,16), N=128, M=128
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) |
+        // D=f32, A=B=tf32 (format 2) or fp16 (format 0), A and B MN-major (bits 15,16), N=128, M=128
+        const uint32_t fmt = H16 ? 0u : 2u;
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 15) | (1u << 16) | ((128u >> 3) << 17) |
                          ((128u >> 4) << 24);
         int stage = 0;
         uint32_t phase = 0;
@@ -92,10 +111,18 @@ __global__ void __launch_bounds__(128) gram_tc_kernel(const __grid_constant__ Gr
             mbar_wait(smem_u32(&full_bar[stage]), phase);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t sa = smem0 + stage * STAGE_BYTES;
+            if (H16) {
 #pragma unroll
-            for (int k = 0; k < KP / 8; ++k) {
-                const uint64_t d = make_desc_mn(sa + k * 1024, BLK_BYTES, 512);
-                umma_tf32(tmem_base, d, d, idesc, (it | k) ? 1u : 0u);
+                for (int k = 0; k < KP / 16; ++k) {     // K = 16 pixels per MMA = two 8-row groups (SBO 1024)
+                    const uint64_t d = make_desc_mn16(sa + k * 2048, BLK_BYTES, 1024);
+                    umma_f16(tmem_base, d, d, idesc, (it | k) ? 1u : 0u);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < KP / 8; ++k) {
+                    const uint64_t d = make_desc_mn(sa + k * 1024, BLK_BYTES, 512);
+                    umma_tf32(tmem_base, d, d, idesc, (it | k) ? 1u : 0u);
+                }
             }
             umma_commit(smem_u32(&empty_bar[stage]));
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -149,9 +176,10 @@ __global__ void __launch_bounds__(128) gram_tc_kernel(const __grid_constant__ Gr
 }  // namespace
 
 int turtle_chan_gram_tc(const float *q, int ldq, int q_hs, const float *k, int ldk, int k_hs, int64_t P, int heads,
-                        int ch, int nsplit, float *gpart, float *sqq, float *sqk, void *stream) {
+                        int ch, int nsplit, float *gpart, float *sqq, float *sqk, int h16, void *stream) {
     if (ch != 64) return TURTLE_ENOTSUP;
-    if ((ldq & 3) || (ldk & 3) || (q_hs & 3) || (k_hs & 3) || (((uintptr_t)q | (uintptr_t)k) & 15)) return TURTLE_ENOTSUP;
+    const int al = h16 ? 7 : 3;
+    if ((ldq & al) || (ldk & al) || (q_hs & al) || (k_hs & al) || (((uintptr_t)q | (uintptr_t)k) & 15)) return TURTLE_ENOTSUP;
     GramParams p{};
     p.q_hs = q_hs; p.k_hs = k_hs; p.heads = heads; p.P = P;
     p.chunk = cdiv64(cdiv64(P, nsplit), KP) * KP;
@@ -159,20 +187,24 @@ int turtle_chan_gram_tc(const float *q, int ldq, int q_hs, const float *k, int l
     {
         uint64_t dq[2] = {(uint64_t)((heads - 1) * q_hs + 64), (uint64_t)P};
         uint64_t dk[2] = {(uint64_t)((heads - 1) * k_hs + 64), (uint64_t)P};
-        uint64_t sq[1] = {(uint64_t)ldq * 4}, sk[1] = {(uint64_t)ldk * 4};
-        uint32_t box[2] = {32, KP};
+        const uint64_t es = h16 ? 2 : 4;
+        uint64_t sq[1] = {(uint64_t)ldq * es}, sk[1] = {(uint64_t)ldk * es};
+        uint32_t box[2] = {h16 ? 64u : 32u, KP};
         if (dq[0] > (uint64_t)ldq || dk[0] > (uint64_t)ldk) return TURTLE_ENOTSUP;
-        if (!turtle_get_tmap(&p.mapQ, q, 2, dq, sq, box, 2) || !turtle_get_tmap(&p.mapK, k, 2, dk, sk, box, 2))
+        if (!turtle_get_tmap2(&p.mapQ, q, 2, dq, sq, box, h16 ? 1 : 2, h16) ||
+            !turtle_get_tmap2(&p.mapK, k, 2, dk, sk, box, h16 ? 1 : 2, h16))
             return TURTLE_ENOTSUP;
     }
     const size_t smem = STAGES * STAGE_BYTES + 1024;
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(gram_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+            cudaFuncSetAttribute(gram_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return TURTLE_ELAUNCH;
         configured = true;
     }
     dim3 grid(nsplit, heads);
-    gram_tc_kernel<<<grid, 128, smem, as_stream(stream)>>>(p);
+    if (h16) gram_tc_kernel<true><<<grid, 128, smem, as_stream(stream)>>>(p);
+    else gram_tc_kernel<false><<<grid, 128, smem, as_stream(stream)>>>(p);
     return cudaGetLastError() == cudaSuccess ? TURTLE_OK : TURTLE_ELAUNCH;
 }

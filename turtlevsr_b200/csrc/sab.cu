@@ -1,5 +1,7 @@
 // StateAlignBlock kernels (T1:548-610): window reducers, correlation + top-5 + local window +
 // clipped softmax (never materialising [F,N,N]), and the sparse history aggregation.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace {
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(256) sab_aggregate_quad_kernel(const int32_t *
     __shared__ float bw[QB * QB][4];      // weight of window-box key for each of the 4 queries
     __shared__ int ekey[QMAX];
     __shared__ float4 ew[QMAX];
-    __shared__ int ecount;
+    __shared__ int ecount, wcount[8];
     const int tid = threadIdx.x, f = blockIdx.y;
     const int qy0 = (blockIdx.x / quads_x) * 2, qx0 = (blockIdx.x % quads_x) * 2;
     const int wy0 = qy0 - 4, wx0 = qx0 - 4;
@@ -334,24 +336,39 @@ __global__ void __launch_bounds__(256) sab_aggregate_quad_kernel(const int32_t *
     for (int i = tid; i < QB * QB * 4; i += 256) (&bw[0][0])[i] = 0.f;
     if (tid == 0) ecount = 0;
     __syncthreads();
-    // scatter the (<=4 x 46) entries: box keys accumulate into bw, far keys are appended
-    if (tid < 4 * 46) {
+    // scatter the (<=4 x 46) entries: box keys accumulate into bw, far keys are appended in (query, slot)
+    // order (ballot-ranked, so the summation order -- and with it the result -- is run-to-run deterministic)
+    {
+        bool far = false;
+        int id = -1;
+        float w = 0.f;
         const int q = tid / 46, t = tid % 46;
-        const int qy = qy0 + (q >> 1), qx = qx0 + (q & 1);
-        if (qy < Hg && qx < Wg) {
-            const int64_t base = ((int64_t)f * N + (int64_t)qy * Wg + qx) * TURTLE_SAB_SLOTS;
-            const int id = idx[base + t];
-            const float w = wgt[base + t];
-            if (id >= 0 && w != 0.f) {
-                const int ry = id / Wg - wy0, rx = id % Wg - wx0;
-                if (ry >= 0 && ry < QB && rx >= 0 && rx < QB) {
-                    bw[ry * QB + rx][q] = w;             // a key appears at most once per query
-                } else {
-                    const int e = atomicAdd(&ecount, 1);
-                    ekey[e] = id;
-                    ew[e] = make_float4(q == 0 ? w : 0.f, q == 1 ? w : 0.f, q == 2 ? w : 0.f, q == 3 ? w : 0.f);
+        if (tid < 4 * 46) {
+            const int qy = qy0 + (q >> 1), qx = qx0 + (q & 1);
+            if (qy < Hg && qx < Wg) {
+                const int64_t base = ((int64_t)f * N + (int64_t)qy * Wg + qx) * TURTLE_SAB_SLOTS;
+                id = idx[base + t];
+                w = wgt[base + t];
+                if (id >= 0 && w != 0.f) {
+                    const int ry = id / Wg - wy0, rx = id % Wg - wx0;
+                    if (ry >= 0 && ry < QB && rx >= 0 && rx < QB) bw[ry * QB + rx][q] = w;   // at most once per query
+                    else far = true;
                 }
             }
+        }
+        const unsigned fm = __ballot_sync(0xffffffffu, far);
+        if ((tid & 31) == 0) wcount[tid >> 5] = __popc(fm);
+        __syncthreads();
+        if (far) {
+            int e = __popc(fm & ((1u << (tid & 31)) - 1));
+            for (int i = 0; i < (tid >> 5); ++i) e += wcount[i];
+            ekey[e] = id;
+            ew[e] = make_float4(q == 0 ? w : 0.f, q == 1 ? w : 0.f, q == 2 ? w : 0.f, q == 3 ? w : 0.f);
+        }
+        if (tid == 0) {
+            int tot = 0;
+            for (int i = 0; i < 8; ++i) tot += wcount[i];
+            ecount = tot;
         }
     }
     __syncthreads();
@@ -394,8 +411,16 @@ __global__ void __launch_bounds__(256) sab_aggregate_quad_kernel(const int32_t *
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int qy = qy0 + (q >> 1), qx = qx0 + (q & 1);
-            if (qy < Hg && qx < Wg)
-                stg_stream(y + (((int64_t)f * H + p1 * Hg + qy) * W + p2 * Wg + qx) * c + d, rnd ? rna_tf32(acc[q]) : acc[q]);
+            if (qy < Hg && qx < Wg) {
+                const int64_t o = (((int64_t)f * H + p1 * Hg + qy) * W + p2 * Wg + qx) * c + d;
+                if (rnd == 2) {         // fp16 output (feeds a kind::f16 GEMM)
+                    __half2 h0 = __floats2half2_rn(acc[q].x, acc[q].y), h1 = __floats2half2_rn(acc[q].z, acc[q].w);
+                    *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(y) + o) =
+                        make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+                } else {
+                    stg_stream(y + o, rnd ? rna_tf32(acc[q]) : acc[q]);
+                }
+            }
         }
     }
 }
@@ -435,6 +460,7 @@ extern "C" int turtle_sab_aggregate(const int32_t *idx, const float *wgt, const 
                                     int F, int Hg, int Wg, int ws, int c, int passthrough, int round_tf32, void *stream) {
     if (!v || !y || F < 1 || (c & 3) || ws < 1) return TURTLE_EINVAL;
     if (!passthrough && (!idx || !wgt)) return TURTLE_EINVAL;
+    if (round_tf32 == 2 && passthrough) return TURTLE_ENOTSUP;
     if (!passthrough && !(((uintptr_t)v | (uintptr_t)y) & 15) && !(v_fstride & 3)) {
         const int quads_x = (Wg + 1) / 2, quads_y = (Hg + 1) / 2;
         dim3 grid(quads_x * quads_y, F);

@@ -297,18 +297,31 @@ class FrameEngine:
         hist_segs: per batch element a list of key/value history segments (oldest first), each
         ``dict(k=ptr, ldk=, khs=, v=ptr, ldv=, vhs=, prenorm=bool)``.  The frame's own q/k/v are
         appended as the last segment.  With ``ring`` the normalised key rows and value rows of the
-        frame are pushed into slot ``ring_slot`` (T1:286)."""
+        frame are pushed into slot ``ring_slot`` (T1:286).
+
+        When ``xn`` is fp16 (tf32 mode, no ring) q/k/v and the folded weight stay fp16 end to end: the Gram and
+        the apply GEMM run as kind::f16 MMAs (history segments must then be fp16 too)."""
         Pimg = H * W
         P = B * Pimg
         ch = c // heads
-        qkv = self.ws.get("wide", P, 3 * c)
-        self.conv1x1(_ptr(xn), c, c, pre + "qkv.weight", _ptr(qkv), 3 * c, P, 3 * c, bias=self._w(pre + "qkv.bias"))
-        qd = self.ws.get("dw", P, 3 * c)
-        self.dwconv(_ptr(qkv), 3 * c, pre + "qkv_dwconv.weight", pre + "qkv_dwconv.bias", _ptr(qd), 3 * c, B, H, W,
-                    3 * c)
+        h16 = xn.dtype == torch.float16
+        dt = torch.float16 if h16 else torch.float32
+        es = 2 if h16 else 4
+        qkv = self.ws.get("wide16" if h16 else "wide", P, 3 * c, dtype=dt)
+        self.conv1x1(_ptr(xn), c, c, pre + "qkv.weight", _ptr(qkv), 3 * c, P, 3 * c, bias=self._w(pre + "qkv.bias"),
+                     a16=h16, o16=h16)
+        qd = self.ws.get("dw16" if h16 else "dw", P, 3 * c, dtype=dt)
+        if h16:
+            self._meta = (2 * P * 6 * c, 2 * 9 * P * 3 * c)
+            self._call("turtle_dwconv3x3", _ptr(qkv), 3 * c, _ptr(self._w(pre + "qkv_dwconv.weight", "dw")),
+                       _ptr(self._w(pre + "qkv_dwconv.bias")), _ptr(qd), 3 * c, B, H, W, 3 * c, 0, 0, 1, 2, self.stream)
+        else:
+            self.dwconv(_ptr(qkv), 3 * c, pre + "qkv_dwconv.weight", pre + "qkv_dwconv.bias", _ptr(qd), 3 * c, B, H, W,
+                        3 * c)
         nsplit = max(1, min((Pimg + 255) // 256, max(1, 296 // heads)))
         temp = self._w(pre + "temperature")
         Wo = self._w(pre + "project_out.weight")
+        gmode = 2 if h16 else self.mode
         for b in range(B):
             segs = list(hist_segs[b]) if hist_segs is not None else []
             base = b * Pimg * 3 * c
@@ -319,24 +332,26 @@ class FrameEngine:
             sqq = self.ws.get("sqq", S, nsplit, c)
             sqk = self.ws.get("sqk", S, nsplit, c)
             for s, sg in enumerate(segs):
-                self._meta = (8 * Pimg * c, 2 * Pimg * c * ch)
+                self._meta = (2 * es * Pimg * c, 2 * Pimg * c * ch)
                 self._call("turtle_chan_gram", _ptr(qd, base), 3 * c, ch, sg["k"], sg["ldk"], sg["khs"], Pimg, heads, ch,
-                     nsplit, _ptr(gpart[s]), _ptr(sqq[s]), _ptr(sqk[s]), self.mode, self.stream)
+                           nsplit, _ptr(gpart[s]), _ptr(sqq[s]), _ptr(sqk[s]), gmode, self.stream)
             flags = self._flags([1 if sg["prenorm"] else 0 for sg in segs])
             Pm = self.ws.get("attnP", heads, ch, S * ch)
             inv = self.ws.get("invk", S, c)
-            self._call("turtle_chan_softmax", _ptr(gpart), _ptr(sqq), _ptr(sqk), _ptr(flags), _ptr(temp), S, nsplit, heads,
-                 ch, _ptr(Pm), _ptr(inv), self.stream)
-            M = self.ws.get("attnM", c, S * c)
-            self._call("turtle_chan_fold", _ptr(Pm), _ptr(Wo), S, heads, ch, _ptr(M), self.rnd, self.stream)
-            vsegs = [(sg["v"] + 4 * h * sg["vhs"], sg["ldv"]) for sg in segs for h in range(heads)]
+            self._call("turtle_chan_softmax", _ptr(gpart), _ptr(sqq), _ptr(sqk), _ptr(flags), _ptr(temp), S, nsplit,
+                       heads, ch, _ptr(Pm), _ptr(inv), self.stream)
+            M = self.ws.get("attnM16" if h16 else "attnM", c, S * c, dtype=dt)
+            self._call("turtle_chan_fold", _ptr(Pm), _ptr(Wo), S, heads, ch, _ptr(M), 2 if h16 else self.rnd, self.stream)
+            vsegs = [(sg["v"] + es * h * sg["vhs"], sg["ldv"]) for sg in segs for h in range(heads)]
             xb = _ptr(x, b * Pimg * c)
-            self.gemm(vsegs, ch, M, xb, c, Pimg, c, bias=self._w(pre + "project_out.bias"), res=xb, ldres=c)
+            self.gemm(vsegs, ch, M, xb, c, Pimg, c, bias=self._w(pre + "project_out.bias"), res=xb, ldres=c, a16=h16)
             if ring is not None:
                 self._call("turtle_scale_cols", _ptr(qd, base + c), 3 * c, ch, _ptr(inv[S - 1]),
-                     ring.slot_ptr(ring.kbuf, b, ring_slot), ring.ld, ring.head_stride, Pimg, heads, ch, self.stream)
+                           ring.slot_ptr(ring.kbuf, b, ring_slot), ring.ld, ring.head_stride, Pimg, heads, ch,
+                           self.stream)
                 self._call("turtle_scale_cols", _ptr(qd, base + 2 * c), 3 * c, ch, None,
-                     ring.slot_ptr(ring.vbuf, b, ring_slot), ring.ld, ring.head_stride, Pimg, heads, ch, self.stream)
+                           ring.slot_ptr(ring.vbuf, b, ring_slot), ring.ld, ring.head_stride, Pimg, heads, ch,
+                           self.stream)
         if self.trace is not None:
             self.trace.setdefault(pre, []).append(dict(qkv_dw=qd.clone()))
 
@@ -477,7 +492,9 @@ class FrameEngine:
         kc = vc = None
         at = blk.attention_type
         if at != "NoAttn":
-            xn = self.layernorm(x, pre + "norm1.", c, P, half=(at == "ReducedAttn" and self.half_path(c, 2 * c)))
+            half1 = (at == "ReducedAttn" and self.half_path(c, 2 * c)) or \
+                    (at == "Channel" and self.half_path(c) and c // lvl.num_heads == 64)
+            xn = self.layernorm(x, pre + "norm1.", c, P, half=half1)
             a = pre + "attn."
             if at == "Channel":
                 self.channel_attn(a, xn, x, B, H, W, c, lvl.num_heads)
