@@ -133,6 +133,9 @@ int turtle_gemm(const TurtleGemmArgs *args, void *stream);
  *           y is then [NB, (H/ws)*(W/ws), ws*ws*C] dense.
  * x [NB,H,W,C] pitch ldx; w tap-major [9,C] (= weight.view(C,9).t(), packed once by the host);
  * bias nullable.
+ * round_tf32: 0 exact | 1 round the stored values to nearest TF32 | 2 fp16 maps: x, y AND the taps w are fp16
+ *   (ldx/ldy in halves, pointers carried in the float* slots; layout 0 and 32-aligned channel counts only),
+ *   products accumulate in fp32.
  * ------------------------------------------------------------------------------------- */
 int turtle_dwconv3x3(const float *x, int ldx, const float *w, const float *bias, float *y, int ldy, int NB,
                      int H, int W, int C, int fuse, int layout, int ws, int round_tf32, void *stream);

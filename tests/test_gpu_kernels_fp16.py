@@ -1,0 +1,136 @@
+"""GPU parity of the fp16-storage variants of the C-ABI kernels (tensor-core mode intermediates).
+
+Each kernel is checked against a torch fp64 restatement of the same op evaluated on the *same fp16-rounded
+inputs*, so the tolerance only has to cover fp32 accumulation plus the final fp16 rounding (2^-11 relative)."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from turtlevsr_b200 import capi  # noqa: E402
+from turtlevsr_b200.capi import GemmArgs, call  # noqa: E402
+from gpu_util import stream  # noqa: E402
+
+H_EPS = 2.0 ** -11
+
+
+def rnd(*s, seed=0):
+    g = torch.Generator().manual_seed(seed + sum(s))
+    return torch.randn(*s, generator=g)
+
+
+def close16(got, want, extra=1e-6):
+    """|got - want| <= one fp16 rounding of want (+ accumulation slack)."""
+    err = (got.double() - want).abs()
+    tol = want.abs() * (1.5 * H_EPS) + extra
+    return bool((err <= tol).all()), float((err / tol).max())
+
+
+@pytest.mark.parametrize("fuse", [0, 1, 2])
+@pytest.mark.parametrize("B,C_,H,W", [(2, 64, 9, 14), (1, 320, 24, 40), (1, 192, 17, 33)])
+def test_dwconv_fp16(fuse, B, C_, H, W):
+    x = rnd(B, H, W, C_).half().cuda()                       # channels-last
+    w = (rnd(C_, 1, 3, 3, seed=1) / 3).half()
+    b = rnd(C_, seed=2)
+    xd = x.cpu().double().permute(0, 3, 1, 2)
+    y = F.conv2d(xd, w.double(), b.double(), padding=1, groups=C_)
+    if fuse == 1:
+        y = F.gelu(y)
+    elif fuse == 2:
+        a, g = y.chunk(2, 1)
+        y = F.gelu(a) * g
+    Co = y.shape[1]
+    out = torch.full((B, H, W, Co), float("nan"), device="cuda", dtype=torch.float16)
+    w9 = w.reshape(C_, 9).t().contiguous().cuda()
+    bd = b.cuda()
+    call("turtle_dwconv3x3", x.data_ptr(), C_, w9.data_ptr(), bd.data_ptr(), out.data_ptr(), Co, B, H, W,
+         C_, fuse, 0, 1, 2, stream())
+    ok, worst = close16(out.cpu().permute(0, 3, 1, 2), y, extra=2e-5)
+    assert ok, worst
+
+
+@pytest.mark.parametrize("C_", [64, 128, 256, 512])
+def test_layernorm_fp16_out(C_):
+    P = 777
+    x = (rnd(P, C_) * 2 + 0.5).cuda()
+    w, b = rnd(C_, seed=1).cuda(), rnd(C_, seed=2).cuda()
+    xd = x.cpu().double()
+    mu = xd.mean(-1, keepdim=True)
+    var = ((xd - mu) ** 2).mean(-1, keepdim=True)
+    want = (xd - mu) / (var + 1e-5).sqrt() * w.cpu().double() + b.cpu().double()
+    y = torch.full((P, C_), float("nan"), device="cuda", dtype=torch.float16)
+    call("turtle_layernorm", x.data_ptr(), C_, w.data_ptr(), b.data_ptr(), y.data_ptr(), C_, P, C_, 2, stream())
+    ok, worst = close16(y.cpu(), want, extra=1e-5)
+    assert ok, worst
+
+
+def _gemm16(A, lda, segs_off, segw, Wt, P, Cout, out, ldo, o16, bias=None, scale=None, act=0, res=None):
+    a = GemmArgs()
+    a.mode, a.im2col, a.P, a.Cout, a.nseg, a.segw = capi.TF32, 0, P, Cout, len(segs_off), segw
+    for i, off in enumerate(segs_off):
+        a.A[i] = A.data_ptr() + 2 * off
+        a.lda[i] = lda
+    a.Wt = Wt.data_ptr()
+    a.bias = None if bias is None else bias.data_ptr()
+    a.scale = None if scale is None else scale.data_ptr()
+    a.act = act
+    if res is not None:
+        a.res, a.ldres = res.data_ptr(), res.shape[-1]
+    a.out, a.ldo, a.store = out.data_ptr(), ldo, capi.STORE_PLAIN
+    a.a_dtype, a.out_dtype = 1, 1 if o16 else 0
+    call("turtle_gemm", C.byref(a), stream())
+
+
+@pytest.mark.parametrize("Cin,Cout,P", [(64, 320, 1000), (256, 768, 333), (512, 2560, 300)])
+def test_gemm_fp16_in_fp16_out(Cin, Cout, P):
+    A = rnd(P, Cin).half().cuda()
+    Wt = (rnd(Cout, Cin, seed=3) / Cin ** 0.5).half().cuda()
+    bias = rnd(Cout, seed=4).cuda()
+    out = torch.full((P, Cout), float("nan"), device="cuda", dtype=torch.float16)
+    _gemm16(A, Cin, [0], Cin, Wt, P, Cout, out, Cout, True, bias=bias, act=capi.ACT_GELU)
+    want = F.gelu(A.cpu().double() @ Wt.cpu().double().t() + bias.cpu().double())
+    ok, worst = close16(out.cpu(), want, extra=2e-5)
+    assert ok, worst
+
+
+@pytest.mark.parametrize("Cin,Cout,P", [(160, 64, 777), (1280, 512, 300), (128, 64, 1000)])
+def test_gemm_fp16_in_fp32_out_residual(Cin, Cout, P):
+    A = rnd(P, Cin).half().cuda()
+    Wt = (rnd(Cout, Cin, seed=3) / Cin ** 0.5).half().cuda()
+    bias, scale = rnd(Cout, seed=4).cuda(), rnd(Cout, seed=5).cuda()
+    x = rnd(P, Cout, seed=6).cuda()
+    want = (A.cpu().double() @ Wt.cpu().double().t() + bias.cpu().double()) * scale.cpu().double() + x.cpu().double()
+    _gemm16(A, Cin, [0], Cin, Wt, P, Cout, x, Cout, False, bias=bias, scale=scale, res=x)
+    assert (x.cpu().double() - want).abs().max() < 1e-5 * want.abs().max()        # fp32 accumulation over K
+
+
+def test_gemm_fp16_segments():
+    """Folded channel-attention apply: K-concatenated fp16 value blocks (one per head), fp16 folded weight."""
+    P, ch, heads = 500, 64, 4
+    c = heads * ch
+    qkv = rnd(P, 3 * c).half().cuda()
+    M = (rnd(c, c, seed=9) / 16).half().cuda()
+    x = rnd(P, c, seed=10).cuda()
+    want = x.cpu().double() + qkv.cpu().double()[:, 2 * c:] @ M.cpu().double().t()
+    _gemm16(qkv, 3 * c, [2 * c + h * ch for h in range(heads)], ch, M, P, c, x, c, False, res=x)
+    assert (x.cpu().double() - want).abs().max() < 1e-5 * want.abs().max()
+
+
+@pytest.mark.parametrize("P,heads,nsplit", [(640, 1, 1), (700, 2, 5), (4096, 4, 7), (130, 8, 3)])
+def test_chan_gram_fp16(P, heads, nsplit):
+    c = heads * 64
+    x = rnd(P, 3 * c).half().cuda()
+    g = torch.full((nsplit, heads, 64, 64), float("nan"), device="cuda")
+    sqq = torch.full((nsplit, c), float("nan"), device="cuda")
+    sqk = torch.full((nsplit, c), float("nan"), device="cuda")
+    call("turtle_chan_gram", x.data_ptr(), 3 * c, 64, x.data_ptr() + 2 * c, 3 * c, 64, P, heads, 64, nsplit,
+         g.data_ptr(), sqq.data_ptr(), sqk.data_ptr(), 2, stream())
+    xd = x.cpu().double()
+    q, k = xd[:, :c].reshape(P, heads, 64), xd[:, c:2 * c].reshape(P, heads, 64)
+    want = torch.einsum("phi,phj->hij", q, k)
+    assert (g.sum(0).cpu().double() - want).abs().max() < 1e-5 * P ** 0.5 * 8
+    assert (sqq.sum(0).cpu().double() - (xd[:, :c] ** 2).sum(0)).abs().max() < 1e-5 * P
+    assert (sqk.sum(0).cpu().double() - (xd[:, c:2 * c] ** 2).sum(0)).abs().max() < 1e-5 * P

@@ -268,6 +268,42 @@ __global__ void __launch_bounds__(128) gemm_tc_kernel(const __grid_constant__ Tc
     }
 }
 
+// Epilogue math on one 32-column chunk of a row.  The (bias, activation, scale) combination is a property of the
+// launch, so it is dispatched ONCE per chunk through a warp-uniform switch into fully specialised bodies: with the
+// flags tested inside the unrolled element loops ptxas predicates everything and every chunk issues the GELU and
+// scale code of all variants (measured: ~1300 SASS instructions per chunk, the small-K GEMMs were epilogue-bound).
+template <bool BIAS, bool GELU, bool SCALE>
+__device__ __forceinline__ void epi_math(float (&v)[32], const float *__restrict__ bias, const float *__restrict__ scale,
+                                         int o0) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        if (BIAS) {
+            const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + o0 + 4 * q));
+            v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
+        }
+        if (GELU) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[4 * q + e] = gelu_fast(v[4 * q + e]);
+        }
+        if (SCALE) {
+            const float4 sc = __ldg(reinterpret_cast<const float4 *>(scale + o0 + 4 * q));
+            v[4 * q] *= sc.x; v[4 * q + 1] *= sc.y; v[4 * q + 2] *= sc.z; v[4 * q + 3] *= sc.w;
+        }
+    }
+}
+__device__ __forceinline__ void epi_apply(int flags, float (&v)[32], const float *bias, const float *scale, int o0) {
+    switch (flags) {
+        case 1: epi_math<true, false, false>(v, bias, scale, o0); break;
+        case 2: epi_math<false, true, false>(v, bias, scale, o0); break;
+        case 3: epi_math<true, true, false>(v, bias, scale, o0); break;
+        case 4: epi_math<false, false, true>(v, bias, scale, o0); break;
+        case 5: epi_math<true, false, true>(v, bias, scale, o0); break;
+        case 6: epi_math<false, true, true>(v, bias, scale, o0); break;
+        case 7: epi_math<true, true, true>(v, bias, scale, o0); break;
+        default: break;
+    }
+}
+
 // =============================================================================================
 // v2: persistent, warp-specialised, TMEM double-buffered
 //
@@ -400,6 +436,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
         // so the only synchronisation inside the epilogue is __syncwarp.
         const int ew = warp - 4, quarter = ew & 3, chalf = ew >> 2;
         const uint32_t mybuf = epi0 + ew * (2 * EPI_BUF);
+        const int eflags = (p.bias ? 1 : 0) | (p.act == TURTLE_ACT_GELU ? 2 : 0) | (p.scale ? 4 : 0);
         int it = 0;
         uint32_t gw = 0;                                     // this warp's staging-box use counter
         for (long long u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
@@ -425,23 +462,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
                     for (int ci = 0; ci < nc; ++ci) {
                         float v[32];
                         tmem_ld32(trow + (j + ci) * 32, v);
-                        const int o0 = n0 + (j + ci) * 32;
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const int o = o0 + 4 * q;
-                            if (p.bias) {
-                                float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + o));
-                                v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
-                            }
-                            if (p.act == TURTLE_ACT_GELU) {
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) v[4 * q + e] = gelu_fast(v[4 * q + e]);
-                            }
-                            if (p.scale) {
-                                float4 sc = __ldg(reinterpret_cast<const float4 *>(p.scale + o));
-                                v[4 * q] *= sc.x; v[4 * q + 1] *= sc.y; v[4 * q + 2] *= sc.z; v[4 * q + 3] *= sc.w;
-                            }
-                        }
+                        epi_apply(eflags, v, p.bias, p.scale, n0 + (j + ci) * 32);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             // nc == 2: 128-byte rows, SWIZZLE_128B (16 B chunk ^= row & 7); nc == 1: 64-byte rows, SWIZZLE_64B
@@ -481,23 +502,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
                     __syncwarp();
                     float v[32];
                     tmem_ld32(trow + j * 32, v);
-                    const int o0 = n0 + j * 32;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const int o = o0 + 4 * q;
-                        if (p.bias) {
-                            float4 bb = __ldg(reinterpret_cast<const float4 *>(p.bias + o));
-                            v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
-                        }
-                        if (p.act == TURTLE_ACT_GELU) {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) v[4 * q + e] = gelu_fast(v[4 * q + e]);
-                        }
-                        if (p.scale) {
-                            float4 sc = __ldg(reinterpret_cast<const float4 *>(p.scale + o));
-                            v[4 * q] *= sc.x; v[4 * q + 1] *= sc.y; v[4 * q + 2] *= sc.z; v[4 * q + 3] *= sc.w;
-                        }
-                    }
+                    epi_apply(eflags, v, p.bias, p.scale, n0 + j * 32);
                     if (O16) {
                         // fp16 output: 32 rows x 64 B, SWIZZLE_64B (16 B chunk ^= (row>>1)&3)
                         const uint32_t rowaddr = buf + lane * 64;

@@ -442,10 +442,16 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const float *__restrict_
 int turtle_dwconv3x3_tma(const float *x, int ldx, const float *w, const float *bias, float *y, int ldy, int NB, int H,
                          int W, int C, int fuse, int layout, int ws, int rnd, void *stream);   // dwconv_tma.cu (rnd==2: fp16 in/out)
 
+int turtle_dwconv3x3_h16(const void *x, int ldx, const void *w9, const float *bias, void *y, int ldy, int NB, int H,
+                         int W, int C, int fuse, void *stream);                                  // dwconv16.cu
+
 extern "C" int turtle_dwconv3x3(const float *x, int ldx, const float *w, const float *bias, float *y, int ldy,
                                 int NB, int H, int W, int C, int fuse, int layout, int ws, int round_tf32, void *stream) {
     const int rnd = round_tf32;     // 2: x and y are fp16 (ldx/ldy in halves); tensor-core mode only
-    if (rnd == 2) return turtle_dwconv3x3_tma(x, ldx, w, bias, y, ldy, NB, H, W, C, fuse, layout, ws, rnd, stream);
+    if (rnd == 2) {                 // fp16 map, fp16 taps [9,C], fp32 bias (dwconv16.cu)
+        if (layout != 0) return TURTLE_ENOTSUP;
+        return turtle_dwconv3x3_h16(x, ldx, w, bias, y, ldy, NB, H, W, C, fuse, stream);
+    }
     if (!x || !w || !y || NB < 1 || C < 4 || fuse < 0 || fuse > 2 || (ldx & 3)) return TURTLE_EINVAL;
     int Cout = fuse == 2 ? C / 2 : C;
     if ((Cout & 3) || (fuse == 2 && (C & 7))) return TURTLE_EINVAL;

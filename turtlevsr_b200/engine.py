@@ -79,6 +79,11 @@ class FrameEngine:
         e0.record()
         call(name, *args)
         e1.record()
+        if self.profile_shapes and name in ("turtle_dwconv3x3", "turtle_layernorm"):
+            if name == "turtle_dwconv3x3":      # (x, ldx, w, b, y, ldy, NB, H, W, C, fuse, layout, ws, rnd, stream)
+                name += f"|C{args[9]}@{args[6]}x{args[7]}x{args[8]}|fuse{args[10]}|lay{args[11]}|rnd{args[13]}"
+            else:                               # (x, ldx, w, b, y, ldy, P, C, rnd, stream)
+                name += f"|C{args[7]}@{args[6]}|rnd{args[8]}"
         self.profile.setdefault("_events", []).append((name, e0, e1, self._meta))
         self._meta = (0, 0)
 
@@ -132,6 +137,8 @@ class FrameEngine:
             t = p.contiguous()
         elif kind == "dw":                # [C,1,k,k] -> tap-major [k*k, C]
             t = p.reshape(p.shape[0], -1).t().contiguous()
+        elif kind == "dw16":              # the same, fp16 (taps of the fp16 depthwise kernel)
+            t = p.reshape(p.shape[0], -1).t().contiguous().half()
         elif kind == "dw_lo" or kind == "dw_hi":     # halves of a depthwise weight (T0 q/k patches)
             h = p.shape[0] // 2
             q = p[:h] if kind == "dw_lo" else p[h:]
@@ -178,13 +185,15 @@ class FrameEngine:
         a.out_dtype = 1 if o16 else 0
         if self.profile is not None:
             K = (9 if im2col else len(segs)) * segw
-            self._meta = (4 * (P * K + Cout * K + P * Cout * (2 if res else 1)), 2 * P * K * Cout)
+            ea, eo = (2 if a16 else 4), (2 if o16 else 4)
+            self._meta = (ea * (P * K + Cout * K) + eo * P * Cout + (4 * P * Cout if res else 0), 2 * P * K * Cout)
         name = "turtle_gemm"
         if self.profile is not None:
             name = "turtle_gemm[conv3x3]" if im2col else "turtle_gemm[1x1]"
             if self.profile_shapes:
                 Kt = (9 if im2col else len(segs)) * segw
-                name += f"|{Kt}->{Cout}@{P}" + ("+res" if res else "") + (f"/{len(segs)}seg" if len(segs) > 1 else "")
+                name += (f"|{Kt}->{Cout}@{P}" + ("+res" if res else "") + (f"/{len(segs)}seg" if len(segs) > 1 else "")
+                         + ("|a16" if a16 else "") + ("|o16" if o16 else ""))
         self._call_gemm(name, a)
 
     def _call_gemm(self, tag, a):
@@ -241,7 +250,7 @@ class FrameEngine:
                          bias=self._w(pre + "project_in.bias"), a16=True, o16=True)
             g = self.ws.get("dw16", P, hid, dtype=torch.float16)
             self._meta = (2 * P * (hid2 + hid), 2 * 9 * P * hid2)
-            self._call("turtle_dwconv3x3", _ptr(t), hid2, _ptr(self._w(pre + "dwconv.weight", "dw")),
+            self._call("turtle_dwconv3x3", _ptr(t), hid2, _ptr(self._w(pre + "dwconv.weight", "dw16")),
                        _ptr(self._w(pre + "dwconv.bias")), _ptr(g), hid, B, H, W, hid2, 2, 0, 1, 2, self.stream)
             self.conv1x1(_ptr(g), hid, hid, pre + "project_out.weight", _ptr(x), c, P, c,
                          bias=self._w(pre + "project_out.bias"), res=_ptr(x), ldres=c, a16=True)
@@ -278,7 +287,7 @@ class FrameEngine:
                          bias=self._w(pre + "conv1.bias"), a16=True, o16=True)
             u = self.ws.get("dw16", P, 2 * c, dtype=torch.float16)
             self._meta = (2 * P * 4 * c, 2 * 9 * P * 2 * c)
-            self._call("turtle_dwconv3x3", _ptr(t), 2 * c, _ptr(self._w(pre + "conv2.weight", "dw")),
+            self._call("turtle_dwconv3x3", _ptr(t), 2 * c, _ptr(self._w(pre + "conv2.weight", "dw16")),
                        _ptr(self._w(pre + "conv2.bias")), _ptr(u), 2 * c, B, H, W, 2 * c, 1, 0, 1, 2, self.stream)
             self.conv1x1(_ptr(u), 2 * c, 2 * c, pre + "conv3.weight", _ptr(x), c, P, c, bias=self._w(pre + "conv3.bias"),
                          scale=self._w(pre + "beta"), res=_ptr(x), ldres=c, a16=True)
@@ -313,7 +322,7 @@ class FrameEngine:
         qd = self.ws.get("dw16" if h16 else "dw", P, 3 * c, dtype=dt)
         if h16:
             self._meta = (2 * P * 6 * c, 2 * 9 * P * 3 * c)
-            self._call("turtle_dwconv3x3", _ptr(qkv), 3 * c, _ptr(self._w(pre + "qkv_dwconv.weight", "dw")),
+            self._call("turtle_dwconv3x3", _ptr(qkv), 3 * c, _ptr(self._w(pre + "qkv_dwconv.weight", "dw16")),
                        _ptr(self._w(pre + "qkv_dwconv.bias")), _ptr(qd), 3 * c, B, H, W, 3 * c, 0, 0, 1, 2, self.stream)
         else:
             self.dwconv(_ptr(qkv), 3 * c, pre + "qkv_dwconv.weight", pre + "qkv_dwconv.bias", _ptr(qd), 3 * c, B, H, W,
