@@ -50,6 +50,7 @@ extern "C" {
 #define TURTLE_SAB_SLOTS 48  /* 5 top-k + 41 local-window entries, padded to 48 */
 
 int turtle_abi_version(void);          /* bumps when a signature changes */
+int turtle_sizeof_gemm_args(void);       /* sizeof(TurtleGemmArgs) as compiled: bindings check their mirror of the struct */
 const char *turtle_build_info(void);   /* "sm_100a nvcc <ver> ..." */
 
 /* ---------------------------------------------------------------------------------------
@@ -121,6 +122,12 @@ typedef struct TurtleGemmArgs {
     int32_t a_dtype;     /* 0: A segments and Wt are fp32 (TF32 MMA); 1: they are fp16 (kind::f16 MMA). TURTLE_TF32 only;
                             lda counts elements of that type, the pointers are carried in the float* slots */
     int32_t out_dtype;   /* 0: out is fp32; 1: out is fp16 (ldo in halves; no residual, plain store) */
+    /* Fused WithBias LayerNorm of the rows just produced (T1:96-112: the norm1/norm2 that reads this output next):
+       ln_out[p,:] = fp16( (out[p,:]-mu)/sqrt(var_biased+1e-5)*ln_w + ln_b ),  ld_ln in halves.
+       TURTLE_TF32 only; needs Cout in {64,128,256}, a residual, a plain fp32 store; else TURTLE_ENOTSUP. */
+    void *ln_out;        /* or NULL */
+    int32_t ld_ln;
+    const float *ln_w, *ln_b;
 } TurtleGemmArgs;
 
 int turtle_gemm(const TurtleGemmArgs *args, void *stream);

@@ -134,3 +134,36 @@ def test_chan_gram_fp16(P, heads, nsplit):
     assert (g.sum(0).cpu().double() - want).abs().max() < 1e-5 * P ** 0.5 * 8
     assert (sqq.sum(0).cpu().double() - (xd[:, :c] ** 2).sum(0)).abs().max() < 1e-5 * P
     assert (sqk.sum(0).cpu().double() - (xd[:, c:2 * c] ** 2).sum(0)).abs().max() < 1e-5 * P
+
+
+@pytest.mark.parametrize("a16", [True, False])
+@pytest.mark.parametrize("Cin,C_,P", [(160, 64, 777), (320, 128, 1000), (640, 256, 300), (64, 64, 130)])
+def test_gemm_fused_layernorm(Cin, C_, P, a16):
+    """x += A W^T (+bias)(*scale); ln_out = fp16(LayerNorm(x) * w + b) produced by the same launch."""
+    A = rnd(P, Cin)
+    Wt = rnd(C_, Cin, seed=3) / Cin ** 0.5
+    if a16:
+        A, Wt = A.half(), Wt.half()
+    A, Wt = A.cuda(), Wt.cuda()
+    bias, scale = rnd(C_, seed=4).cuda(), rnd(C_, seed=5).cuda()
+    lw, lb = (rnd(C_, seed=7) * 0.5 + 1).cuda(), rnd(C_, seed=8).cuda()
+    x = (rnd(P, C_, seed=6) * 2 + 0.7).cuda()
+    xn = torch.full((P, C_), float("nan"), device="cuda", dtype=torch.float16)
+    want_x = (A.cpu().double() @ Wt.cpu().double().t() + bias.cpu().double()) * scale.cpu().double() + x.cpu().double()
+    a = GemmArgs()
+    a.mode, a.im2col, a.P, a.Cout, a.nseg, a.segw = capi.TF32, 0, P, C_, 1, Cin
+    a.A[0], a.lda[0] = A.data_ptr(), Cin
+    a.Wt, a.bias, a.scale = Wt.data_ptr(), bias.data_ptr(), scale.data_ptr()
+    a.res, a.ldres, a.out, a.ldo, a.store = x.data_ptr(), C_, x.data_ptr(), C_, capi.STORE_PLAIN
+    a.a_dtype = 1 if a16 else 0
+    a.ln_out, a.ld_ln, a.ln_w, a.ln_b = xn.data_ptr(), C_, lw.data_ptr(), lb.data_ptr()
+    call("turtle_gemm", C.byref(a), stream())
+    got_x = x.cpu().double()
+    tol = (1e-5 if a16 else 3e-3) * want_x.abs().max()
+    assert (got_x - want_x).abs().max() < tol
+    # the normalisation is checked against the rows the kernel actually stored
+    mu = got_x.mean(-1, keepdim=True)
+    var = ((got_x - mu) ** 2).mean(-1, keepdim=True)
+    want_n = (got_x - mu) / (var + 1e-5).sqrt() * lw.cpu().double() + lb.cpu().double()
+    ok, worst = close16(xn.cpu(), want_n, extra=2e-5)
+    assert ok, worst

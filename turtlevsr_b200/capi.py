@@ -27,11 +27,13 @@ class GemmArgs(C.Structure):
         ("nseg", _i32), ("segw", _i32), ("A", _fp * MAX_SEG), ("lda", _i32 * MAX_SEG), ("Wt", _fp),
         ("bias", _fp), ("scale", _fp), ("act", _i32), ("res", _fp), ("ldres", _i32), ("out", _fp),
         ("ldo", _i32), ("store", _i32), ("round_out", _i32), ("a_dtype", _i32), ("out_dtype", _i32),
+        ("ln_out", _fp), ("ld_ln", _i32), ("ln_w", _fp), ("ln_b", _fp),
     ]
 
 
 _SIGS = {
     "turtle_abi_version": ([], C.c_int),
+    "turtle_sizeof_gemm_args": ([], C.c_int),
     "turtle_build_info": ([], C.c_char_p),
     "turtle_pack_frame": ([_fp, _i64, _fp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _fp], C.c_int),
     "turtle_conv3x3_first": ([_fp, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _i32, _fp], C.c_int),
@@ -61,7 +63,7 @@ launch_count = 0          # number of kernel-launching C-ABI calls made by this 
 
 
 class TurtleKernelError(RuntimeError):
-    pass
+    code = 0
 
 
 def lib_path() -> str:
@@ -80,6 +82,8 @@ def load():
     for name, (argtypes, restype) in _SIGS.items():
         fn = getattr(lib, name)       # AttributeError if a declared symbol is not exported
         fn.argtypes, fn.restype = argtypes, restype
+    if lib.turtle_sizeof_gemm_args() != C.sizeof(GemmArgs):
+        raise TurtleKernelError("GemmArgs does not mirror TurtleGemmArgs of the loaded library (stale build?)")
     _lib = lib
     return lib
 
@@ -90,4 +94,6 @@ def call(name: str, *args) -> None:
     rc = getattr(load(), name)(*args)
     launch_count += 1
     if rc != 0:
-        raise TurtleKernelError(f"{name} failed with code {rc}")
+        err = TurtleKernelError(f"{name} failed with code {rc}")
+        err.code = rc
+        raise err

@@ -127,74 +127,121 @@ __global__ void __launch_bounds__(256) gram_generic_kernel(const float *__restri
     }
 }
 
-__global__ void __launch_bounds__(128) chan_softmax_kernel(const float *__restrict__ gpart,
+// One block per attention row (i, h).  The Gram / norm partials of the pixel splits are summed by 4 thread groups in
+// parallel (each thread keeps 8 independent loads in flight; the kernel used to be bound by the latency of nsplit
+// serial strided loads per thread) and combined in a fixed order, so the result is run-to-run deterministic.
+__global__ void __launch_bounds__(256) chan_softmax_kernel(const float *__restrict__ gpart,
                                                            const float *__restrict__ sqq,
                                                            const float *__restrict__ sqk,
                                                            const int32_t *__restrict__ prenorm,
                                                            const float *__restrict__ temperature, int nseg,
                                                            int nsplit, int heads, int ch, float *__restrict__ Pout,
                                                            float *__restrict__ inv_knorm) {
-    __shared__ float red[4];
+    __shared__ float ps[4][64], pk[4][64], lg[512], red[8];
     __shared__ float bc;
     const int i = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
     const int C = heads * ch, ncol = nseg * ch;
+    const int part = tid >> 6, j = tid & 63;
     const int64_t seg_stride = (int64_t)nsplit * heads * ch * ch;
-    float nq = 0.f;
-    for (int s = 0; s < nsplit; ++s) nq += sqq[(int64_t)s * C + h * ch + i];
+    // sum of base[s * stride] over the splits s = first, first + step, ...
+    auto split_sum = [&](const float *base, int64_t stride, int first, int step) {
+        float a8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        int s = first;
+        for (; s + 7 * step < nsplit; s += 8 * step) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a8[u] += __ldg(base + (int64_t)(s + u * step) * stride);
+        }
+        for (; s < nsplit; s += step) a8[0] += __ldg(base + (int64_t)s * stride);
+        return ((a8[0] + a8[1]) + (a8[2] + a8[3])) + ((a8[4] + a8[5]) + (a8[6] + a8[7]));
+    };
+    auto block_sum = [&](float v) {           // all threads get the total; fixed order
+        v = warp_sum(v);
+        __syncthreads();
+        if ((tid & 31) == 0) red[tid >> 5] = v;
+        __syncthreads();
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w];
+        return t;
+    };
+    const float nq = block_sum(split_sum(sqq + h * ch + i, C, tid, 256));
     const float inv_q = 1.0f / fmaxf(sqrtf(nq), 1e-12f);
     const float tau = temperature[h];
-    float logit[4];   // ncol <= 512 -> up to 4 columns per thread
-    float mx = -INFINITY;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        int c = tid + 128 * r;
-        logit[r] = -INFINITY;
-        if (c < ncol) {
-            int seg = c / ch, j = c - seg * ch;
-            float g = 0.f;
-            const float *gp = gpart + seg * seg_stride + ((int64_t)h * ch + i) * ch + j;
-            for (int s = 0; s < nsplit; ++s) g += gp[(int64_t)s * heads * ch * ch];
+    for (int seg = 0; seg < nseg; ++seg) {
+        const bool pre = prenorm[seg] != 0;
+        if (j < ch) {
+            ps[part][j] = split_sum(gpart + seg * seg_stride + ((int64_t)h * ch + i) * ch + j, (int64_t)heads * ch * ch, part, 4);
+            if (!pre) pk[part][j] = split_sum(sqk + (int64_t)seg * nsplit * C + h * ch + j, C, part, 4);
+        }
+        __syncthreads();
+        if (tid < ch) {
+            const float g = (ps[0][tid] + ps[1][tid]) + (ps[2][tid] + ps[3][tid]);
             float inv_k = 1.0f;
-            if (!prenorm[seg]) {
-                float nk = 0.f;
-                const float *kp = sqk + (int64_t)seg * nsplit * C + h * ch + j;
-                for (int s = 0; s < nsplit; ++s) nk += kp[(int64_t)s * C];
+            if (!pre) {
+                const float nk = (pk[0][tid] + pk[1][tid]) + (pk[2][tid] + pk[3][tid]);
                 inv_k = 1.0f / fmaxf(sqrtf(nk), 1e-12f);
             }
-            if (i == 0 && inv_knorm) inv_knorm[(int64_t)seg * C + h * ch + j] = inv_k;
-            logit[r] = g * inv_q * inv_k * tau;
-            mx = fmaxf(mx, logit[r]);
+            if (i == 0 && inv_knorm) inv_knorm[(int64_t)seg * C + h * ch + tid] = inv_k;
+            lg[seg * ch + tid] = g * inv_q * inv_k * tau;
         }
+        __syncthreads();
     }
+    float mx = -INFINITY;
+    for (int c = tid; c < ncol; c += 256) mx = fmaxf(mx, lg[c]);
     mx = warp_max(mx);
     if ((tid & 31) == 0) red[tid >> 5] = mx;
     __syncthreads();
-    if (tid == 0) bc = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    if (tid == 0) {
+        float m = red[0];
+        for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+        bc = m;
+    }
     __syncthreads();
     mx = bc;
-    float e[4], sum = 0.f;
+    float e[2], sum = 0.f;      // ncol <= 512
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        int c = tid + 128 * r;
-        e[r] = c < ncol ? expf(logit[r] - mx) : 0.f;
+    for (int r = 0; r < 2; ++r) {
+        const int c = tid + 256 * r;
+        e[r] = c < ncol ? expf(lg[c] - mx) : 0.f;
         sum += e[r];
     }
-    sum = warp_sum(sum);
-    __syncthreads();
-    if ((tid & 31) == 0) red[tid >> 5] = sum;
-    __syncthreads();
-    if (tid == 0) bc = (red[0] + red[1]) + (red[2] + red[3]);
-    __syncthreads();
-    sum = bc;
+    sum = block_sum(sum);
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        int c = tid + 128 * r;
+    for (int r = 0; r < 2; ++r) {
+        const int c = tid + 256 * r;
         if (c < ncol) Pout[((int64_t)h * ch + i) * ncol + c] = e[r] / sum;
     }
 }
 
-__global__ void chan_fold_kernel(const float *__restrict__ Pm, const float *__restrict__ Wo, int nseg, int heads,
-                                 int ch, float *__restrict__ M, int rnd) {
+// M[o, seg, h, j] = sum_i Wo[o, h*ch+i] * P[h, i, seg*ch+j]: thread = 4 consecutive j (128-bit loads of the P rows)
+__global__ void __launch_bounds__(256) chan_fold_kernel(const float *__restrict__ Pm, const float *__restrict__ Wo,
+                                                        int nseg, int heads, int ch, float *__restrict__ M, int rnd) {
+    const int C = heads * ch, ncolP = nseg * ch, K = nseg * C;
+    const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (idx >= (int64_t)C * K) return;
+    const int col = (int)(idx % K), o = (int)(idx / K);
+    const int seg = col / C, r = col - seg * C, h = r / ch, j = r - h * ch;
+    const float *wp = Wo + (int64_t)o * C + h * ch;
+    const float *pp = Pm + ((int64_t)h * ch) * ncolP + seg * ch + j;
+    float4 acc = make_float4(0, 0, 0, 0);
+#pragma unroll 8
+    for (int i = 0; i < ch; ++i) {
+        const float w = __ldg(wp + i);
+        const float4 pv = __ldg(reinterpret_cast<const float4 *>(pp + (int64_t)i * ncolP));
+        acc.x = fmaf(w, pv.x, acc.x); acc.y = fmaf(w, pv.y, acc.y); acc.z = fmaf(w, pv.z, acc.z); acc.w = fmaf(w, pv.w, acc.w);
+    }
+    if (rnd == 2) {                                   // fp16 weights for kind::f16
+        const __half2 h0 = __floats2half2_rn(acc.x, acc.y), h1 = __floats2half2_rn(acc.z, acc.w);
+        *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(M) + idx) =
+            make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+    } else {
+        *reinterpret_cast<float4 *>(M + idx) = rnd ? rna_tf32(acc) : acc;
+    }
+}
+
+// scalar variant for head widths that are not a multiple of 4
+__global__ void chan_fold_scalar_kernel(const float *__restrict__ Pm, const float *__restrict__ Wo, int nseg, int heads,
+                                        int ch, float *__restrict__ M, int rnd) {
     const int C = heads * ch, ncolP = nseg * ch, K = nseg * C;
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)C * K) return;
@@ -204,7 +251,7 @@ __global__ void chan_fold_kernel(const float *__restrict__ Pm, const float *__re
     const float *pp = Pm + ((int64_t)h * ch) * ncolP + seg * ch + j;
     float acc = 0.f;
     for (int i = 0; i < ch; ++i) acc = fmaf(__ldg(wp + i), __ldg(pp + (int64_t)i * ncolP), acc);
-    if (rnd == 2) reinterpret_cast<__half *>(M)[idx] = __float2half_rn(acc);     // fp16 weights for kind::f16
+    if (rnd == 2) reinterpret_cast<__half *>(M)[idx] = __float2half_rn(acc);
     else M[idx] = rnd ? rna_tf32(acc) : acc;
 }
 
@@ -240,10 +287,10 @@ extern "C" int turtle_chan_gram(const float *q, int ldq, int q_hs, const float *
 extern "C" int turtle_chan_softmax(const float *gpart, const float *sqq, const float *sqk, const int32_t *seg_prenorm,
                                    const float *temperature, int nseg, int nsplit, int heads, int ch, float *Pout,
                                    float *inv_knorm, void *stream) {
-    if (!gpart || !sqq || !sqk || !seg_prenorm || !temperature || !Pout || nseg < 1 || nseg * ch > 512)
+    if (!gpart || !sqq || !sqk || !seg_prenorm || !temperature || !Pout || nseg < 1 || ch > 64 || nseg * ch > 512)
         return TURTLE_EINVAL;
     dim3 grid(ch, heads);
-    chan_softmax_kernel<<<grid, 128, 0, as_stream(stream)>>>(gpart, sqq, sqk, seg_prenorm, temperature, nseg, nsplit,
+    chan_softmax_kernel<<<grid, 256, 0, as_stream(stream)>>>(gpart, sqq, sqk, seg_prenorm, temperature, nseg, nsplit,
                                                             heads, ch, Pout, inv_knorm);
     TURTLE_CHECK_LAUNCH();
     return TURTLE_OK;
@@ -253,7 +300,10 @@ extern "C" int turtle_chan_fold(const float *Pm, const float *Wo, int nseg, int 
                                 void *stream) {
     if (!Pm || !Wo || !M) return TURTLE_EINVAL;
     int64_t total = (int64_t)heads * ch * nseg * heads * ch;
-    chan_fold_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, as_stream(stream)>>>(Pm, Wo, nseg, heads, ch, M, round_tf32);
+    if (!(ch & 3) && !(((uintptr_t)Pm | (uintptr_t)M) & 15))
+        chan_fold_kernel<<<(unsigned)cdiv64(total / 4, 256), 256, 0, as_stream(stream)>>>(Pm, Wo, nseg, heads, ch, M, round_tf32);
+    else
+        chan_fold_scalar_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, as_stream(stream)>>>(Pm, Wo, nseg, heads, ch, M, round_tf32);
     TURTLE_CHECK_LAUNCH();
     return TURTLE_OK;
 }

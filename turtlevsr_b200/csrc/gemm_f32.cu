@@ -167,10 +167,12 @@ extern "C" int turtle_gemm(const TurtleGemmArgs *a, void *stream) {
     if (a->store == TURTLE_STORE_PLAIN && ((a->ldo & 3) || ((uintptr_t)a->out & 15))) return TURTLE_EINVAL;
     if (a->res && ((a->ldres & 3) || ((uintptr_t)a->res & 15))) return TURTLE_EINVAL;
     if ((a->a_dtype || a->out_dtype) && a->mode != TURTLE_TF32) return TURTLE_EINVAL;   // fp16 I/O is a tensor-core feature
+    if (a->ln_out && (a->mode != TURTLE_TF32 || !a->ln_w || !a->ln_b || (a->ld_ln & 7) || ((uintptr_t)a->ln_out & 15)))
+        return TURTLE_EINVAL;
     if (a->mode == TURTLE_TF32) {
         int r = turtle_gemm_tc(a, stream);
         if (r != TURTLE_ENOTSUP) return r;
-        if (a->a_dtype || a->out_dtype) return TURTLE_ENOTSUP;
+        if (a->a_dtype || a->out_dtype || a->ln_out) return TURTLE_ENOTSUP;
         // shapes the tensor-core kernel does not cover run on the CUDA-core kernel (still on device)
     }
     GemmParams g;

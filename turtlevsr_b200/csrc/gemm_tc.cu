@@ -317,6 +317,9 @@ __device__ __forceinline__ void epi_apply(int flags, float (&v)[32], const float
 struct alignas(64) Tc2Params {
     CUtensorMap mapA[MAX_TC_SEG];
     CUtensorMap mapW, mapOut, mapRes, mapOut2;   // mapOut2: fp16 out, 64-column (128 B) boxes
+    CUtensorMap mapLN;                           // fused LayerNorm output (fp16, 32x32 boxes, SWIZZLE_64B)
+    const float *ln_w, *ln_b;
+    int ln;
     int nseg, kb_per_seg, kb_per_sub;
     int nkb, stages;
     int im2col, BW, BH, B, H, W, tiles_x, tiles_y;
@@ -339,6 +342,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2], rfull_bar[EPI_WARPS][2];
     __shared__ uint32_t tmem_base_sh;
+    __shared__ float2 lnstat[2][4][2][32];      // fused LN: (mean, M2) of each row half, [tile parity][quarter][chalf][lane]
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t stage_bytes = A_STAGE_BYTES + (uint32_t)p.NG * TK * 4;
@@ -439,6 +443,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
         const int eflags = (p.bias ? 1 : 0) | (p.act == TURTLE_ACT_GELU ? 2 : 0) | (p.scale ? 4 : 0);
         int it = 0;
         uint32_t gw = 0;                                     // this warp's staging-box use counter
+        uint32_t rph = 0;                                    // fused-LN path: residual-barrier phase bit per box
         for (long long u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
             const int ng = (int)(u % p.ngroups);
             const long long tile = u / p.ngroups;
@@ -485,6 +490,105 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     j += nc;
+                }
+            } else if (!O16 && p.tma_epi && p.ln) {
+                // -------- residual update + fused LayerNorm of the updated rows (NG == Cout) --------
+                // pass 1: x = acc(+bias)(*scale) + res -> TMA store (fp32) ; x parked back in TMEM ; running (mean, M2)
+                // exchange the row statistics with the warp that owns the other chunk parity of the same rows
+                // pass 2: TMEM -> (x - mu) * rstd * w + b -> fp16 -> TMA store
+                const int m0 = (int)(tile * TM) + quarter * 32;
+                const int nch = NG / 32;
+                float mean = 0.f, M2 = 0.f, cnt = 0.f;
+                for (int j = chalf; j < nch; j += 2, ++gw) {
+                    const int b = gw & 1;
+                    const uint32_t buf = mybuf + b * EPI_BUF;
+                    const uint32_t rb = smem_u32(&rfull_bar[ew][b]);
+                    if (lane == 0) {
+                        if (gw >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        mbar_expect_tx(rb, EPI_BUF);
+                        tma_load_2d(buf, &p.mapRes, n0 + j * 32, m0, rb);
+                    }
+                    __syncwarp();
+                    float v[32];
+                    tmem_ld32(trow + j * 32, v);
+                    epi_apply(eflags, v, p.bias, p.scale, n0 + j * 32);
+                    mbar_wait(rb, (rph >> b) & 1u);       // gw also counts pass-2 boxes here: track the phase per box
+                    rph ^= 1u << b;
+                    const uint32_t rowaddr = buf + lane * 128;
+                    float cs = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const uint32_t addr = rowaddr + (((uint32_t)q ^ ((uint32_t)lane & 7u)) << 4);
+                        float4 r;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                     : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                                     : "r"(addr));
+                        v[4 * q] += r.x; v[4 * q + 1] += r.y; v[4 * q + 2] += r.z; v[4 * q + 3] += r.w;
+                        cs += (v[4 * q] + v[4 * q + 1]) + (v[4 * q + 2] + v[4 * q + 3]);
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v[4 * q]), "f"(v[4 * q + 1]),
+                                     "f"(v[4 * q + 2]), "f"(v[4 * q + 3])
+                                     : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&p.mapOut, buf, n0 + j * 32, m0);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    tmem_st32(trow + j * 32, v);
+                    // chunk statistics (two-pass inside the chunk), merged with Chan's formula
+                    const float cm = cs * (1.0f / 32.0f);
+                    float cM2 = 0.f;
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) cM2 = fmaf(v[e] - cm, v[e] - cm, cM2);
+                    const float tot = cnt + 32.0f, delta = cm - mean;
+                    mean = fmaf(delta, 32.0f / tot, mean);
+                    M2 += cM2 + delta * delta * (cnt * 32.0f / tot);
+                    cnt = tot;
+                }
+                tmem_wait_st();
+                lnstat[it & 1][quarter][chalf][lane] = make_float2(mean, M2);
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+                const float2 o = lnstat[it & 1][quarter][chalf ^ 1][lane];
+                const float dl = o.x - mean;
+                const float mu = fmaf(0.5f, dl, mean);
+                const float var = (M2 + o.y + dl * dl * cnt * 0.5f) / (2.0f * cnt);
+                const float rstd = rsqrtf(var + 1e-5f);
+                for (int j = chalf; j < nch; j += 2, ++gw) {
+                    const int b = gw & 1;
+                    const uint32_t buf = mybuf + b * EPI_BUF;
+                    if (lane == 0 && gw >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+                    float v[32];
+                    tmem_ld32(trow + j * 32, v);
+                    const int o0 = n0 + j * 32;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 w4 = __ldg(reinterpret_cast<const float4 *>(p.ln_w + o0 + 4 * q));
+                        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.ln_b + o0 + 4 * q));
+                        v[4 * q] = fmaf((v[4 * q] - mu) * rstd, w4.x, b4.x);
+                        v[4 * q + 1] = fmaf((v[4 * q + 1] - mu) * rstd, w4.y, b4.y);
+                        v[4 * q + 2] = fmaf((v[4 * q + 2] - mu) * rstd, w4.z, b4.z);
+                        v[4 * q + 3] = fmaf((v[4 * q + 3] - mu) * rstd, w4.w, b4.w);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {     // 32 rows x 64 B, SWIZZLE_64B (16 B chunk ^= (row>>1)&3)
+                        const uint32_t addr = buf + lane * 64 + (((uint32_t)q ^ (((uint32_t)lane >> 1) & 3u)) << 4);
+                        __half2 h0 = __floats2half2_rn(v[8 * q + 0], v[8 * q + 1]);
+                        __half2 h1 = __floats2half2_rn(v[8 * q + 2], v[8 * q + 3]);
+                        __half2 h2 = __floats2half2_rn(v[8 * q + 4], v[8 * q + 5]);
+                        __half2 h3 = __floats2half2_rn(v[8 * q + 6], v[8 * q + 7]);
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(*reinterpret_cast<uint32_t *>(&h0)),
+                                     "r"(*reinterpret_cast<uint32_t *>(&h1)), "r"(*reinterpret_cast<uint32_t *>(&h2)),
+                                     "r"(*reinterpret_cast<uint32_t *>(&h3))
+                                     : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&p.mapLN, buf, n0 + j * 32, m0);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
                 }
             } else if (p.tma_epi) {
                 const int m0 = (int)(tile * TM) + quarter * 32;
@@ -802,7 +906,7 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
     }
     p.total_units = tiles * p.ngroups;
     const size_t stage_bytes = A_STAGE_BYTES + (size_t)NG * TK * 4;
-    const size_t max_smem = 232448 - 2048;   // 227 KB opt-in limit minus the kernel's static smem
+    const size_t max_smem = 232448 - 6144;   // 227 KB opt-in limit minus the kernel's static smem (barriers, LN statistics)
     int stages = (int)((max_smem - 1024 - EPI_BYTES) / stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) return TURTLE_ENOTSUP;
@@ -822,7 +926,17 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
             uint64_t sr[1] = {(uint64_t)a->ldres * 4};
             ok = get_map(&p.mapRes, a->res, 2, dims, sr, box);
         }
+        if (ok && a->ln_out) {
+            uint64_t sl[1] = {(uint64_t)a->ld_ln * 2};
+            ok = turtle_get_tmap2(&p.mapLN, a->ln_out, 2, dims, sl, box, 3, 1);
+        }
         p.tma_epi = ok ? 1 : 0;
+    }
+    p.ln = 0;
+    if (a->ln_out) {
+        // the row statistics need the whole row in one n-group, split evenly between the two chunk parities
+        if (!p.tma_epi || o16 || !a->res || p.ngroups != 1 || (NG != 64 && NG != 128 && NG != 256)) return TURTLE_ENOTSUP;
+        p.ln = 1; p.ln_w = a->ln_w; p.ln_b = a->ln_b;
     }
     const size_t smem = stages * stage_bytes + EPI_BYTES + 1024;
     if (o16 && !p.tma_epi) return TURTLE_ENOTSUP;
@@ -858,7 +972,7 @@ int turtle_gemm_tc(const TurtleGemmArgs *a, void *stream) {
     if (!a->a_dtype && a->segw % TK) return TURTLE_ENOTSUP;
     if (((uintptr_t)a->Wt & 15) || ((uintptr_t)a->out & 15)) return TURTLE_ENOTSUP;
     static const bool use_v1 = getenv("TURTLE_GEMM_V1") != nullptr;
-    const bool half_io = a->a_dtype || a->out_dtype;
+    const bool half_io = a->a_dtype || a->out_dtype || a->ln_out;
     if (!use_v1 || half_io) {
         int r = turtle_gemm_tc2(a, stream);
         if (r != TURTLE_ENOTSUP || half_io) return r;
@@ -868,6 +982,7 @@ int turtle_gemm_tc(const TurtleGemmArgs *a, void *stream) {
 
 int turtle_gemm_tc_v1(const TurtleGemmArgs *a, void *stream) {
     const int Cout = a->Cout;
+    if (a->ln_out) return TURTLE_ENOTSUP;
     if (Cout % 16 || Cout < 16) return TURTLE_ENOTSUP;
     if (a->segw % TK) return TURTLE_ENOTSUP;
     if (((uintptr_t)a->Wt & 15) || ((uintptr_t)a->out & 15)) return TURTLE_ENOTSUP;

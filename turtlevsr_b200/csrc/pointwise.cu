@@ -99,12 +99,81 @@ __global__ void conv3x3_first_kernel(const float *__restrict__ x, const float *_
     stg_stream(y + p * Cout + g * 4, acc);
 }
 
+
+// first conv, tiled: persistent blocks keep the [9][CIN][Cout] weights in shared memory; a thread produces 4 consecutive
+// pixels x 4 output channels (each weight LDS.128 feeds 16 FMAs; the 6x3 input window lives in registers).
+template <int CIN>
+__global__ void __launch_bounds__(256) conv3x3_first_quad_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                                 const float *__restrict__ bias, float *__restrict__ y,
+                                                                 int B, int H, int W, int Cout) {
+    extern __shared__ float ws[];   // [9][CIN][Cout]
+    for (int i = threadIdx.x; i < 9 * CIN * Cout; i += blockDim.x) {
+        int co = i % Cout, ci = (i / Cout) % CIN, tap = i / (Cout * CIN);
+        ws[i] = w[((int64_t)co * CIN + ci) * 9 + tap];
+    }
+    __syncthreads();
+    const int groups = Cout >> 2, W4 = W >> 2;
+    const int64_t total = (int64_t)B * H * W4 * groups;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int g = (int)(idx % groups);
+        const int64_t q = idx / groups;
+        const int px0 = (int)(q % W4) * 4, py = (int)((q / W4) % H);
+        const int64_t b = q / ((int64_t)W4 * H);
+        float4 acc[4];
+        const float4 b4 = bias ? *reinterpret_cast<const float4 *>(bias + g * 4) : make_float4(0, 0, 0, 0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i] = b4;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int yy = py + ky - 1;
+            if (yy < 0 || yy >= H) continue;
+            float in[6][CIN];
+            const float *row = x + ((b * H + yy) * W) * CIN;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const int xx = px0 + c - 1;
+                const bool ok = xx >= 0 && xx < W;
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci) in[c][ci] = ok ? __ldg(row + (int64_t)xx * CIN + ci) : 0.f;
+            }
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+#pragma unroll
+                for (int ci = 0; ci < CIN; ++ci) {
+                    const float4 wv = *reinterpret_cast<const float4 *>(ws + ((ky * 3 + kx) * CIN + ci) * Cout + g * 4);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float v = in[i + kx][ci];
+                        acc[i].x = fmaf(v, wv.x, acc[i].x);
+                        acc[i].y = fmaf(v, wv.y, acc[i].y);
+                        acc[i].z = fmaf(v, wv.z, acc[i].z);
+                        acc[i].w = fmaf(v, wv.w, acc[i].w);
+                    }
+                }
+            }
+        }
+        float *yp = y + (((b * H + py) * W) + px0) * (int64_t)Cout + g * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) stg_stream(yp + (int64_t)i * Cout, acc[i]);
+    }
+}
+
 extern "C" int turtle_conv3x3_first(const float *x, const float *w, const float *bias, float *y, int B, int H,
                                     int W, int Cin, int Cout, void *stream) {
     if (!x || !w || !y || Cin < 1 || Cin > 16 || Cout < 4 || (Cout & 3)) return TURTLE_EINVAL;
     size_t smem = (size_t)9 * Cin * Cout * sizeof(float);
     if (smem > 48 * 1024) return TURTLE_EINVAL;
     int64_t total = (int64_t)B * H * W * (Cout >> 2);
+    if ((Cin == 3 || Cin == 6) && !(W & 3) && !((uintptr_t)y & 15)) {
+        const int64_t quads = total >> 2;
+        const unsigned grid = (unsigned)(cdiv64(quads, 256) < 148 * 8 ? cdiv64(quads, 256) : 148 * 8);
+        if (Cin == 3)
+            conv3x3_first_quad_kernel<3><<<grid, 256, smem, as_stream(stream)>>>(x, w, bias, y, B, H, W, Cout);
+        else
+            conv3x3_first_quad_kernel<6><<<grid, 256, smem, as_stream(stream)>>>(x, w, bias, y, B, H, W, Cout);
+        TURTLE_CHECK_LAUNCH();
+        return TURTLE_OK;
+    }
     conv3x3_first_kernel<<<(unsigned)cdiv64(total, 256), 256, smem, as_stream(stream)>>>(x, w, bias, y, B, H, W,
                                                                                         Cin, Cout);
     TURTLE_CHECK_LAUNCH();
@@ -160,10 +229,92 @@ __global__ void conv3x3_last_kernel(const float *__restrict__ x, const float *__
     }
 }
 
+
+// last conv, warp-cooperative (Cin == 64): a warp produces 8 consecutive output pixels.  Half-warp lanes hold one float4
+// of the 64 input channels each (coalesced 256 B per pixel), taps are the outer loop so every weight LDS.128 feeds four
+// pixel pairs, and the 16-lane partial sums are combined with xor shuffles.
+__global__ void __launch_bounds__(256) conv3x3_last_warp_kernel(const float *__restrict__ x, const float *__restrict__ w,
+                                                                const float *__restrict__ bias,
+                                                                const float *__restrict__ cur, int cur_ld, int cur_coff,
+                                                                float *__restrict__ out, int B, int H, int W, int Cout,
+                                                                int Hc, int Wc) {
+    constexpr int CIN = 64;
+    __shared__ __align__(16) float ws[3 * 9 * CIN];   // [co][tap][ci], rows of unused output channels are zero
+    for (int i = threadIdx.x; i < 3 * 9 * CIN; i += blockDim.x) {
+        int ci = i % CIN, tap = (i / CIN) % 9, co = i / (9 * CIN);
+        ws[i] = co < Cout ? w[((int64_t)co * CIN + ci) * 9 + tap] : 0.f;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, sub = lane >> 4, l16 = lane & 15;
+    const int W8 = (Wc + 7) >> 3;
+    const int64_t nw = (int64_t)B * Hc * W8;
+    for (int64_t wi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wi < nw;
+         wi += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+        const int x0 = (int)(wi % W8) * 8, py = (int)((wi / W8) % Hc);
+        const int64_t b = wi / ((int64_t)W8 * Hc);
+        float acc[4][3];
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp) acc[pp][0] = acc[pp][1] = acc[pp][2] = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int yy = py + ky - 1;
+            if (yy < 0 || yy >= H) continue;                     // warp-uniform
+            const float *row = x + ((b * H + yy) * W) * (int64_t)CIN + l16 * 4;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                float4 wv[3];
+#pragma unroll
+                for (int co = 0; co < 3; ++co)
+                    wv[co] = *reinterpret_cast<const float4 *>(ws + (co * 9 + ky * 3 + kx) * CIN + l16 * 4);
+#pragma unroll
+                for (int pp = 0; pp < 4; ++pp) {
+                    const int xx = x0 + 2 * pp + sub + kx - 1;
+                    float4 v = make_float4(0, 0, 0, 0);
+                    if (xx >= 0 && xx < W) v = __ldg(reinterpret_cast<const float4 *>(row + (int64_t)xx * CIN));
+#pragma unroll
+                    for (int co = 0; co < 3; ++co)
+                        acc[pp][co] = fmaf(v.x, wv[co].x, fmaf(v.y, wv[co].y, fmaf(v.z, wv[co].z, fmaf(v.w, wv[co].w, acc[pp][co]))));
+                }
+            }
+        }
+#pragma unroll
+        for (int pp = 0; pp < 4; ++pp)
+#pragma unroll
+            for (int co = 0; co < 3; ++co) {
+                float a = acc[pp][co];
+                a += __shfl_xor_sync(0xffffffffu, a, 8);
+                a += __shfl_xor_sync(0xffffffffu, a, 4);
+                a += __shfl_xor_sync(0xffffffffu, a, 2);
+                a += __shfl_xor_sync(0xffffffffu, a, 1);
+                acc[pp][co] = a;
+            }
+        // lanes 0..2 of each half write channel co = l16 of their four pixels
+        if (l16 < Cout) {
+#pragma unroll
+            for (int pp = 0; pp < 4; ++pp) {
+                const int px = x0 + 2 * pp + sub;
+                if (px < Wc) {
+                    const float a = l16 == 0 ? acc[pp][0] : l16 == 1 ? acc[pp][1] : acc[pp][2];
+                    const float c = __ldg(cur + ((b * H + py) * W + px) * (int64_t)cur_ld + cur_coff + l16);
+                    out[((b * Cout + l16) * Hc + py) * (int64_t)Wc + px] = a + (bias ? bias[l16] : 0.f) + c;
+                }
+            }
+        }
+    }
+}
+
 extern "C" int turtle_conv3x3_last(const float *x, const float *w, const float *bias, const float *cur, int cur_ld,
                                    int cur_coff, float *out, int B, int H, int W, int Cin, int Cout, int Hc, int Wc,
                                    void *stream) {
     if (!x || !w || !cur || !out || Cout < 1 || Cout > 4 || (Cin & 3) || Hc > H || Wc > W) return TURTLE_EINVAL;
+    if (Cin == 64 && Cout <= 3 && !((uintptr_t)x & 15)) {
+        const int64_t nw = (int64_t)B * Hc * ((Wc + 7) >> 3);
+        const int64_t blocks = cdiv64(nw, 8);
+        conv3x3_last_warp_kernel<<<(unsigned)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, as_stream(stream)>>>(
+            x, w, bias, cur, cur_ld, cur_coff, out, B, H, W, Cout, Hc, Wc);
+        TURTLE_CHECK_LAUNCH();
+        return TURTLE_OK;
+    }
     size_t smem = (size_t)Cout * 9 * Cin * sizeof(float);
     if (smem > 48 * 1024) return TURTLE_EINVAL;
     int64_t total = (int64_t)B * Hc * Wc;
@@ -539,7 +690,8 @@ extern "C" int turtle_add_posenc(const float *x, float *y, int B, int H, int W, 
     return TURTLE_OK;
 }
 
-extern "C" int turtle_abi_version(void) { return 2; }
+extern "C" int turtle_abi_version(void) { return 3; }
+extern "C" int turtle_sizeof_gemm_args(void) { return (int)sizeof(TurtleGemmArgs); }
 extern "C" const char *turtle_build_info(void) {
     return "libturtle_b200 sm_100a, CUDA "
 #define TURTLE_STR2(x) #x

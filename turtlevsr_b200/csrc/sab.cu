@@ -55,6 +55,63 @@ __global__ void __launch_bounds__(256) window_reduce_kernel(const float *__restr
     }
 }
 
+// vectorised variant (D % 4 == 0, D/4 a power of two <= 128): the 256 threads are G = 1024/D pixel groups of D/4 float4
+// lanes, each group strides over the window's pixels with independent 128-bit loads, then the groups are summed through
+// shared memory.  (The scalar kernel above used D of the 256 threads and kept one 4-byte load in flight.)
+__global__ void __launch_bounds__(256) window_reduce_vec_kernel(const float *__restrict__ t, int ldt,
+                                                                const float *__restrict__ wk /* [ws*ws][D] */,
+                                                                float *__restrict__ out, int64_t out_bstride, int H,
+                                                                int W, int D, int ws) {
+    __shared__ float4 part[256];
+    __shared__ float red[8];
+    __shared__ float bc;
+    const int Wg = W / ws;
+    const int n = blockIdx.x, b = blockIdx.y;
+    const int gi = n / Wg, gj = n % Wg;
+    const int tid = threadIdx.x;
+    const int L = D >> 2, G = 256 / L;
+    const int lane = tid % L, grp = tid / L;
+    const int y0 = gi * ws - 1, x0 = gj * ws - 1;
+    float4 acc = make_float4(0, 0, 0, 0);
+    const float *tb = t + (int64_t)b * H * W * ldt + lane * 4;
+    const float *wb = wk + lane * 4;
+#pragma unroll 4
+    for (int pidx = grp; pidx < ws * ws; pidx += G) {
+        const int ky = pidx / ws, kx = pidx - ky * ws;
+        const int y = y0 + ky, x = x0 + kx;
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+            const float4 v = ldg_stream(tb + ((int64_t)y * W + x) * ldt);
+            const float4 w4 = __ldg(reinterpret_cast<const float4 *>(wb + (int64_t)pidx * D));
+            acc.x = fmaf(v.x, w4.x, acc.x); acc.y = fmaf(v.y, w4.y, acc.y);
+            acc.z = fmaf(v.z, w4.z, acc.z); acc.w = fmaf(v.w, w4.w, acc.w);
+        }
+    }
+    part[tid] = acc;
+    __syncthreads();
+    float ss = 0.f;
+    if (tid < L) {
+        for (int g = 1; g < G; ++g) {          // fixed order: deterministic
+            const float4 o = part[g * L + tid];
+            acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        }
+        ss = acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
+    }
+    ss = warp_sum(ss);
+    if ((tid & 31) == 0) red[tid >> 5] = ss;
+    __syncthreads();
+    if (tid == 0) {
+        float s_ = 0.f;
+        for (int i = 0; i < 8; ++i) s_ += red[i];
+        bc = fmaxf(sqrtf(s_), 1e-12f);
+    }
+    __syncthreads();
+    if (tid < L) {
+        const float nrm = bc;
+        float *op = out + (int64_t)b * out_bstride + (int64_t)n * D + tid * 4;
+        *reinterpret_cast<float4 *>(op) = make_float4(acc.x / nrm, acc.y / nrm, acc.z / nrm, acc.w / nrm);
+    }
+}
+
 // in-place row L2 normalisation (T0 q/k patches); one block per row
 __global__ void __launch_bounds__(256) row_normalize_kernel(float *__restrict__ rows, int D) {
     __shared__ float red[8];
@@ -431,7 +488,12 @@ extern "C" int turtle_sab_window_reduce(const float *t, int ldt, const float *w,
                                         int B, int H, int W, int D, int ws, void *stream) {
     if (!t || !w || !out || D < 1 || D > 512 || ws < 1 || H % ws || W % ws) return TURTLE_EINVAL;
     dim3 grid((H / ws) * (W / ws), B);
-    window_reduce_kernel<<<grid, 256, 0, as_stream(stream)>>>(t, ldt, w, out, out_bstride, H, W, D, ws);
+    const int L = D >> 2;
+    if (!(D & 3) && L >= 1 && L <= 128 && !(L & (L - 1)) && !(ldt & 3) && !(out_bstride & 3) &&
+        !(((uintptr_t)t | (uintptr_t)w | (uintptr_t)out) & 15))
+        window_reduce_vec_kernel<<<grid, 256, 0, as_stream(stream)>>>(t, ldt, w, out, out_bstride, H, W, D, ws);
+    else
+        window_reduce_kernel<<<grid, 256, 0, as_stream(stream)>>>(t, ldt, w, out, out_bstride, H, W, D, ws);
     TURTLE_CHECK_LAUNCH();
     return TURTLE_OK;
 }

@@ -157,8 +157,9 @@ class FrameEngine:
     # kernel wrappers
     # ------------------------------------------------------------------------------------
     def gemm(self, segs, segw, Wt, out, ldo, P, Cout, bias=None, scale=None, act=0, res=None, ldres=0,
-             im2col=0, geom=None, store=0, round_out=False, a16=False, o16=False):
-        """segs: list of (ptr:int, lda:int).  round_out: the result feeds another tensor-core op."""
+             im2col=0, geom=None, store=0, round_out=False, a16=False, o16=False, ln=None):
+        """segs: list of (ptr:int, lda:int).  round_out: the result feeds another tensor-core op.
+        ln = (out_ptr, ld, norm_prefix): also emit fp16 LayerNorm(out rows) for the norm that reads them next."""
         a = GemmArgs()
         a.mode = self.mode
         a.im2col = im2col
@@ -183,29 +184,45 @@ class FrameEngine:
         a.round_out = 1 if (round_out and self.mode == capi.TF32 and not o16) else 0
         a.a_dtype = 1 if a16 else 0
         a.out_dtype = 1 if o16 else 0
+        if ln is not None:
+            a.ln_out, a.ld_ln = ln[0], ln[1]
+            a.ln_w, a.ln_b = _ptr(self._w(ln[2] + "body.weight")), _ptr(self._w(ln[2] + "body.bias"))
         if self.profile is not None:
             K = (9 if im2col else len(segs)) * segw
             ea, eo = (2 if a16 else 4), (2 if o16 else 4)
-            self._meta = (ea * (P * K + Cout * K) + eo * P * Cout + (4 * P * Cout if res else 0), 2 * P * K * Cout)
+            self._meta = (ea * (P * K + Cout * K) + eo * P * Cout + (4 * P * Cout if res else 0)
+                          + (2 * P * Cout if ln is not None else 0), 2 * P * K * Cout)
         name = "turtle_gemm"
         if self.profile is not None:
             name = "turtle_gemm[conv3x3]" if im2col else "turtle_gemm[1x1]"
             if self.profile_shapes:
                 Kt = (9 if im2col else len(segs)) * segw
                 name += (f"|{Kt}->{Cout}@{P}" + ("+res" if res else "") + (f"/{len(segs)}seg" if len(segs) > 1 else "")
-                         + ("|a16" if a16 else "") + ("|o16" if o16 else ""))
+                         + ("|a16" if a16 else "") + ("|o16" if o16 else "") + ("|ln" if ln is not None else ""))
         self._call_gemm(name, a)
+
+    def _gemm_launch(self, a):
+        try:
+            call("turtle_gemm", C.byref(a), self.stream)
+        except capi.TurtleKernelError as e:
+            # the fused LayerNorm epilogue exists on the tensor-core kernel only: a shape that kernel does not cover
+            # (sub-32 head widths of reduced configs) runs without it and the norm stays a launch of its own
+            if e.code != capi.ENOTSUP or not a.ln_out:
+                raise
+            a.ln_out = None
+            self._fused = None
+            call("turtle_gemm", C.byref(a), self.stream)
 
     def _call_gemm(self, tag, a):
         if self.dry_run:
             self.launch_log.append("turtle_gemm")
             return
         if self.profile is None:
-            call("turtle_gemm", C.byref(a), self.stream)
+            self._gemm_launch(a)
             return
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        call("turtle_gemm", C.byref(a), self.stream)
+        self._gemm_launch(a)
         e1.record()
         self.profile.setdefault("_events", []).append((tag, e0, e1, self._meta))
         self._meta = (0, 0)
@@ -219,13 +236,35 @@ class FrameEngine:
         return (self.mode == capi.TF32 and self.use_half and not self.dry_run
                 and chans[0] in (64, 128, 256, 512) and all(ch % 32 == 0 for ch in chans))
 
+    def ln_fusable(self, c: int, prefix: str) -> bool:
+        """Can the GEMM that updates the residual stream also emit fp16 LayerNorm(x) for norm ``prefix``?
+        (tensor-core mode, whole row in one n-group, WithBias norm)"""
+        return (self.mode == capi.TF32 and self.use_half and self.fuse_ln and not self.dry_run and c in (64, 128, 256)
+                and (prefix + "body.bias") in self._sd)
+
+    def ln_target(self, P: int, c: int, prefix: str, b0: int = 0, Pimg: int = 0):
+        """-> (ptr, ld, prefix) of the fp16 buffer the fused LayerNorm writes (rows b0*Pimg.. of it)."""
+        y = self.ws.get("xn16", P, c, dtype=torch.float16)
+        self._fused = (prefix, y)
+        return (_ptr(y, b0 * Pimg * c), c, prefix)
+
+    def take_fused(self, prefix: str):
+        f, self._fused = self._fused, None
+        if f is not None and f[0] == prefix:
+            return f[1]
+        return None
+
     def layernorm(self, x: torch.Tensor, pre: str, C_: int, P: int, half: bool = False) -> torch.Tensor:
         if half:
+            y = self.take_fused(pre)
+            if y is not None:
+                return y
             y = self.ws.get("xn16", P, C_, dtype=torch.float16)
             self._meta = (6 * P * C_, 0)
             self._call("turtle_layernorm", _ptr(x), C_, _ptr(self._w(pre + "body.weight")),
                        _ptr(self._w(pre + "body.bias")), _ptr(y), C_, P, C_, 2, self.stream)
             return y
+        self._fused = None
         y = self.ws.get("xn", P, C_)
         self._meta = (8 * P * C_, 0)
         self._call("turtle_layernorm", _ptr(x), C_, _ptr(self._w(pre + "body.weight")), _ptr(self._w(pre + "body.bias")),
@@ -241,7 +280,7 @@ class FrameEngine:
     # ------------------------------------------------------------------------------------
     # feed-forwards (x updated in place)
     # ------------------------------------------------------------------------------------
-    def gated_ffw(self, pre, xn, x, P, c, H, W, B):
+    def gated_ffw(self, pre, xn, x, P, c, H, W, B, ln=None):
         hid2 = self._sd[pre + "project_in.weight"].shape[0]
         hid = hid2 // 2
         if xn.dtype == torch.float16:       # fp16 intermediates, kind::f16 MMAs
@@ -253,7 +292,8 @@ class FrameEngine:
             self._call("turtle_dwconv3x3", _ptr(t), hid2, _ptr(self._w(pre + "dwconv.weight", "dw16")),
                        _ptr(self._w(pre + "dwconv.bias")), _ptr(g), hid, B, H, W, hid2, 2, 0, 1, 2, self.stream)
             self.conv1x1(_ptr(g), hid, hid, pre + "project_out.weight", _ptr(x), c, P, c,
-                         bias=self._w(pre + "project_out.bias"), res=_ptr(x), ldres=c, a16=True)
+                         bias=self._w(pre + "project_out.bias"), res=_ptr(x), ldres=c, a16=True,
+                         ln=self.ln_target(P, c, ln) if ln else None)
             return
         t = self.ws.get("wide", P, hid2)
         self.conv1x1(_ptr(xn), c, c, pre + "project_in.weight", _ptr(t), hid2, P, hid2,
@@ -263,13 +303,14 @@ class FrameEngine:
         self.conv1x1(_ptr(g), hid, hid, pre + "project_out.weight", _ptr(x), c, P, c,
                      bias=self._w(pre + "project_out.bias"), res=_ptr(x), ldres=c)
 
-    def plain_ffw(self, pre, xn, x, P, c):
+    def plain_ffw(self, pre, xn, x, P, c, ln=None):
         if xn.dtype == torch.float16:
             t = self.ws.get("wide16", P, 2 * c, dtype=torch.float16)
             self.conv1x1(_ptr(xn), c, c, pre + "conv4.weight", _ptr(t), 2 * c, P, 2 * c,
                          bias=self._w(pre + "conv4.bias"), act=capi.ACT_GELU, a16=True, o16=True)
             self.conv1x1(_ptr(t), 2 * c, 2 * c, pre + "conv5.weight", _ptr(x), c, P, c, bias=self._w(pre + "conv5.bias"),
-                         scale=self._w(pre + "gamma"), res=_ptr(x), ldres=c, a16=True)
+                         scale=self._w(pre + "gamma"), res=_ptr(x), ldres=c, a16=True,
+                         ln=self.ln_target(P, c, ln) if ln else None)
             return
         t = self.ws.get("wide", P, 2 * c)
         self.conv1x1(_ptr(xn), c, c, pre + "conv4.weight", _ptr(t), 2 * c, P, 2 * c, bias=self._w(pre + "conv4.bias"),
@@ -280,7 +321,7 @@ class FrameEngine:
     # ------------------------------------------------------------------------------------
     # attentions (x updated in place: x += attn(xn))
     # ------------------------------------------------------------------------------------
-    def reduced_attn(self, pre, xn, x, P, c, H, W, B):
+    def reduced_attn(self, pre, xn, x, P, c, H, W, B, ln=None):
         if xn.dtype == torch.float16:
             t = self.ws.get("wide16", P, 2 * c, dtype=torch.float16)
             self.conv1x1(_ptr(xn), c, c, pre + "conv1.weight", _ptr(t), 2 * c, P, 2 * c,
@@ -290,7 +331,8 @@ class FrameEngine:
             self._call("turtle_dwconv3x3", _ptr(t), 2 * c, _ptr(self._w(pre + "conv2.weight", "dw16")),
                        _ptr(self._w(pre + "conv2.bias")), _ptr(u), 2 * c, B, H, W, 2 * c, 1, 0, 1, 2, self.stream)
             self.conv1x1(_ptr(u), 2 * c, 2 * c, pre + "conv3.weight", _ptr(x), c, P, c, bias=self._w(pre + "conv3.bias"),
-                         scale=self._w(pre + "beta"), res=_ptr(x), ldres=c, a16=True)
+                         scale=self._w(pre + "beta"), res=_ptr(x), ldres=c, a16=True,
+                         ln=self.ln_target(P, c, ln) if ln else None)
             return
         t = self.ws.get("wide", P, 2 * c)
         self.conv1x1(_ptr(xn), c, c, pre + "conv1.weight", _ptr(t), 2 * c, P, 2 * c, bias=self._w(pre + "conv1.bias"))
@@ -300,7 +342,7 @@ class FrameEngine:
                      scale=self._w(pre + "beta"), res=_ptr(x), ldres=c)
 
     def channel_attn(self, pre, xn, x, B, H, W, c, heads, hist_segs=None, ring: Optional[FhrRing] = None,
-                     ring_slot: int = -1):
+                     ring_slot: int = -1, ln=None):
         """ChannelAttention / FrameHistoryRouter.
 
         hist_segs: per batch element a list of key/value history segments (oldest first), each
@@ -353,7 +395,8 @@ class FrameEngine:
             self._call("turtle_chan_fold", _ptr(Pm), _ptr(Wo), S, heads, ch, _ptr(M), 2 if h16 else self.rnd, self.stream)
             vsegs = [(sg["v"] + es * h * sg["vhs"], sg["ldv"]) for sg in segs for h in range(heads)]
             xb = _ptr(x, b * Pimg * c)
-            self.gemm(vsegs, ch, M, xb, c, Pimg, c, bias=self._w(pre + "project_out.bias"), res=xb, ldres=c, a16=h16)
+            self.gemm(vsegs, ch, M, xb, c, Pimg, c, bias=self._w(pre + "project_out.bias"), res=xb, ldres=c, a16=h16,
+                      ln=self.ln_target(P, c, ln, b, Pimg) if ln else None)
             if ring is not None:
                 self._call("turtle_scale_cols", _ptr(qd, base + c), 3 * c, ch, _ptr(inv[S - 1]),
                            ring.slot_ptr(ring.kbuf, b, ring_slot), ring.ld, ring.head_stride, Pimg, heads, ch,
@@ -372,7 +415,7 @@ class FrameEngine:
             self.packed[key] = t
         return t
 
-    def fhr(self, pre, xn, x, B, H, W, c, heads, keep, k_in, v_in):
+    def fhr(self, pre, xn, x, B, H, W, c, heads, keep, k_in, v_in, ln=None):
         """FrameHistoryRouter with its ring (latent blocks 0 and -1, T1:243-286)."""
         Pimg, ch = H * W, c // heads
         ring = resolve_ring(k_in, v_in)
@@ -389,12 +432,12 @@ class FrameEngine:
                 segs.append(dict(k=ring.slot_ptr(ring.kbuf, b, t), ldk=ring.ld, khs=ring.head_stride,
                                  v=ring.slot_ptr(ring.vbuf, b, t), ldv=ring.ld, vhs=ring.head_stride, prenorm=True))
             hist.append(segs)
-        self.channel_attn(pre, xn, x, B, H, W, c, heads, hist_segs=hist, ring=ring, ring_slot=slot)
+        self.channel_attn(pre, xn, x, B, H, W, c, heads, hist_segs=hist, ring=ring, ring_slot=slot, ln=ln)
         # the reference returns cat(history, new)[-K:]; the window after commit is exactly that
         ring.commit()
         return ring.views()
 
-    def chm(self, pre, xn, x, B, H, W, c, heads, scale_patch, keep, k_in, v_in):
+    def chm(self, pre, xn, x, B, H, W, c, heads, scale_patch, keep, k_in, v_in, ln=None):
         """CausalHistoryModel (T1:627-662) = StateAlignBlock (T1:548-610 / T0:459-533) + router."""
         t0 = self.model.variant == "t0"
         sa = pre + "spatial_aligner."
@@ -490,64 +533,84 @@ class FrameEngine:
                 segs.append(dict(k=_ptr(kvd, base), ldk=2 * c, khs=ch, v=_ptr(kvd, base + c), ldv=2 * c, vhs=ch,
                                  prenorm=False))
             hist.append(segs)
-        self.channel_attn(pre + "ChanAttn.", xn, x, B, H, W, c, heads, hist_segs=hist)
+        self.channel_attn(pre + "ChanAttn.", xn, x, B, H, W, c, heads, hist_segs=hist, ln=ln)
         return k_out, v_out
 
     # ------------------------------------------------------------------------------------
     # block / level
     # ------------------------------------------------------------------------------------
-    def block(self, pre, blk, x, B, H, W, c, lvl, k_in=None, v_in=None):
+    def _ffn_half(self, pre, blk, c) -> bool:
+        if blk.FFW_type == "GFFW":
+            return self.half_path(c, self._sd[pre + "ffn.project_in.weight"].shape[0] // 2)
+        return self.half_path(c, 2 * c)
+
+    def _attn_half(self, blk, c, lvl) -> bool:
+        at = blk.attention_type
+        return ((at == "ReducedAttn" and self.half_path(c, 2 * c)) or
+                (at == "Channel" and self.half_path(c) and c // lvl.num_heads == 64))
+
+    def _first_norm(self, pre, blk, c, lvl):
+        """(prefix, consumer takes fp16) of the first LayerNorm a block applies to its input."""
+        if blk.attention_type == "NoAttn":
+            return pre + "norm2.", self._ffn_half(pre, blk, c)
+        return pre + "norm1.", self._attn_half(blk, c, lvl)
+
+    def block(self, pre, blk, x, B, H, W, c, lvl, k_in=None, v_in=None, next_norm=None):
+        """next_norm: ``_first_norm`` of the block that reads x next (same map), or None.  Whenever the reader takes
+        fp16 and the row fits one n-group, the GEMM that finishes a residual update also emits that LayerNorm."""
         P = B * H * W
         kc = vc = None
         at = blk.attention_type
+        half = self._ffn_half(pre, blk, c)
         if at != "NoAttn":
-            half1 = (at == "ReducedAttn" and self.half_path(c, 2 * c)) or \
-                    (at == "Channel" and self.half_path(c) and c // lvl.num_heads == 64)
-            xn = self.layernorm(x, pre + "norm1.", c, P, half=half1)
+            xn = self.layernorm(x, pre + "norm1.", c, P, half=self._attn_half(blk, c, lvl))
             a = pre + "attn."
+            ln2 = pre + "norm2." if half and self.ln_fusable(c, pre + "norm2.") else None
             if at == "Channel":
-                self.channel_attn(a, xn, x, B, H, W, c, lvl.num_heads)
+                self.channel_attn(a, xn, x, B, H, W, c, lvl.num_heads, ln=ln2)
             elif at == "ReducedAttn":
-                self.reduced_attn(a, xn, x, P, c, H, W, B)
+                self.reduced_attn(a, xn, x, P, c, H, W, B, ln=ln2)
             elif at == "FHR":
-                kc, vc = self.fhr(a, xn, x, B, H, W, c, lvl.num_heads, lvl.num_frames_tocache, k_in, v_in)
+                kc, vc = self.fhr(a, xn, x, B, H, W, c, lvl.num_heads, lvl.num_frames_tocache, k_in, v_in, ln=ln2)
             elif at == "CHM":
                 kc, vc = self.chm(a, xn, x, B, H, W, c, lvl.num_heads, lvl.Scale_patchsize, lvl.num_frames_tocache,
-                                  k_in, v_in)
-        if blk.FFW_type == "GFFW":
-            hid2 = self._sd[pre + "ffn.project_in.weight"].shape[0]
-            half = self.half_path(c, hid2 // 2)
-        else:
-            half = self.half_path(c, 2 * c)
+                                  k_in, v_in, ln=ln2)
         xn = self.layernorm(x, pre + "norm2.", c, P, half=half)
+        nl = None
+        if next_norm is not None and next_norm[1] and xn.dtype == torch.float16 and self.ln_fusable(c, next_norm[0]):
+            nl = next_norm[0]
         if blk.FFW_type == "GFFW":
-            self.gated_ffw(pre + "ffn.", xn, x, P, c, H, W, B)
+            self.gated_ffw(pre + "ffn.", xn, x, P, c, H, W, B, ln=nl)
         else:
-            self.plain_ffw(pre + "ffn.", xn, x, P, c)
+            self.plain_ffw(pre + "ffn.", xn, x, P, c, ln=nl)
         return kc, vc
 
     def level(self, name, x, B, H, W, k_in=None, v_in=None):
         lvl = getattr(self.model, name)
-        n = len(lvl.transformer_blocks)
+        blocks = list(lvl.transformer_blocks)
+        n = len(blocks)
         kc = vc = None
-        for i, blk in enumerate(lvl.transformer_blocks):
+        for i, blk in enumerate(blocks):
             last = i == n - 1
+            nxt = None if last else self._first_norm(f"{name}.transformer_blocks.{i + 1}.", blocks[i + 1], lvl.dim, lvl)
             kc, vc = self.block(f"{name}.transformer_blocks.{i}.", blk, x, B, H, W, lvl.dim, lvl,
-                                k_in if last else None, v_in if last else None)
+                                k_in if last else None, v_in if last else None, next_norm=nxt)
         return kc, vc
 
     def latent(self, x, B, H, W, k1, v1, k2, v2):
         lvl = self.model.latent
-        n = len(lvl.transformer_blocks)
+        blocks = list(lvl.transformer_blocks)
+        n = len(blocks)
         out = [None] * 4
-        for i, blk in enumerate(lvl.transformer_blocks):
+        for i, blk in enumerate(blocks):
             pre = f"latent.transformer_blocks.{i}."
+            nxt = None if i == n - 1 else self._first_norm(f"latent.transformer_blocks.{i + 1}.", blocks[i + 1], lvl.dim, lvl)
             if i == 0:
-                out[0], out[1] = self.block(pre, blk, x, B, H, W, lvl.dim, lvl, k1, v1)
+                out[0], out[1] = self.block(pre, blk, x, B, H, W, lvl.dim, lvl, k1, v1, next_norm=nxt)
             elif i == n - 1:
-                out[2], out[3] = self.block(pre, blk, x, B, H, W, lvl.dim, lvl, k2, v2)
+                out[2], out[3] = self.block(pre, blk, x, B, H, W, lvl.dim, lvl, k2, v2, next_norm=nxt)
             else:
-                self.block(pre, blk, x, B, H, W, lvl.dim, lvl)
+                self.block(pre, blk, x, B, H, W, lvl.dim, lvl, next_norm=nxt)
         return out
 
     def conv3x3(self, x, Cin, wname, out, ldo, B, H, W, Cout, store, round_out=False):
@@ -575,6 +638,8 @@ class FrameEngine:
         self.mode = capi.TF32 if m.precision == "tf32" else capi.FP32
         self.rnd = 1 if self.mode == capi.TF32 else 0
         self.use_half = bool(getattr(m, "half_intermediates", True))
+        self.fuse_ln = bool(getattr(m, "fuse_layernorm", True))
+        self._fused = None
         self.trace = {} if getattr(m, "record_trace", False) else None
         inp = inp.float().contiguous()
         B, _, Cc, Hs, Ws = inp.shape
