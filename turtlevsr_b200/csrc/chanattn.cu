@@ -127,21 +127,21 @@ __global__ void __launch_bounds__(256) gram_generic_kernel(const float *__restri
     }
 }
 
-// One block per attention row (i, h).  The Gram / norm partials of the pixel splits are summed by 4 thread groups in
-// parallel (each thread keeps 8 independent loads in flight; the kernel used to be bound by the latency of nsplit
-// serial strided loads per thread) and combined in a fixed order, so the result is run-to-run deterministic.
-__global__ void __launch_bounds__(256) chan_softmax_kernel(const float *__restrict__ gpart,
-                                                           const float *__restrict__ sqq,
-                                                           const float *__restrict__ sqk,
-                                                           const int32_t *__restrict__ prenorm,
-                                                           const float *__restrict__ temperature, int nseg,
-                                                           int nsplit, int heads, int ch, float *__restrict__ Pout,
-                                                           float *__restrict__ inv_knorm) {
-    __shared__ float ps[4][64], pk[4][64], lg[512], red[8];
-    __shared__ float bc;
+// One block per attention row (i, h), 16 groups of 64 threads.  The Gram / norm partials of the pixel splits are summed
+// by (segment, quarter-of-the-splits) units spread over the groups, every thread keeping 8 independent loads in flight
+// (the kernel is pure L2 latency: the serial per-thread version took 21 us for a few MB), and combined in a fixed order,
+// so the result is run-to-run deterministic.
+__global__ void __launch_bounds__(1024) chan_softmax_kernel(const float *__restrict__ gpart,
+                                                            const float *__restrict__ sqq,
+                                                            const float *__restrict__ sqk,
+                                                            const int32_t *__restrict__ prenorm,
+                                                            const float *__restrict__ temperature, int nseg,
+                                                            int nsplit, int heads, int ch, float *__restrict__ Pout,
+                                                            float *__restrict__ inv_knorm) {
+    __shared__ float ps[8][4][64], pk[8][4][64], red[32];
     const int i = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
     const int C = heads * ch, ncol = nseg * ch;
-    const int part = tid >> 6, j = tid & 63;
+    const int grp = tid >> 6, j = tid & 63;
     const int64_t seg_stride = (int64_t)nsplit * heads * ch * ch;
     // sum of base[s * stride] over the splits s = first, first + step, ...
     auto split_sum = [&](const float *base, int64_t stride, int first, int step) {
@@ -161,85 +161,93 @@ __global__ void __launch_bounds__(256) chan_softmax_kernel(const float *__restri
         __syncthreads();
         float t = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) t += red[w];
+        for (int w = 0; w < 32; ++w) t += red[w];
         return t;
     };
-    const float nq = block_sum(split_sum(sqq + h * ch + i, C, tid, 256));
+    // all global partials are requested before the first barrier
+    float nqp = split_sum(sqq + h * ch + i, C, tid, 1024);
+    for (int u = grp; u < 4 * nseg; u += 16) {
+        const int seg = u >> 2, part = u & 3;
+        if (j < ch) {
+            ps[seg][part][j] = split_sum(gpart + seg * seg_stride + ((int64_t)h * ch + i) * ch + j, (int64_t)heads * ch * ch, part, 4);
+            if (!prenorm[seg]) pk[seg][part][j] = split_sum(sqk + (int64_t)seg * nsplit * C + h * ch + j, C, part, 4);
+        }
+    }
+    const float nq = block_sum(nqp);           // contains the barrier that publishes ps / pk
     const float inv_q = 1.0f / fmaxf(sqrtf(nq), 1e-12f);
     const float tau = temperature[h];
-    for (int seg = 0; seg < nseg; ++seg) {
-        const bool pre = prenorm[seg] != 0;
-        if (j < ch) {
-            ps[part][j] = split_sum(gpart + seg * seg_stride + ((int64_t)h * ch + i) * ch + j, (int64_t)heads * ch * ch, part, 4);
-            if (!pre) pk[part][j] = split_sum(sqk + (int64_t)seg * nsplit * C + h * ch + j, C, part, 4);
+    float mx = -INFINITY, lgc = -INFINITY;
+    if (tid < ncol) {
+        const int seg = tid / ch, jj = tid - seg * ch;
+        const float g = (ps[seg][0][jj] + ps[seg][1][jj]) + (ps[seg][2][jj] + ps[seg][3][jj]);
+        float inv_k = 1.0f;
+        if (!prenorm[seg]) {
+            const float nk = (pk[seg][0][jj] + pk[seg][1][jj]) + (pk[seg][2][jj] + pk[seg][3][jj]);
+            inv_k = 1.0f / fmaxf(sqrtf(nk), 1e-12f);
         }
-        __syncthreads();
-        if (tid < ch) {
-            const float g = (ps[0][tid] + ps[1][tid]) + (ps[2][tid] + ps[3][tid]);
-            float inv_k = 1.0f;
-            if (!pre) {
-                const float nk = (pk[0][tid] + pk[1][tid]) + (pk[2][tid] + pk[3][tid]);
-                inv_k = 1.0f / fmaxf(sqrtf(nk), 1e-12f);
-            }
-            if (i == 0 && inv_knorm) inv_knorm[(int64_t)seg * C + h * ch + tid] = inv_k;
-            lg[seg * ch + tid] = g * inv_q * inv_k * tau;
-        }
-        __syncthreads();
+        if (i == 0 && inv_knorm) inv_knorm[(int64_t)seg * C + h * ch + jj] = inv_k;
+        lgc = g * inv_q * inv_k * tau;
+        mx = lgc;
     }
-    float mx = -INFINITY;
-    for (int c = tid; c < ncol; c += 256) mx = fmaxf(mx, lg[c]);
     mx = warp_max(mx);
+    __syncthreads();
     if ((tid & 31) == 0) red[tid >> 5] = mx;
     __syncthreads();
-    if (tid == 0) {
-        float m = red[0];
-        for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
-        bc = m;
+    mx = red[0];
+#pragma unroll
+    for (int w = 1; w < 32; ++w) mx = fmaxf(mx, red[w]);
+    const float e = tid < ncol ? expf(lgc - mx) : 0.f;
+    const float sum = block_sum(e);
+    if (tid < ncol) Pout[((int64_t)h * ch + i) * ncol + tid] = e / sum;
+}
+
+// M[o, seg, h, j] = sum_i Wo[o, h*ch+i] * P[h, i, seg*ch+j]   (ch == 64)
+// One block per (64 output rows, head, segment): the 64x64 tile of Wo and the 64x64 block of P are fetched with one
+// round of coalesced 128-bit loads into shared memory (the per-thread 64-step global-load loop this replaces was pure
+// L2 latency: 22 us for a 4 MFLOP launch), then every thread produces a 4x4 register tile.
+__global__ void __launch_bounds__(256) chan_fold_tile_kernel(const float *__restrict__ Pm, const float *__restrict__ Wo,
+                                                             int nseg, int heads, float *__restrict__ M, int rnd) {
+    constexpr int CH = 64;
+    __shared__ float ws[CH][CH + 4];      // [o][i]  (+4: conflict-free column reads)
+    __shared__ float pt[CH][CH];          // [i][j]
+    const int ot = blockIdx.x, h = blockIdx.y, seg = blockIdx.z, tid = threadIdx.x;
+    const int C = heads * CH, ncolP = nseg * CH, K = nseg * C;
+    for (int e = tid; e < CH * CH / 4; e += 256) {
+        const int r = e >> 4, c4 = (e & 15) * 4;
+        const float4 w4 = __ldg(reinterpret_cast<const float4 *>(Wo + (int64_t)(ot * CH + r) * C + h * CH + c4));
+        ws[r][c4] = w4.x; ws[r][c4 + 1] = w4.y; ws[r][c4 + 2] = w4.z; ws[r][c4 + 3] = w4.w;
+        *reinterpret_cast<float4 *>(&pt[r][c4]) =
+            __ldg(reinterpret_cast<const float4 *>(Pm + ((int64_t)h * CH + r) * ncolP + seg * CH + c4));
     }
     __syncthreads();
-    mx = bc;
-    float e[2], sum = 0.f;      // ncol <= 512
+    const int o0 = (tid >> 4) * 4, j0 = (tid & 15) * 4;
+    float4 acc[4];
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const int c = tid + 256 * r;
-        e[r] = c < ncol ? expf(lg[c] - mx) : 0.f;
-        sum += e[r];
-    }
-    sum = block_sum(sum);
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-        const int c = tid + 256 * r;
-        if (c < ncol) Pout[((int64_t)h * ch + i) * ncol + c] = e[r] / sum;
-    }
-}
-
-// M[o, seg, h, j] = sum_i Wo[o, h*ch+i] * P[h, i, seg*ch+j]: thread = 4 consecutive j (128-bit loads of the P rows)
-__global__ void __launch_bounds__(256) chan_fold_kernel(const float *__restrict__ Pm, const float *__restrict__ Wo,
-                                                        int nseg, int heads, int ch, float *__restrict__ M, int rnd) {
-    const int C = heads * ch, ncolP = nseg * ch, K = nseg * C;
-    const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (idx >= (int64_t)C * K) return;
-    const int col = (int)(idx % K), o = (int)(idx / K);
-    const int seg = col / C, r = col - seg * C, h = r / ch, j = r - h * ch;
-    const float *wp = Wo + (int64_t)o * C + h * ch;
-    const float *pp = Pm + ((int64_t)h * ch) * ncolP + seg * ch + j;
-    float4 acc = make_float4(0, 0, 0, 0);
+    for (int r = 0; r < 4; ++r) acc[r] = make_float4(0, 0, 0, 0);
 #pragma unroll 8
-    for (int i = 0; i < ch; ++i) {
-        const float w = __ldg(wp + i);
-        const float4 pv = __ldg(reinterpret_cast<const float4 *>(pp + (int64_t)i * ncolP));
-        acc.x = fmaf(w, pv.x, acc.x); acc.y = fmaf(w, pv.y, acc.y); acc.z = fmaf(w, pv.z, acc.z); acc.w = fmaf(w, pv.w, acc.w);
+    for (int i = 0; i < CH; ++i) {
+        const float4 pv = *reinterpret_cast<const float4 *>(&pt[i][j0]);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float w = ws[o0 + r][i];
+            acc[r].x = fmaf(w, pv.x, acc[r].x); acc[r].y = fmaf(w, pv.y, acc[r].y);
+            acc[r].z = fmaf(w, pv.z, acc[r].z); acc[r].w = fmaf(w, pv.w, acc[r].w);
+        }
     }
-    if (rnd == 2) {                                   // fp16 weights for kind::f16
-        const __half2 h0 = __floats2half2_rn(acc.x, acc.y), h1 = __floats2half2_rn(acc.z, acc.w);
-        *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(M) + idx) =
-            make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
-    } else {
-        *reinterpret_cast<float4 *>(M + idx) = rnd ? rna_tf32(acc) : acc;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int64_t idx = (int64_t)(ot * CH + o0 + r) * K + (int64_t)seg * C + h * CH + j0;
+        if (rnd == 2) {                                   // fp16 weights for kind::f16
+            const __half2 h0 = __floats2half2_rn(acc[r].x, acc[r].y), h1 = __floats2half2_rn(acc[r].z, acc[r].w);
+            *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(M) + idx) =
+                make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+        } else {
+            *reinterpret_cast<float4 *>(M + idx) = rnd ? rna_tf32(acc[r]) : acc[r];
+        }
     }
 }
 
-// scalar variant for head widths that are not a multiple of 4
+// generic variant (any head width)
 __global__ void chan_fold_scalar_kernel(const float *__restrict__ Pm, const float *__restrict__ Wo, int nseg, int heads,
                                         int ch, float *__restrict__ M, int rnd) {
     const int C = heads * ch, ncolP = nseg * ch, K = nseg * C;
@@ -287,10 +295,10 @@ extern "C" int turtle_chan_gram(const float *q, int ldq, int q_hs, const float *
 extern "C" int turtle_chan_softmax(const float *gpart, const float *sqq, const float *sqk, const int32_t *seg_prenorm,
                                    const float *temperature, int nseg, int nsplit, int heads, int ch, float *Pout,
                                    float *inv_knorm, void *stream) {
-    if (!gpart || !sqq || !sqk || !seg_prenorm || !temperature || !Pout || nseg < 1 || ch > 64 || nseg * ch > 512)
+    if (!gpart || !sqq || !sqk || !seg_prenorm || !temperature || !Pout || nseg < 1 || nseg > 8 || ch > 64 || nseg * ch > 512)
         return TURTLE_EINVAL;
     dim3 grid(ch, heads);
-    chan_softmax_kernel<<<grid, 256, 0, as_stream(stream)>>>(gpart, sqq, sqk, seg_prenorm, temperature, nseg, nsplit,
+    chan_softmax_kernel<<<grid, 1024, 0, as_stream(stream)>>>(gpart, sqq, sqk, seg_prenorm, temperature, nseg, nsplit,
                                                             heads, ch, Pout, inv_knorm);
     TURTLE_CHECK_LAUNCH();
     return TURTLE_OK;
@@ -300,10 +308,12 @@ extern "C" int turtle_chan_fold(const float *Pm, const float *Wo, int nseg, int 
                                 void *stream) {
     if (!Pm || !Wo || !M) return TURTLE_EINVAL;
     int64_t total = (int64_t)heads * ch * nseg * heads * ch;
-    if (!(ch & 3) && !(((uintptr_t)Pm | (uintptr_t)M) & 15))
-        chan_fold_kernel<<<(unsigned)cdiv64(total / 4, 256), 256, 0, as_stream(stream)>>>(Pm, Wo, nseg, heads, ch, M, round_tf32);
-    else
+    if (ch == 64 && !(((uintptr_t)Pm | (uintptr_t)M | (uintptr_t)Wo) & 15)) {
+        dim3 grid(heads, heads, nseg);          // (C/64 output tiles, heads, segments)
+        chan_fold_tile_kernel<<<grid, 256, 0, as_stream(stream)>>>(Pm, Wo, nseg, heads, M, round_tf32);
+    } else {
         chan_fold_scalar_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, as_stream(stream)>>>(Pm, Wo, nseg, heads, ch, M, round_tf32);
+    }
     TURTLE_CHECK_LAUNCH();
     return TURTLE_OK;
 }
