@@ -531,6 +531,7 @@ extern "C" int turtle_sab_aggregate(const int32_t *idx, const float *wgt, const 
         TURTLE_CHECK_LAUNCH();
         return TURTLE_OK;
     }
+    if (round_tf32 == 2) return TURTLE_ENOTSUP;     // fp16 output exists on the quad kernel only
     dim3 grid(Hg * Wg, F);
     sab_aggregate_kernel<<<grid, 256, 0, as_stream(stream)>>>(idx, wgt, v, v_fstride, y, Hg, Wg, ws, c, passthrough, round_tf32);
     TURTLE_CHECK_LAUNCH();

@@ -342,7 +342,7 @@ class FrameEngine:
                      scale=self._w(pre + "beta"), res=_ptr(x), ldres=c)
 
     def channel_attn(self, pre, xn, x, B, H, W, c, heads, hist_segs=None, ring: Optional[FhrRing] = None,
-                     ring_slot: int = -1, ln=None):
+                     ring_slot: int = -1, ln=None, force16: bool = False):
         """ChannelAttention / FrameHistoryRouter.
 
         hist_segs: per batch element a list of key/value history segments (oldest first), each
@@ -355,12 +355,13 @@ class FrameEngine:
         Pimg = H * W
         P = B * Pimg
         ch = c // heads
-        h16 = xn.dtype == torch.float16
+        a16 = xn.dtype == torch.float16
+        h16 = a16 or force16            # force16: fp32 (TF32) input rows, everything downstream of the qkv conv in fp16
         dt = torch.float16 if h16 else torch.float32
         es = 2 if h16 else 4
         qkv = self.ws.get("wide16" if h16 else "wide", P, 3 * c, dtype=dt)
         self.conv1x1(_ptr(xn), c, c, pre + "qkv.weight", _ptr(qkv), 3 * c, P, 3 * c, bias=self._w(pre + "qkv.bias"),
-                     a16=h16, o16=h16)
+                     a16=a16, o16=h16)
         qd = self.ws.get("dw16" if h16 else "dw", P, 3 * c, dtype=dt)
         if h16:
             self._meta = (2 * P * 6 * c, 2 * 9 * P * 3 * c)
@@ -492,7 +493,10 @@ class FrameEngine:
                 self._call("turtle_sab_patch_normalize", _ptr(ring.kbuf[b, slot]), N, Dk, self.stream)
 
         # --- selection + aggregation over the F live frames ------------------------------------
-        agg = self.ws.get("sab_agg", B, F_, Pimg, c)
+        # router side in fp16 (tensor-core mode): aligned frames, their kv maps and the inner channel attention
+        r16 = (not t0) and self.half_path(c, 2 * c) and c // heads == 64
+        dt16 = torch.float16 if r16 else torch.float32
+        agg = self.ws.get("sab_agg16" if r16 else "sab_agg", B, F_, Pimg, c, dtype=dt16)
         idx = self.ws.get("sab_idx", B, F_, N, capi.SAB_SLOTS, dtype=torch.int32)
         wgt = self.ws.get("sab_wgt", B, F_, N, capi.SAB_SLOTS)
         temp = self._w(sa + "temperature")
@@ -511,19 +515,25 @@ class FrameEngine:
                                _ptr(idx[b]), _ptr(wgt[b]), self.mode, self.stream)
             self._meta = (4 * (2 * F_ * N * Dv + 2 * F_ * N * capi.SAB_SLOTS), 2 * F_ * N * 46 * Dv)
             self._call("turtle_sab_aggregate", _ptr(idx[b]), _ptr(wgt[b]), vf, N * Dv, _ptr(agg[b]), F_, Hg, Wg, ws_, c,
-                 1 if t0 else 0, self.rnd, self.stream)
+                 1 if t0 else 0, 2 if r16 else self.rnd, self.stream)
         if self.trace is not None:
             self.trace.setdefault(sa, []).append(dict(idx=idx.clone(), wgt=wgt.clone(), qn=qn.clone()))
-        xs = self.ws.get("sab_xs", B, F_, Pimg, c)
-        self.conv1x1(_ptr(agg), c, c, sa + "project_out.weight", _ptr(xs), c, B * F_ * Pimg, c, round_out=True)
+        xs = self.ws.get("sab_xs16" if r16 else "sab_xs", B, F_, Pimg, c, dtype=dt16)
+        self.conv1x1(_ptr(agg), c, c, sa + "project_out.weight", _ptr(xs), c, B * F_ * Pimg, c, round_out=True,
+                     a16=r16, o16=r16)
         ring.commit()
         k_out, v_out = ring.views()
 
         # --- router over the aligned history (T1:649-660) ---------------------------------------
-        kv = self.ws.get("chm_kv", B * F_ * Pimg, 2 * c)
-        self.conv1x1(_ptr(xs), c, c, pre + "kv.weight", _ptr(kv), 2 * c, B * F_ * Pimg, 2 * c)
-        kvd = self.ws.get("chm_kvd", B, F_, Pimg, 2 * c)
-        self.dwconv(_ptr(kv), 2 * c, pre + "kv_dwconv.weight", None, _ptr(kvd), 2 * c, B * F_, H, W, 2 * c)
+        kv = self.ws.get("chm_kv16" if r16 else "chm_kv", B * F_ * Pimg, 2 * c, dtype=dt16)
+        self.conv1x1(_ptr(xs), c, c, pre + "kv.weight", _ptr(kv), 2 * c, B * F_ * Pimg, 2 * c, a16=r16, o16=r16)
+        kvd = self.ws.get("chm_kvd16" if r16 else "chm_kvd", B, F_, Pimg, 2 * c, dtype=dt16)
+        if r16:
+            self._meta = (2 * B * F_ * Pimg * 4 * c, 2 * 9 * B * F_ * Pimg * 2 * c)
+            self._call("turtle_dwconv3x3", _ptr(kv), 2 * c, _ptr(self._w(pre + "kv_dwconv.weight", "dw16")), None,
+                       _ptr(kvd), 2 * c, B * F_, H, W, 2 * c, 0, 0, 1, 2, self.stream)
+        else:
+            self.dwconv(_ptr(kv), 2 * c, pre + "kv_dwconv.weight", None, _ptr(kvd), 2 * c, B * F_, H, W, 2 * c)
         ch = c // heads
         hist = []
         for b in range(B):
@@ -533,7 +543,7 @@ class FrameEngine:
                 segs.append(dict(k=_ptr(kvd, base), ldk=2 * c, khs=ch, v=_ptr(kvd, base + c), ldv=2 * c, vhs=ch,
                                  prenorm=False))
             hist.append(segs)
-        self.channel_attn(pre + "ChanAttn.", xn, x, B, H, W, c, heads, hist_segs=hist, ln=ln)
+        self.channel_attn(pre + "ChanAttn.", xn, x, B, H, W, c, heads, hist_segs=hist, ln=ln, force16=r16)
         return k_out, v_out
 
     # ------------------------------------------------------------------------------------
