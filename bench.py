@@ -83,6 +83,18 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def measured_traffic(entry: str):
+    """DRAM read+write bytes per launch of a C-ABI entry point, from the newest committed ncu launch list
+    (profiles/*_traffic.json, written by scripts/ncu_frame_summary.py); None if there is none."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return None, None
+    d = json.load(open(files[-1]))
+    k = d.get("kernels", {}).get(entry)
+    return (k["dram_bytes_per_launch"], os.path.basename(files[-1])) if k else (None, None)
+
+
 def build_model(precision: str, device):
     from turtlevsr_b200.archs import create_video_model
     from turtlevsr_b200.configs import shipped
@@ -257,6 +269,11 @@ def main():
             ach = top["bytes"] / (top["ms"] * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
                     "traffic": None, "peak_note": f"{pk['src']} copy bandwidth"}
+        tr, tr_src = measured_traffic(top_name)
+        roof["traffic"] = tr
+        roof["traffic_note"] = (f"dram__bytes_read.sum + dram__bytes_write.sum per launch, {tr_src}" if tr else
+                                "no ncu capture committed")
+        roof["algorithmic_per_launch"] = (top["bytes"] if roof["bound"] == "hbm" else top["flops"]) / max(top["launches"], 1)
         roof.update(kernel=top_name, kernel_ms_per_frame=top["ms"], kernel_launches_per_frame=top["launches"],
                     kernel_share_of_frame=top["ms"] / total_ms,
                     per_kernel_ms={n: round(d["ms"], 3) for n, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])})
@@ -270,7 +287,10 @@ def main():
             "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD if (Hh, Ww) == (H720, W720) else WORKLOAD.replace("1280x720", f"{Ww}x{Hh}"),
                        "parallelism": f"clip-sharded x{world} (one clip per GPU, no collective)",
-                       "precision_mode": args.precision, "storage": "fp32 channels-last",
+                       "precision_mode": args.precision,
+                       "storage": ("fp32 channels-last residual stream and history rings; fp16 block intermediates, "
+                                   "TF32/fp16 tensor-core operands, fp32 accumulation" if args.precision == "tf32"
+                                   else "fp32 channels-last"),
                        "l2": "per-frame working set (several GB) >> 126 MB L2; no explicit flush"},
             "clocks": clk.summary(),
             "e2e": {"value": world * K / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,

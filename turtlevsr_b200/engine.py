@@ -194,8 +194,8 @@ class FrameEngine:
                           + (2 * P * Cout if ln is not None else 0), 2 * P * K * Cout)
         name = "turtle_gemm"
         if self.profile is not None:
-            name = "turtle_gemm[conv3x3]" if im2col else "turtle_gemm[1x1]"
             if self.profile_shapes:
+                name = "turtle_gemm[conv3x3]" if im2col else "turtle_gemm[1x1]"
                 Kt = (9 if im2col else len(segs)) * segw
                 name += (f"|{Kt}->{Cout}@{P}" + ("+res" if res else "") + (f"/{len(segs)}seg" if len(segs) > 1 else "")
                          + ("|a16" if a16 else "") + ("|o16" if o16 else "") + ("|ln" if ln is not None else ""))
