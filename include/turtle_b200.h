@@ -188,6 +188,9 @@ int turtle_scale_cols(const float *x, int ldx, int x_hs, const float *s, float *
  * batch stride out_bstride floats. */
 int turtle_sab_window_reduce(const float *t, int ldt, const float *w, float *out, int64_t out_bstride, int B,
                              int H, int W, int D, int ws, void *stream);
+/* the same on an fp16 map (ldt in halves; tensor-core mode intermediates); taps, sum and output stay fp32 */
+int turtle_sab_window_reduce_h16(const void *t, int ldt, const float *w, float *out, int64_t out_bstride, int B, int H,
+                                int W, int D, int ws, void *stream);
 
 /* 'b d (p1 h)(p2 w) -> b (h w) (p1 p2 d)' + F.normalize, for the T0 q/k path (T0:487-498). */
 int turtle_sab_patch_normalize(float *rows, int64_t n_rows, int D, void *stream);

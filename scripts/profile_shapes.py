@@ -21,6 +21,6 @@ with torch.no_grad():
 rows = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])
 tot = sum(d["ms"] for _, d in rows) / n
 print(f"total {tot:.2f} ms/frame")
-for name, d in rows[:60]:
+for name, d in rows:
     ms, L, by, fl = d["ms"] / n, d["launches"] / n, d["bytes"] / n, d["flops"] / n
     print(f"{name:58s} n={L:5.1f} {ms:8.3f} ms  {by/ms/1e6 if ms else 0:8.0f} GB/s  {fl/ms/1e9 if ms else 0:8.1f} TF/s  {by/1e9:7.2f} GB")

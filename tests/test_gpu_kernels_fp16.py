@@ -167,3 +167,18 @@ def test_gemm_fused_layernorm(Cin, C_, P, a16):
     want_n = (got_x - mu) / (var + 1e-5).sqrt() * lw.cpu().double() + lb.cpu().double()
     ok, worst = close16(xn.cpu(), want_n, extra=2e-5)
     assert ok, worst
+
+
+@pytest.mark.parametrize("ws,D", [(4, 64), (8, 128), (16, 32)])
+def test_sab_window_reduce_fp16_map(ws, D):
+    from oracle import turtle_oracle as orc
+    B, H, W = 2, 32, 48
+    t = rnd(B, H, W, D).half().cuda()
+    w = rnd(D, 1, ws, ws, seed=1)
+    td = t.cpu().float().permute(0, 3, 1, 2)
+    want = orc.l2norm_rows(F.conv2d(td, w, stride=ws, padding=1, groups=D).flatten(2).transpose(1, 2))
+    N = (H // ws) * (W // ws)
+    out = torch.full((B, N, D), float("nan"), device="cuda")
+    wk = w.reshape(D, -1).t().contiguous().cuda()
+    call("turtle_sab_window_reduce_h16", t.data_ptr(), D, wk.data_ptr(), out.data_ptr(), N * D, B, H, W, D, ws, stream())
+    assert (out.cpu() - want).abs().max() < 2e-5

@@ -195,3 +195,24 @@ def test_sr_long_sequence_history_stress():
         vb = [None if t is None else t.clone() for t in vb]
         assert torch.equal(oa, ob), f"frame {j}"
     assert oa.shape == (1, 3, 96, 128) and torch.isfinite(oa).all()
+
+
+def test_720p_benchmark_config_fast_mode_tracks_exact_mode():
+    """BASELINE cfg 2 at its full size (Gopro yml, 1280x720, live gates): the benchmarked tensor-core mode against the
+    exact fp32 mode of the same kernels (which the 480p / fixture tests pin to the reference): 2e-3 max-abs, 0.02 dB,
+    over enough frames to fill every history ring (K = 3)."""
+    from oracle.turtle_oracle import randomize_gates
+    from turtlevsr_b200.configs import shipped
+    opt = shipped("Turtle_Deblur_Gopro")
+    torch.manual_seed(opt["manual_seed"])
+    net = create_video_model(opt).eval()
+    sd = randomize_gates({k: v.detach().clone() for k, v in net.state_dict().items()}, seed=1234)
+    g = torch.Generator().manual_seed(720)
+    clip = torch.rand(1, 5, 3, 720, 1280, generator=g).cuda()
+    exact, _, _ = run_clip(build(opt, sd, "fp32"), clip)
+    fast, _, _ = run_clip(build(opt, sd, "tf32"), clip)
+    err = (fast - exact).abs().amax(dim=(0, 2, 3, 4))
+    dpsnr = abs(psnr(fast.cpu(), clip.cpu()) - psnr(exact.cpu(), clip.cpu()))
+    print(f"720p fast vs exact: per-frame max|d| {[f'{e:.2e}' for e in err.tolist()]}  dPSNR={dpsnr:.4f} dB")
+    assert err.max() < 2e-3 and dpsnr < 0.02
+    assert torch.isfinite(fast).all()

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(256) window_reduce_kernel(const float *__restr
 // vectorised variant (D % 4 == 0, D/4 a power of two <= 128): the 256 threads are G = 1024/D pixel groups of D/4 float4
 // lanes, each group strides over the window's pixels with independent 128-bit loads, then the groups are summed through
 // shared memory.  (The scalar kernel above used D of the 256 threads and kept one 4-byte load in flight.)
+template <bool H16>
 __global__ void __launch_bounds__(256) window_reduce_vec_kernel(const float *__restrict__ t, int ldt,
                                                                 const float *__restrict__ wk /* [ws*ws][D] */,
                                                                 float *__restrict__ out, int64_t out_bstride, int H,
@@ -73,14 +74,24 @@ __global__ void __launch_bounds__(256) window_reduce_vec_kernel(const float *__r
     const int lane = tid % L, grp = tid / L;
     const int y0 = gi * ws - 1, x0 = gj * ws - 1;
     float4 acc = make_float4(0, 0, 0, 0);
+    // H16: the map is fp16 (ldt in halves); the taps and the sum stay fp32
     const float *tb = t + (int64_t)b * H * W * ldt + lane * 4;
+    const __half *tbh = reinterpret_cast<const __half *>(t) + (int64_t)b * H * W * ldt + lane * 4;
     const float *wb = wk + lane * 4;
 #pragma unroll 4
     for (int pidx = grp; pidx < ws * ws; pidx += G) {
         const int ky = pidx / ws, kx = pidx - ky * ws;
         const int y = y0 + ky, x = x0 + kx;
         if (y >= 0 && y < H && x >= 0 && x < W) {
-            const float4 v = ldg_stream(tb + ((int64_t)y * W + x) * ldt);
+            float4 v;
+            if (H16) {
+                const uint2 u = __ldg(reinterpret_cast<const uint2 *>(tbh + ((int64_t)y * W + x) * ldt));
+                const float2 lo = __half22float2(*reinterpret_cast<const __half2 *>(&u.x));
+                const float2 hi = __half22float2(*reinterpret_cast<const __half2 *>(&u.y));
+                v = make_float4(lo.x, lo.y, hi.x, hi.y);
+            } else {
+                v = ldg_stream(tb + ((int64_t)y * W + x) * ldt);
+            }
             const float4 w4 = __ldg(reinterpret_cast<const float4 *>(wb + (int64_t)pidx * D));
             acc.x = fmaf(v.x, w4.x, acc.x); acc.y = fmaf(v.y, w4.y, acc.y);
             acc.z = fmaf(v.z, w4.z, acc.z); acc.w = fmaf(v.w, w4.w, acc.w);
@@ -491,9 +502,23 @@ extern "C" int turtle_sab_window_reduce(const float *t, int ldt, const float *w,
     const int L = D >> 2;
     if (!(D & 3) && L >= 1 && L <= 128 && !(L & (L - 1)) && !(ldt & 3) && !(out_bstride & 3) &&
         !(((uintptr_t)t | (uintptr_t)w | (uintptr_t)out) & 15))
-        window_reduce_vec_kernel<<<grid, 256, 0, as_stream(stream)>>>(t, ldt, w, out, out_bstride, H, W, D, ws);
+        window_reduce_vec_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(t, ldt, w, out, out_bstride, H, W, D, ws);
     else
         window_reduce_kernel<<<grid, 256, 0, as_stream(stream)>>>(t, ldt, w, out, out_bstride, H, W, D, ws);
+    TURTLE_CHECK_LAUNCH();
+    return TURTLE_OK;
+}
+
+extern "C" int turtle_sab_window_reduce_h16(const void *t, int ldt, const float *w, float *out, int64_t out_bstride,
+                                            int B, int H, int W, int D, int ws, void *stream) {
+    if (!t || !w || !out || D < 1 || D > 512 || ws < 1 || H % ws || W % ws) return TURTLE_EINVAL;
+    const int L = D >> 2;
+    if ((D & 3) || L > 128 || (L & (L - 1)) || (ldt & 3) || (out_bstride & 3) || ((uintptr_t)t & 7) ||
+        (((uintptr_t)w | (uintptr_t)out) & 15))
+        return TURTLE_ENOTSUP;
+    dim3 grid((H / ws) * (W / ws), B);
+    window_reduce_vec_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float *>(t), ldt, w, out,
+                                                                       out_bstride, H, W, D, ws);
     TURTLE_CHECK_LAUNCH();
     return TURTLE_OK;
 }

@@ -464,13 +464,27 @@ class FrameEngine:
         if t0:
             src = self.ws.get("xpe", P, c)
             self._call("turtle_add_posenc", _ptr(xn), _ptr(src), B, H, W, c, self.stream)
-        qk = self.ws.get("wide", P, 2 * c)
-        self.conv1x1(_ptr(src), c, c, sa + "qk.weight", _ptr(qk), 2 * c, P, 2 * c)
-        qkd = self.ws.get("dw", P, 2 * c)
+        # selection front end in fp16 (tensor-core mode): qk map, its depthwise, the k2 / q2 maps; sums stay fp32
+        s16 = (not t0) and self.sab_front_half and self.half_path(c, 2 * c)
+        sdt = torch.float16 if s16 else torch.float32
+        qk = self.ws.get("wide16" if s16 else "wide", P, 2 * c, dtype=sdt)
+        self.conv1x1(_ptr(src), c, c, sa + "qk.weight", _ptr(qk), 2 * c, P, 2 * c, o16=s16)
+        qkd = self.ws.get("dw16" if s16 else "dw", P, 2 * c, dtype=sdt)
         vt = self.ws.get("sab_v", P, c)
         self.conv1x1(_ptr(xn), c, c, sa + "v.weight", _ptr(vt), c, P, c)
         qn = self.ws.get("sab_qn", B, N, Dk)
-        if not t0:
+        if not t0 and s16:
+            self._meta = (2 * P * 4 * c, 2 * 9 * P * 2 * c)
+            self._call("turtle_dwconv3x3", _ptr(qk), 2 * c, _ptr(self._w(sa + "qk_dwconv.weight", "dw16")), None,
+                       _ptr(qkd), 2 * c, B, H, W, 2 * c, 0, 0, 1, 2, self.stream)
+            red = self.ws.get("wide16", P, 2 * c, dtype=torch.float16)            # qk no longer needed
+            self.conv1x1(_ptr(qkd, c), 2 * c, c, sa + "k2.weight", _ptr(red), 2 * c, P, 2 * c, a16=True, o16=True)
+            self._call("turtle_sab_window_reduce_h16", _ptr(red), 2 * c, _ptr(self._w(sa + "k2_dwconv.weight", "dw")),
+                       _ptr(ring.kbuf[:, slot]), ring.kbuf.stride(0), B, H, W, 2 * c, ws_, self.stream)
+            self.conv1x1(_ptr(qkd), 2 * c, c, sa + "q2.weight", _ptr(red), 2 * c, P, 2 * c, a16=True, o16=True)
+            self._call("turtle_sab_window_reduce_h16", _ptr(red), 2 * c, _ptr(self._w(sa + "q2_dwconv.weight", "dw")),
+                       _ptr(qn), N * Dk, B, H, W, 2 * c, ws_, self.stream)
+        elif not t0:
             self.dwconv(_ptr(qk), 2 * c, sa + "qk_dwconv.weight", None, _ptr(qkd), 2 * c, B, H, W, 2 * c)
             red = self.ws.get("wide", P, 2 * c)            # qk no longer needed
             # k: 1x1 c->2c on the k half, then window reduce + normalise straight into the ring slot
@@ -649,6 +663,7 @@ class FrameEngine:
         self.rnd = 1 if self.mode == capi.TF32 else 0
         self.use_half = bool(getattr(m, "half_intermediates", True))
         self.fuse_ln = bool(getattr(m, "fuse_layernorm", True))
+        self.sab_front_half = bool(getattr(m, "sab_front_half", True))
         self._fused = None
         self.trace = {} if getattr(m, "record_trace", False) else None
         inp = inp.float().contiguous()
