@@ -138,6 +138,8 @@ __global__ void __launch_bounds__(1024) chan_softmax_kernel(const float *__restr
                                                             const float *__restrict__ temperature, int nseg,
                                                             int nsplit, int heads, int ch, float *__restrict__ Pout,
                                                             float *__restrict__ inv_knorm) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float ps[8][4][64], pk[8][4][64], red[32];
     const int i = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
     const int C = heads * ch, ncol = nseg * ch;
@@ -207,6 +209,8 @@ __global__ void __launch_bounds__(1024) chan_softmax_kernel(const float *__restr
 // L2 latency: 22 us for a 4 MFLOP launch), then every thread produces a 4x4 register tile.
 __global__ void __launch_bounds__(256) chan_fold_tile_kernel(const float *__restrict__ Pm, const float *__restrict__ Wo,
                                                              int nseg, int heads, float *__restrict__ M, int rnd) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int CH = 64;
     __shared__ float ws[CH][CH + 4];      // [o][i]  (+4: conflict-free column reads)
     __shared__ float pt[CH][CH];          // [i][j]
@@ -298,7 +302,7 @@ extern "C" int turtle_chan_softmax(const float *gpart, const float *sqq, const f
     if (!gpart || !sqq || !sqk || !seg_prenorm || !temperature || !Pout || nseg < 1 || nseg > 8 || ch > 64 || nseg * ch > 512)
         return TURTLE_EINVAL;
     dim3 grid(ch, heads);
-    chan_softmax_kernel<<<grid, 1024, 0, as_stream(stream)>>>(gpart, sqq, sqk, seg_prenorm, temperature, nseg, nsplit,
+    launch_pdl(chan_softmax_kernel, dim3(grid), dim3(1024), 0, as_stream(stream), gpart, sqq, sqk, seg_prenorm, temperature, nseg, nsplit,
                                                             heads, ch, Pout, inv_knorm);
     TURTLE_CHECK_LAUNCH();
     return TURTLE_OK;
@@ -310,7 +314,7 @@ extern "C" int turtle_chan_fold(const float *Pm, const float *Wo, int nseg, int 
     int64_t total = (int64_t)heads * ch * nseg * heads * ch;
     if (ch == 64 && !(((uintptr_t)Pm | (uintptr_t)M | (uintptr_t)Wo) & 15)) {
         dim3 grid(heads, heads, nseg);          // (C/64 output tiles, heads, segments)
-        chan_fold_tile_kernel<<<grid, 256, 0, as_stream(stream)>>>(Pm, Wo, nseg, heads, M, round_tf32);
+        launch_pdl(chan_fold_tile_kernel, dim3(grid), dim3(256), 0, as_stream(stream), Pm, Wo, nseg, heads, M, round_tf32);
     } else {
         chan_fold_scalar_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, as_stream(stream)>>>(Pm, Wo, nseg, heads, ch, M, round_tf32);
     }

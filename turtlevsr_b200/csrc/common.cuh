@@ -13,6 +13,40 @@
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (griddepcontrol), opt-in with TURTLE_PDL=1: the frame is ~500 dependent launches on one
+// stream, so every kernel
+// (a) lets its successor start launching as soon as all of its own CTAs are resident (pdl_trigger, first statement) and
+// (b) blocks in pdl_wait() -- after its prologue (barrier init, TMEM allocation, constant taps), before the first access
+// to memory an earlier kernel may still be writing or reading.  The successor's launch latency and prologue then overlap
+// the predecessor's tail.  Completion is transitive: a kernel finishes only after its own wait returned.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+#ifdef __CUDACC__
+#include <cstdlib>
+#include <utility>
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                     Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    // measured on B200 (bench.py A/B, 20 steps x 2): 30.2-30.4 ms/frame with the attribute, 29.6-29.8 without -- early
+    // resident successors cost more than the hidden launch latency, so plain stream order is the default
+    static const bool off = getenv("TURTLE_PDL") == nullptr;
+    cfg.attrs = at;
+    cfg.numAttrs = off ? 0 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+#endif
+
 __device__ __forceinline__ float gelu_erf(float x) {
     // F.gelu default: 0.5*x*(1+erf(x/sqrt(2)))
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
@@ -71,5 +105,44 @@ __device__ __forceinline__ float gelu_fast(float x) {
     const float h = 0.5f * x;
     return fmaf(fabsf(h), fmaf(-q, e, 1.0f), h);
 }
+// two elements per instruction: Blackwell's packed fp32 pipe ops (FFMA2 / FMUL2 take |x| and immediates directly), so
+// the pair costs 12 issue slots + 4 MUFU instead of 22 + 4.  Same arithmetic as gelu_fast, element for element.
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
+    float2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(*reinterpret_cast<unsigned long long *>(&r))
+        : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)),
+          "l"(*reinterpret_cast<unsigned long long *>(&c)));
+    return r;
+}
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b) {
+    float2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;"
+        : "=l"(*reinterpret_cast<unsigned long long *>(&r))
+        : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+    return r;
+}
+__device__ __forceinline__ float2 f2_set(float v) { return make_float2(v, v); }
+__device__ __forceinline__ float2 gelu_fast2(float2 x) {
+    const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+    const float2 d = f2_fma(ax, f2_set(0.23164189f), f2_set(1.0f));
+    float2 t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(d.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(d.y));
+    const float2 k = f2_mul(ax, f2_set(0.84932180f));
+    const float2 nk2 = f2_mul(k, make_float2(-k.x, -k.y));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(nk2.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(nk2.y));
+    float2 q = f2_fma(f2_set(1.061405429f), t, f2_set(-1.453152027f));
+    q = f2_fma(q, t, f2_set(1.421413741f));
+    q = f2_fma(q, t, f2_set(-0.284496736f));
+    q = f2_fma(q, t, f2_set(0.254829592f));
+    q = f2_mul(q, t);
+    const float2 h = f2_mul(x, f2_set(0.5f));
+    const float2 ah = f2_mul(ax, f2_set(0.5f));
+    const float2 u = f2_fma(make_float2(-q.x, -q.y), e, f2_set(1.0f));
+    return f2_fma(ah, u, h);
+}
+
 template <bool FAST>
 __device__ __forceinline__ float gelu_sel(float x) { return FAST ? gelu_fast(x) : gelu_erf(x); }

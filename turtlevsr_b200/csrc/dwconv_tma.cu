@@ -43,6 +43,7 @@ template <int FUSE, bool FAST, bool IO16>
 __global__ void __launch_bounds__(256, 2) dwconv_tma_kernel(const __grid_constant__ DwParams p) {
     constexpr int NS = FUSE == 2 ? 2 : 1;
     constexpr int BOXB = IO16 ? BOX_BYTES / 2 : BOX_BYTES;
+    pdl_trigger();
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[2];
     const uint32_t smem0 = (smem_u32(smem_raw) + 127u) & ~127u;
@@ -53,6 +54,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_tma_kernel(const __grid_constan
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    pdl_wait();
 
     auto decode = [&](unsigned it, int &cb, int &tx, int &ty, int &nb) {     // 32-bit: 64-bit div is ~10x dearer
         cb = (int)(it % (unsigned)p.cblocks);
@@ -203,7 +205,7 @@ int launch(const DwParams &p, cudaStream_t s) {
     const int per_sm = NS == 2 ? 2 : 4;
     long long grid = (long long)nsm * per_sm;
     if (grid > p.nitems) grid = p.nitems;
-    dwconv_tma_kernel<FUSE, FAST, IO16><<<(unsigned)grid, 256, smem, s>>>(p);
+    launch_pdl(dwconv_tma_kernel<FUSE, FAST, IO16>, dim3((unsigned)grid), dim3(256), smem, s, p);
     return cudaGetLastError() == cudaSuccess ? TURTLE_OK : TURTLE_ELAUNCH;
 }
 

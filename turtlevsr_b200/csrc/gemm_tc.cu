@@ -282,8 +282,9 @@ __device__ __forceinline__ void epi_math(float (&v)[32], const float *__restrict
             v[4 * q] += bb.x; v[4 * q + 1] += bb.y; v[4 * q + 2] += bb.z; v[4 * q + 3] += bb.w;
         }
         if (GELU) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) v[4 * q + e] = gelu_fast(v[4 * q + e]);
+            const float2 g0 = gelu_fast2(make_float2(v[4 * q], v[4 * q + 1]));
+            const float2 g1 = gelu_fast2(make_float2(v[4 * q + 2], v[4 * q + 3]));
+            v[4 * q] = g0.x; v[4 * q + 1] = g0.y; v[4 * q + 2] = g1.x; v[4 * q + 3] = g1.y;
         }
         if (SCALE) {
             const float4 sc = __ldg(reinterpret_cast<const float4 *>(scale + o0 + 4 * q));
@@ -343,6 +344,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
     __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2], rfull_bar[EPI_WARPS][2];
     __shared__ uint32_t tmem_base_sh;
     __shared__ float2 lnstat[2][4][2][32];      // fused LN: (mean, M2) of each row half, [tile parity][quarter][chalf][lane]
+    pdl_trigger();
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t stage_bytes = A_STAGE_BYTES + (uint32_t)p.NG * TK * 4;
@@ -373,6 +375,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_sh;
     const int NG = p.NG;
+    pdl_wait();          // everything above touched only this CTA's shared memory / TMEM
 
     if (warp == 0 && lane == 0) {
         // ------------------------------ TMA producer ------------------------------
@@ -955,10 +958,10 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
     }
     long long grid = p.total_units < nsm ? p.total_units : nsm;
     cudaStream_t st = as_stream(stream);
-    if (a16 && o16) gemm_tc2_kernel<true, true><<<(unsigned)grid, 384, smem, st>>>(p);
-    else if (a16) gemm_tc2_kernel<true, false><<<(unsigned)grid, 384, smem, st>>>(p);
-    else if (o16) gemm_tc2_kernel<false, true><<<(unsigned)grid, 384, smem, st>>>(p);
-    else gemm_tc2_kernel<false, false><<<(unsigned)grid, 384, smem, st>>>(p);
+    if (a16 && o16) launch_pdl(gemm_tc2_kernel<true, true>, dim3((unsigned)grid), dim3(384), smem, st, p);
+    else if (a16) launch_pdl(gemm_tc2_kernel<true, false>, dim3((unsigned)grid), dim3(384), smem, st, p);
+    else if (o16) launch_pdl(gemm_tc2_kernel<false, true>, dim3((unsigned)grid), dim3(384), smem, st, p);
+    else launch_pdl(gemm_tc2_kernel<false, false>, dim3((unsigned)grid), dim3(384), smem, st, p);
     return cudaGetLastError() == cudaSuccess ? TURTLE_OK : TURTLE_ELAUNCH;
 }
 

@@ -54,6 +54,7 @@ template <bool H16>
 __global__ void __launch_bounds__(128) gram_tc_kernel(const __grid_constant__ GramParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
+    pdl_trigger();
     __shared__ uint32_t tmem_base_sh;
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -78,6 +79,7 @@ __global__ void __launch_bounds__(128) gram_tc_kernel(const __grid_constant__ Gr
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_sh;
+    pdl_wait();
 
     if (warp == 0 && lane == 0) {
         int stage = 0;
@@ -204,7 +206,7 @@ int turtle_chan_gram_tc(const float *q, int ldq, int q_hs, const float *k, int l
         configured = true;
     }
     dim3 grid(nsplit, heads);
-    if (h16) gram_tc_kernel<true><<<grid, 128, smem, as_stream(stream)>>>(p);
-    else gram_tc_kernel<false><<<grid, 128, smem, as_stream(stream)>>>(p);
+    if (h16) launch_pdl(gram_tc_kernel<true>, dim3(grid), dim3(128), smem, as_stream(stream), p);
+    else launch_pdl(gram_tc_kernel<false>, dim3(grid), dim3(128), smem, as_stream(stream), p);
     return cudaGetLastError() == cudaSuccess ? TURTLE_OK : TURTLE_ELAUNCH;
 }

@@ -10,6 +10,8 @@
 // ------------------------------------------------------------------------------------------
 __global__ void pack_frame_kernel(const float *__restrict__ src, int64_t bstride, float *__restrict__ dst, int B,
                                   int C, int Hs, int Ws, int Hp, int Wp, int up) {
+    pdl_trigger();
+    pdl_wait();
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t total = (int64_t)B * Hp * Wp;
     if (idx >= total) return;
@@ -49,7 +51,7 @@ extern "C" int turtle_pack_frame(const float *src, int64_t src_bstride, float *d
         Wp < Ws * upscale)
         return TURTLE_EINVAL;
     int64_t total = (int64_t)B * Hp * Wp;
-    pack_frame_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, as_stream(stream)>>>(src, src_bstride, dst, B, C, Hs,
+    launch_pdl(pack_frame_kernel, dim3((unsigned)cdiv64(total, 256)), dim3(256), 0, as_stream(stream), src, src_bstride, dst, B, C, Hs,
                                                                                   Ws, Hp, Wp, upscale);
     TURTLE_CHECK_LAUNCH();
     return TURTLE_OK;
@@ -106,6 +108,8 @@ template <int CIN>
 __global__ void __launch_bounds__(256) conv3x3_first_quad_kernel(const float *__restrict__ x, const float *__restrict__ w,
                                                                  const float *__restrict__ bias, float *__restrict__ y,
                                                                  int B, int H, int W, int Cout) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ float ws[];   // [9][CIN][Cout]
     for (int i = threadIdx.x; i < 9 * CIN * Cout; i += blockDim.x) {
         int co = i % Cout, ci = (i / Cout) % CIN, tap = i / (Cout * CIN);
@@ -168,9 +172,9 @@ extern "C" int turtle_conv3x3_first(const float *x, const float *w, const float 
         const int64_t quads = total >> 2;
         const unsigned grid = (unsigned)(cdiv64(quads, 256) < 148 * 8 ? cdiv64(quads, 256) : 148 * 8);
         if (Cin == 3)
-            conv3x3_first_quad_kernel<3><<<grid, 256, smem, as_stream(stream)>>>(x, w, bias, y, B, H, W, Cout);
+            launch_pdl(conv3x3_first_quad_kernel<3>, dim3(grid), dim3(256), smem, as_stream(stream), x, w, bias, y, B, H, W, Cout);
         else
-            conv3x3_first_quad_kernel<6><<<grid, 256, smem, as_stream(stream)>>>(x, w, bias, y, B, H, W, Cout);
+            launch_pdl(conv3x3_first_quad_kernel<6>, dim3(grid), dim3(256), smem, as_stream(stream), x, w, bias, y, B, H, W, Cout);
         TURTLE_CHECK_LAUNCH();
         return TURTLE_OK;
     }
@@ -238,6 +242,8 @@ __global__ void __launch_bounds__(256) conv3x3_last_warp_kernel(const float *__r
                                                                 const float *__restrict__ cur, int cur_ld, int cur_coff,
                                                                 float *__restrict__ out, int B, int H, int W, int Cout,
                                                                 int Hc, int Wc) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int CIN = 64;
     __shared__ __align__(16) float ws[3 * 9 * CIN];   // [co][tap][ci], rows of unused output channels are zero
     for (int i = threadIdx.x; i < 3 * 9 * CIN; i += blockDim.x) {
@@ -310,8 +316,7 @@ extern "C" int turtle_conv3x3_last(const float *x, const float *w, const float *
     if (Cin == 64 && Cout <= 3 && !((uintptr_t)x & 15)) {
         const int64_t nw = (int64_t)B * Hc * ((Wc + 7) >> 3);
         const int64_t blocks = cdiv64(nw, 8);
-        conv3x3_last_warp_kernel<<<(unsigned)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, as_stream(stream)>>>(
-            x, w, bias, cur, cur_ld, cur_coff, out, B, H, W, Cout, Hc, Wc);
+        launch_pdl(conv3x3_last_warp_kernel, dim3((unsigned)(blocks < 148 * 8 ? blocks : 148 * 8)), dim3(256), 0, as_stream(stream), x, w, bias, cur, cur_ld, cur_coff, out, B, H, W, Cout, Hc, Wc);
         TURTLE_CHECK_LAUNCH();
         return TURTLE_OK;
     }
@@ -403,6 +408,8 @@ template <int NV, int G, int U, bool O16>
 __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float *__restrict__ x, int ldx,
                                                             const float *__restrict__ w, const float *__restrict__ b,
                                                             float *__restrict__ y, int ldy, int64_t P, int rnd) {
+    pdl_trigger();
+    pdl_wait();
     constexpr int C = 4 * NV * G;
     constexpr int GPW = 32 / G;                       // pixel groups per warp
     const int lane = threadIdx.x & 31, gl = lane % G, gi = lane / G;
@@ -467,9 +474,9 @@ static void launch_ln_vec(const float *x, int ldx, const float *w, const float *
     const int64_t per_warp = (32 / G) * U;
     const int64_t warps = cdiv64(P, per_warp);
     if (rnd == 2)
-        layernorm_vec_kernel<NV, G, U, true><<<(unsigned)cdiv64(warps, 8), 256, 0, s>>>(x, ldx, w, b, y, ldy, P, rnd);
+        launch_pdl(layernorm_vec_kernel<NV, G, U, true>, dim3((unsigned)cdiv64(warps, 8)), dim3(256), 0, s, x, ldx, w, b, y, ldy, P, rnd);
     else
-        layernorm_vec_kernel<NV, G, U, false><<<(unsigned)cdiv64(warps, 8), 256, 0, s>>>(x, ldx, w, b, y, ldy, P, rnd);
+        launch_pdl(layernorm_vec_kernel<NV, G, U, false>, dim3((unsigned)cdiv64(warps, 8)), dim3(256), 0, s, x, ldx, w, b, y, ldy, P, rnd);
 }
 
 extern "C" int turtle_layernorm(const float *x, int ldx, const float *w, const float *b, float *y, int ldy,
@@ -638,6 +645,8 @@ extern "C" int turtle_dwconv3x3(const float *x, int ldx, const float *w, const f
 // ------------------------------------------------------------------------------------------
 __global__ void scale_cols_kernel(const float *__restrict__ x, int ldx, int x_hs, const float *__restrict__ s,
                                   float *__restrict__ y, int ldy, int y_hs, int64_t P, int heads, int ch) {
+    pdl_trigger();
+    pdl_wait();
     int per = heads * (ch >> 2);
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= P * per) return;
@@ -656,7 +665,7 @@ extern "C" int turtle_scale_cols(const float *x, int ldx, int x_hs, const float 
                                  int64_t P, int heads, int ch, void *stream) {
     if (!x || !y || (ch & 3) || (ldx & 3) || (ldy & 3) || (x_hs & 3) || (y_hs & 3)) return TURTLE_EINVAL;
     int64_t total = P * heads * (ch >> 2);
-    scale_cols_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, as_stream(stream)>>>(x, ldx, x_hs, s, y, ldy, y_hs, P,
+    launch_pdl(scale_cols_kernel, dim3((unsigned)cdiv64(total, 256)), dim3(256), 0, as_stream(stream), x, ldx, x_hs, s, y, ldy, y_hs, P,
                                                                                   heads, ch);
     TURTLE_CHECK_LAUNCH();
     return TURTLE_OK;

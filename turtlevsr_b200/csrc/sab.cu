@@ -63,6 +63,8 @@ __global__ void __launch_bounds__(256) window_reduce_vec_kernel(const float *__r
                                                                 const float *__restrict__ wk /* [ws*ws][D] */,
                                                                 float *__restrict__ out, int64_t out_bstride, int H,
                                                                 int W, int D, int ws) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float4 part[256];
     __shared__ float red[8];
     __shared__ float bc;
@@ -392,6 +394,8 @@ __global__ void __launch_bounds__(256) sab_aggregate_quad_kernel(const int32_t *
                                                                  const float *__restrict__ v, int64_t v_fstride,
                                                                  float *__restrict__ y, int Hg, int Wg, int ws, int c,
                                                                  int quads_x, int rnd) {
+    pdl_trigger();
+    pdl_wait();
     __shared__ float bw[QB * QB][4];      // weight of window-box key for each of the 4 queries
     __shared__ int ekey[QMAX];
     __shared__ float4 ew[QMAX];
@@ -502,7 +506,7 @@ extern "C" int turtle_sab_window_reduce(const float *t, int ldt, const float *w,
     const int L = D >> 2;
     if (!(D & 3) && L >= 1 && L <= 128 && !(L & (L - 1)) && !(ldt & 3) && !(out_bstride & 3) &&
         !(((uintptr_t)t | (uintptr_t)w | (uintptr_t)out) & 15))
-        window_reduce_vec_kernel<false><<<grid, 256, 0, as_stream(stream)>>>(t, ldt, w, out, out_bstride, H, W, D, ws);
+        launch_pdl(window_reduce_vec_kernel<false>, dim3(grid), dim3(256), 0, as_stream(stream), t, ldt, w, out, out_bstride, H, W, D, ws);
     else
         window_reduce_kernel<<<grid, 256, 0, as_stream(stream)>>>(t, ldt, w, out, out_bstride, H, W, D, ws);
     TURTLE_CHECK_LAUNCH();
@@ -517,7 +521,7 @@ extern "C" int turtle_sab_window_reduce_h16(const void *t, int ldt, const float 
         (((uintptr_t)w | (uintptr_t)out) & 15))
         return TURTLE_ENOTSUP;
     dim3 grid((H / ws) * (W / ws), B);
-    window_reduce_vec_kernel<true><<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float *>(t), ldt, w, out,
+    launch_pdl(window_reduce_vec_kernel<true>, dim3(grid), dim3(256), 0, as_stream(stream), reinterpret_cast<const float *>(t), ldt, w, out,
                                                                        out_bstride, H, W, D, ws);
     TURTLE_CHECK_LAUNCH();
     return TURTLE_OK;
@@ -551,7 +555,7 @@ extern "C" int turtle_sab_aggregate(const int32_t *idx, const float *wgt, const 
     if (!passthrough && !(((uintptr_t)v | (uintptr_t)y) & 15) && !(v_fstride & 3)) {
         const int quads_x = (Wg + 1) / 2, quads_y = (Hg + 1) / 2;
         dim3 grid(quads_x * quads_y, F);
-        sab_aggregate_quad_kernel<<<grid, 256, 0, as_stream(stream)>>>(idx, wgt, v, v_fstride, y, Hg, Wg, ws, c, quads_x,
+        launch_pdl(sab_aggregate_quad_kernel, dim3(grid), dim3(256), 0, as_stream(stream), idx, wgt, v, v_fstride, y, Hg, Wg, ws, c, quads_x,
                                                                       round_tf32);
         TURTLE_CHECK_LAUNCH();
         return TURTLE_OK;

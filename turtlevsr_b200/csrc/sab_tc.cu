@@ -24,6 +24,8 @@ constexpr int KSPLIT = 2;
 constexpr int NLOC = 41;
 
 __global__ void split_tf32_kernel(const float *__restrict__ x, float *__restrict__ y, long long rows, int D, int is_key) {
+    pdl_trigger();
+    pdl_wait();
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * D) return;
     long long r = idx / D;
@@ -45,6 +47,8 @@ struct alignas(64) CorrParams {
 };
 
 __global__ void __launch_bounds__(192, 1) sab_corr_top5_kernel(const __grid_constant__ CorrParams p) {
+    pdl_trigger();
+    pdl_wait();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], tfull_bar[2], tempty_bar[2];
     __shared__ uint32_t tmem_base_sh;
@@ -185,6 +189,8 @@ __global__ void __launch_bounds__(256) sab_finalize_kernel(const float *__restri
                                                            const float *__restrict__ tau_ptr, int halve, const float *__restrict__ topv,
                                                            const int *__restrict__ topi, int32_t *__restrict__ idx,
                                                            float *__restrict__ wgt) {
+    pdl_trigger();
+    pdl_wait();
     const int N = Hg * Wg;
     const int lane = threadIdx.x & 31;
     const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -289,8 +295,8 @@ extern "C" int turtle_sab_select_tc(const float *qn, const float *kn, int64_t k_
     int *topi = reinterpret_cast<int *>(topv + (long long)F * N * KSPLIT * 5);
     {
         long long nq = (long long)N * D, nk = (long long)F * N * D;
-        split_tf32_kernel<<<(unsigned)cdiv64(nq, 256), 256, 0, s>>>(qn, qs, N, D, 0);
-        split_tf32_kernel<<<(unsigned)cdiv64(nk, 256), 256, 0, s>>>(kn, ks, (long long)F * N, D, 1);
+        launch_pdl(split_tf32_kernel, dim3((unsigned)cdiv64(nq, 256)), dim3(256), 0, s, qn, qs, N, D, 0);
+        launch_pdl(split_tf32_kernel, dim3((unsigned)cdiv64(nk, 256)), dim3(256), 0, s, kn, ks, (long long)F * N, D, 1);
     }
     CorrParams p{};
     p.N = N; p.F = F; p.nkb = 3 * D / TK; p.qtiles = (N + TM - 1) / TM;
@@ -311,10 +317,10 @@ extern "C" int turtle_sab_select_tc(const float *qn, const float *kn, int64_t k_
             return TURTLE_ELAUNCH;
         configured = true;
     }
-    sab_corr_top5_kernel<<<(unsigned)(F * p.qtiles * KSPLIT), 192, smem, s>>>(p);
+    launch_pdl(sab_corr_top5_kernel, dim3((unsigned)(F * p.qtiles * KSPLIT)), dim3(192), smem, s, p);
     if (cudaGetLastError() != cudaSuccess) return TURTLE_ELAUNCH;
     long long warps = (long long)F * N;
-    sab_finalize_kernel<<<(unsigned)cdiv64(warps, 8), 256, 0, s>>>(qn, kn, k_fstride, F, Hg, Wg, D, temperature, halve, topv, topi,
+    launch_pdl(sab_finalize_kernel, dim3((unsigned)cdiv64(warps, 8)), dim3(256), 0, s, qn, kn, k_fstride, F, Hg, Wg, D, temperature, halve, topv, topi,
                                                                    idx, wgt);
     return cudaGetLastError() == cudaSuccess ? TURTLE_OK : TURTLE_ELAUNCH;
 }
