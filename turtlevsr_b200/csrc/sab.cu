@@ -399,6 +399,7 @@ __global__ void __launch_bounds__(256) sab_aggregate_quad_kernel(const int32_t *
     __shared__ float bw[QB * QB][4];      // weight of window-box key for each of the 4 queries
     __shared__ int ekey[QMAX];
     __shared__ float4 ew[QMAX];
+    __shared__ __align__(16) float2 ew2[QMAX][4];      // the same weights duplicated into (w, w) pairs for the packed FMAs
     __shared__ int ecount, wcount[8];
     const int tid = threadIdx.x, f = blockIdx.y;
     const int qy0 = (blockIdx.x / quads_x) * 2, qx0 = (blockIdx.x % quads_x) * 2;
@@ -464,22 +465,38 @@ __global__ void __launch_bounds__(256) sab_aggregate_quad_kernel(const int32_t *
     }
     __syncthreads();
     const int m = ecount;
-    const float *vf = v + (int64_t)f * v_fstride;
+    const int dv4 = (int)(Dv >> 2);
+    for (int t = tid; t < m; t += 256) {
+        ekey[t] *= dv4;                            // row offset in float4 units (N * Dv / 4 < 2^31)
+        const float4 w = ew[t];
+        ew2[t][0] = make_float2(w.x, w.x); ew2[t][1] = make_float2(w.y, w.y);
+        ew2[t][2] = make_float2(w.z, w.z); ew2[t][3] = make_float2(w.w, w.w);
+    }
+    __syncthreads();
+    const float4 *vf4 = reinterpret_cast<const float4 *>(v + (int64_t)f * v_fstride);
     const int c4 = c >> 2;
-    for (int64_t e4 = tid; e4 < (Dv >> 2); e4 += 256) {
-        float4 a0 = make_float4(0, 0, 0, 0), a1 = a0, a2 = a0, a3 = a0;
+    for (int e4 = tid; e4 < dv4; e4 += 256) {
+        // 4 queries x (lo, hi) channel pairs: 8 packed FMAs per key instead of 16 scalar ones
+        float2 a[4][2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[q][0] = a[q][1] = make_float2(0.f, 0.f);
 #pragma unroll 4
         for (int t = 0; t < m; ++t) {
-            const float4 x = __ldg(reinterpret_cast<const float4 *>(vf + (int64_t)ekey[t] * Dv) + e4);
-            const float4 w = ew[t];
-            a0.x = fmaf(w.x, x.x, a0.x); a0.y = fmaf(w.x, x.y, a0.y); a0.z = fmaf(w.x, x.z, a0.z); a0.w = fmaf(w.x, x.w, a0.w);
-            a1.x = fmaf(w.y, x.x, a1.x); a1.y = fmaf(w.y, x.y, a1.y); a1.z = fmaf(w.y, x.z, a1.z); a1.w = fmaf(w.y, x.w, a1.w);
-            a2.x = fmaf(w.z, x.x, a2.x); a2.y = fmaf(w.z, x.y, a2.y); a2.z = fmaf(w.z, x.z, a2.z); a2.w = fmaf(w.z, x.w, a2.w);
-            a3.x = fmaf(w.w, x.x, a3.x); a3.y = fmaf(w.w, x.y, a3.y); a3.z = fmaf(w.w, x.z, a3.z); a3.w = fmaf(w.w, x.w, a3.w);
+            const float4 x = __ldg(vf4 + (ekey[t] + e4));
+            const float2 xl = make_float2(x.x, x.y), xh = make_float2(x.z, x.w);
+            const float4 w01 = *reinterpret_cast<const float4 *>(&ew2[t][0]);
+            const float4 w23 = *reinterpret_cast<const float4 *>(&ew2[t][2]);
+            a[0][0] = f2_fma(make_float2(w01.x, w01.y), xl, a[0][0]); a[0][1] = f2_fma(make_float2(w01.x, w01.y), xh, a[0][1]);
+            a[1][0] = f2_fma(make_float2(w01.z, w01.w), xl, a[1][0]); a[1][1] = f2_fma(make_float2(w01.z, w01.w), xh, a[1][1]);
+            a[2][0] = f2_fma(make_float2(w23.x, w23.y), xl, a[2][0]); a[2][1] = f2_fma(make_float2(w23.x, w23.y), xh, a[2][1]);
+            a[3][0] = f2_fma(make_float2(w23.z, w23.w), xl, a[3][0]); a[3][1] = f2_fma(make_float2(w23.z, w23.w), xh, a[3][1]);
         }
         const int pp = (int)(e4 / c4), d = (int)(e4 % c4) * 4;
         const int p1 = pp / ws, p2 = pp % ws;
-        const float4 acc[4] = {a0, a1, a2, a3};
+        const float4 acc[4] = {make_float4(a[0][0].x, a[0][0].y, a[0][1].x, a[0][1].y),
+                               make_float4(a[1][0].x, a[1][0].y, a[1][1].x, a[1][1].y),
+                               make_float4(a[2][0].x, a[2][0].y, a[2][1].x, a[2][1].y),
+                               make_float4(a[3][0].x, a[3][0].y, a[3][1].x, a[3][1].y)};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const int qy = qy0 + (q >> 1), qx = qx0 + (q & 1);
