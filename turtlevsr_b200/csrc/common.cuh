@@ -27,6 +27,25 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 #ifdef __CUDACC__
 #include <cstdlib>
 #include <utility>
+// launch with a thread-block cluster of `cluster` CTAs along x (CTA pairs of the tcgen05 cta_group::2 kernels)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_cluster(void (*kern)(KArgs...), unsigned cluster, dim3 grid, dim3 block, size_t smem,
+                                         cudaStream_t s, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cluster;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                                      Args &&...args) {

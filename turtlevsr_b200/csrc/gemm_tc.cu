@@ -338,7 +338,12 @@ constexpr int EPI_WARPS = 8;
 constexpr int EPI_BUF = 32 * 128;                       // one 32-row x 32-column staging box (4 KB)
 constexpr int EPI_BYTES = EPI_WARPS * 2 * EPI_BUF;      // 64 KB
 
-template <bool A16, bool O16>
+// PAIR: the kernel runs as clusters of two CTAs sharing one M256 x NG MMA (tcgen05 cta_group::2).  Each CTA stages its
+// own 128 rows of A and HALF of the weight rows of the n-group (the tensor core reads the other half from the peer's
+// shared memory): the operand feed per MAC drops by a third and a stage shrinks from 16+NG/8 KB to 16+NG/16 KB.  Loads
+// complete on the leader's full barrier, the leader's MMA thread multicasts its commits to both CTAs' empty / tfull
+// barriers, and both CTAs' epilogue warps hand the accumulator back on the leader's tempty barrier.
+template <bool A16, bool O16, bool PAIR>
 __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant__ Tc2Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2], rfull_bar[EPI_WARPS][2];
@@ -347,8 +352,13 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
     pdl_trigger();
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t stage_bytes = A_STAGE_BYTES + (uint32_t)p.NG * TK * 4;
+    const uint32_t b_bytes = (uint32_t)(PAIR ? p.NG / 2 : p.NG) * TK * 4;   // weight rows staged by THIS CTA
+    const uint32_t stage_bytes = A_STAGE_BYTES + b_bytes;
     const uint32_t epi0 = smem0 + (uint32_t)p.stages * stage_bytes;     // per-warp staging boxes (1024 B aligned)
+    const uint32_t rank = PAIR ? cluster_rank() : 0u;
+    const long long u0 = PAIR ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+    const long long ustride = PAIR ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
+    constexpr int TPU = PAIR ? 2 : 1;                                   // pixel tiles per work unit
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
@@ -357,7 +367,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&tfull_bar[s]), 1);
-            mbar_init(smem_u32(&tempty_bar[s]), EPI_WARPS);
+            mbar_init(smem_u32(&tempty_bar[s]), EPI_WARPS * TPU);
         }
         for (int w = 0; w < EPI_WARPS; ++w) {
             mbar_init(smem_u32(&rfull_bar[w][0]), 1);
@@ -366,12 +376,19 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_sh))
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_sh))
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_sh))
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (PAIR) cluster_sync_all();       // the peer's barriers exist before anything signals them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_sh;
     const int NG = p.NG;
@@ -381,9 +398,9 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
         // ------------------------------ TMA producer ------------------------------
         int stage = 0;
         uint32_t phase = 0;
-        for (long long u = blockIdx.x; u < p.total_units; u += gridDim.x) {
+        for (long long u = u0; u < p.total_units; u += ustride) {
             const int ng = (int)(u % p.ngroups);
-            const long long tile = u / p.ngroups;
+            const long long tile = (u / p.ngroups) * TPU + rank;
             int tb = 0, ty0 = 0, tx0 = 0;
             if (p.im2col) {
                 tx0 = (int)(tile % p.tiles_x) * p.BW;
@@ -395,28 +412,41 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
                 mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
                 const uint32_t fb = smem_u32(&full_bar[stage]);
                 const uint32_t sa = smem0 + stage * stage_bytes;
-                mbar_expect_tx(fb, A_STAGE_BYTES + (uint32_t)NG * TK * 4);
                 constexpr int KE = A16 ? 64 : 32;       // K elements per 128-byte k-block
                 const int seg = kb / p.kb_per_seg, r = kb - seg * p.kb_per_seg;
-                if (p.im2col) {
-                    tma_load_4d(sa, &p.mapA[0], r * KE, tx0 + seg % 3 - 1, ty0 + seg / 3 - 1, tb, fb);
+                if (PAIR) {
+                    // both CTAs' bytes complete on the leader's barrier; only the leader posts the expectation
+                    if (rank == 0) mbar_expect_tx(fb, 2 * stage_bytes);
+                    if (p.im2col) {
+                        tma_load_4d_pair(sa, &p.mapA[0], r * KE, tx0 + seg % 3 - 1, ty0 + seg / 3 - 1, tb, fb);
+                    } else {
+                        const int sub = r / p.kb_per_sub;
+                        tma_load_3d_pair(sa, &p.mapA[seg], (r - sub * p.kb_per_sub) * KE, sub, m0, fb);
+                    }
+                    tma_load_2d_pair(sa + A_STAGE_BYTES, &p.mapW, kb * KE, ng * NG + (int)rank * (NG / 2), fb);
                 } else {
-                    const int sub = r / p.kb_per_sub;
-                    tma_load_3d(sa, &p.mapA[seg], (r - sub * p.kb_per_sub) * KE, sub, m0, fb);
+                    mbar_expect_tx(fb, stage_bytes);
+                    if (p.im2col) {
+                        tma_load_4d(sa, &p.mapA[0], r * KE, tx0 + seg % 3 - 1, ty0 + seg / 3 - 1, tb, fb);
+                    } else {
+                        const int sub = r / p.kb_per_sub;
+                        tma_load_3d(sa, &p.mapA[seg], (r - sub * p.kb_per_sub) * KE, sub, m0, fb);
+                    }
+                    tma_load_2d(sa + A_STAGE_BYTES, &p.mapW, kb * KE, ng * NG, fb);
                 }
-                tma_load_2d(sa + A_STAGE_BYTES, &p.mapW, kb * KE, ng * NG, fb);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ------------------------------ MMA issuer ------------------------------
-        // D=f32; A,B = tf32 (format 2, K=8 per MMA) or fp16 (format 0, K=16 per MMA); both K-major
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+        // ------------------------------ MMA issuer (PAIR: the leader CTA only) ------------------------------
+        // D=f32; A,B = tf32 (format 2, K=8 per MMA) or fp16 (format 0, K=16 per MMA); both K-major; M = 128 or 256
         const uint32_t fmt = A16 ? 0u : 2u;
-        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NG >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NG >> 3) << 17) |
+                               ((uint32_t)((TM * TPU) >> 4) << 24);
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
-        for (long long u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
+        for (long long u = u0; u < p.total_units; u += ustride, ++it) {
             const int acc = it & 1;
             mbar_wait(smem_u32(&tempty_bar[acc]), ((it >> 1) & 1) ^ 1);     // epilogue drained this accumulator
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -428,13 +458,16 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
                 const uint32_t sb = sa + A_STAGE_BYTES;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {       // 4 x 32 B of K per 128 B swizzle row
-                    if (A16) umma_f16(tacc, make_desc(sa + k * 32), make_desc(sb + k * 32), idesc, (kb | k) ? 1u : 0u);
+                    if (PAIR) umma_pair(A16, tacc, make_desc(sa + k * 32), make_desc(sb + k * 32), idesc, (kb | k) ? 1u : 0u);
+                    else if (A16) umma_f16(tacc, make_desc(sa + k * 32), make_desc(sb + k * 32), idesc, (kb | k) ? 1u : 0u);
                     else umma_tf32(tacc, make_desc(sa + k * 32), make_desc(sb + k * 32), idesc, (kb | k) ? 1u : 0u);
                 }
-                umma_commit(smem_u32(&empty_bar[stage]));
+                if (PAIR) umma_commit_pair(smem_u32(&empty_bar[stage]));
+                else umma_commit(smem_u32(&empty_bar[stage]));
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
-            umma_commit(smem_u32(&tfull_bar[acc]));
+            if (PAIR) umma_commit_pair(smem_u32(&tfull_bar[acc]));
+            else umma_commit(smem_u32(&tfull_bar[acc]));
         }
     } else if (warp >= 4) {
         // ------------------------------ epilogue: 8 warps ------------------------------
@@ -447,9 +480,9 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
         int it = 0;
         uint32_t gw = 0;                                     // this warp's staging-box use counter
         uint32_t rph = 0;                                    // fused-LN path: residual-barrier phase bit per box
-        for (long long u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
+        for (long long u = u0; u < p.total_units; u += ustride, ++it) {
             const int ng = (int)(u % p.ngroups);
-            const long long tile = u / p.ngroups;
+            const long long tile = (u / p.ngroups) * TPU + rank;
             const int n0 = ng * NG;
             const int acc = it & 1;
             mbar_wait(smem_u32(&tfull_bar[acc]), (it >> 1) & 1);
@@ -663,7 +696,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
                     tb = (int)(tile / ((long long)p.tiles_x * p.tiles_y));
                     py = ty0 + row / p.BW;
                     px = tx0 + row % p.BW;
-                    live = py < p.H && px < p.W;
+                    live = py < p.H && px < p.W && tb < p.B;
                     pix = ((long long)tb * p.H + py) * p.W + px;
                 } else {
                     pix = tile * TM + row;
@@ -716,15 +749,20 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
             // every tcgen05.ld of this warp has completed (wait::ld): hand the accumulator back
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+            if (lane == 0) {
+                if (PAIR) mbar_arrive_leader(smem_u32(&tempty_bar[acc]));
+                else mbar_arrive(smem_u32(&tempty_bar[acc]));
+            }
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     __syncwarp();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (PAIR) cluster_sync_all();       // no CTA frees TMEM or exits while the pair's MMAs / remote arrives are in flight
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
 }
 
@@ -841,7 +879,8 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
     p.out = a->out; p.ldo = a->ldo; p.store = a->store; p.round_out = a->round_out;
     p.B = a->B; p.H = a->H; p.W = a->W;
     p.im2col = a->im2col;
-    int NG = 256;
+    static const int ng_max = getenv("TURTLE_GEMM_NGMAX") ? atoi(getenv("TURTLE_GEMM_NGMAX")) : 256;   // tuning knob
+    int NG = (Cout % ng_max == 0 && !a->ln_out) ? ng_max : 256;
     while (NG >= 16 && Cout % NG) NG -= 16;
     if (NG < 16) return TURTLE_ENOTSUP;
     p.NG = NG;
@@ -901,14 +940,22 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
         tiles = (a->P + TM - 1) / TM;
     }
     p.nkb = a->im2col ? K / TK : p.nseg * p.kb_per_seg;
+    // CTA pairs (one M256 MMA per two SMs) pay off once the K loop is long enough for the operand feed to matter;
+    // the short-K full-resolution convs are bound by their output stream and stay on single CTAs
+    static const bool no_pair = getenv("TURTLE_GEMM_NO_PAIR") != nullptr;
+    static const int pair_min_kb = getenv("TURTLE_GEMM_PAIR_MINKB") ? atoi(getenv("TURTLE_GEMM_PAIR_MINKB")) : 4;
+    // measured per shape (profile_shapes A/B): pairs win where the weight slab dominates the feed (NG = 256: 256->1280,
+    // 256->768, 512->2560, 1280->512, the 3x3 up-convs: -5..-10 %), lose a few % on narrow n-groups and on the two-pass LN
+    // epilogue, whose longer accumulator hold now stalls two SMs
+    const bool pair = !no_pair && p.nkb >= pair_min_kb && NG == 256 && !a->ln_out && tiles >= 8;
     {
         uint64_t dims[2] = {(uint64_t)K, (uint64_t)Cout};
         uint64_t str[1] = {(uint64_t)K * es};
-        uint32_t box[2] = {(uint32_t)KE, (uint32_t)NG};
+        uint32_t box[2] = {(uint32_t)KE, (uint32_t)(pair ? NG / 2 : NG)};
         if (!turtle_get_tmap2(&p.mapW, a->Wt, 2, dims, str, box, 1, a16 ? 1 : 0)) return TURTLE_ENOTSUP;
     }
-    p.total_units = tiles * p.ngroups;
-    const size_t stage_bytes = A_STAGE_BYTES + (size_t)NG * TK * 4;
+    p.total_units = (pair ? (tiles + 1) / 2 : tiles) * p.ngroups;
+    const size_t stage_bytes = A_STAGE_BYTES + (size_t)(pair ? NG / 2 : NG) * TK * 4;
     const size_t max_smem = 232448 - 6144;   // 227 KB opt-in limit minus the kernel's static smem (barriers, LN statistics)
     int stages = (int)((max_smem - 1024 - EPI_BYTES) / stage_bytes);
     if (stages > 8) stages = 8;
@@ -946,22 +993,36 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
     static bool configured = false;
     static int nsm = 148;
     if (!configured) {
-        if (cudaFuncSetAttribute(gemm_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess ||
-            cudaFuncSetAttribute(gemm_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess ||
-            cudaFuncSetAttribute(gemm_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess ||
-            cudaFuncSetAttribute(gemm_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) != cudaSuccess)
-            return TURTLE_ELAUNCH;
+        bool ok = true;
+        auto cfg = [&](auto kern) {
+            ok = ok && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) == cudaSuccess;
+        };
+        cfg(gemm_tc2_kernel<false, false, false>); cfg(gemm_tc2_kernel<true, false, false>);
+        cfg(gemm_tc2_kernel<true, true, false>);   cfg(gemm_tc2_kernel<false, true, false>);
+        cfg(gemm_tc2_kernel<false, false, true>);  cfg(gemm_tc2_kernel<true, false, true>);
+        cfg(gemm_tc2_kernel<true, true, true>);    cfg(gemm_tc2_kernel<false, true, true>);
+        if (!ok) return TURTLE_ELAUNCH;
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
         configured = true;
     }
-    long long grid = p.total_units < nsm ? p.total_units : nsm;
     cudaStream_t st = as_stream(stream);
-    if (a16 && o16) launch_pdl(gemm_tc2_kernel<true, true>, dim3((unsigned)grid), dim3(384), smem, st, p);
-    else if (a16) launch_pdl(gemm_tc2_kernel<true, false>, dim3((unsigned)grid), dim3(384), smem, st, p);
-    else if (o16) launch_pdl(gemm_tc2_kernel<false, true>, dim3((unsigned)grid), dim3(384), smem, st, p);
-    else launch_pdl(gemm_tc2_kernel<false, false>, dim3((unsigned)grid), dim3(384), smem, st, p);
+    if (pair) {
+        long long pairs = nsm / 2;
+        if (pairs > p.total_units) pairs = p.total_units;
+        const dim3 grid((unsigned)(2 * pairs)), block(384);
+        if (a16 && o16) launch_cluster(gemm_tc2_kernel<true, true, true>, 2, grid, block, smem, st, p);
+        else if (a16) launch_cluster(gemm_tc2_kernel<true, false, true>, 2, grid, block, smem, st, p);
+        else if (o16) launch_cluster(gemm_tc2_kernel<false, true, true>, 2, grid, block, smem, st, p);
+        else launch_cluster(gemm_tc2_kernel<false, false, true>, 2, grid, block, smem, st, p);
+    } else {
+        const long long grid = p.total_units < nsm ? p.total_units : nsm;
+        if (a16 && o16) launch_pdl(gemm_tc2_kernel<true, true, false>, dim3((unsigned)grid), dim3(384), smem, st, p);
+        else if (a16) launch_pdl(gemm_tc2_kernel<true, false, false>, dim3((unsigned)grid), dim3(384), smem, st, p);
+        else if (o16) launch_pdl(gemm_tc2_kernel<false, true, false>, dim3((unsigned)grid), dim3(384), smem, st, p);
+        else launch_pdl(gemm_tc2_kernel<false, false, false>, dim3((unsigned)grid), dim3(384), smem, st, p);
+    }
     return cudaGetLastError() == cudaSuccess ? TURTLE_OK : TURTLE_ELAUNCH;
 }
 

@@ -129,6 +129,71 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ---- CTA-pair (cta_group::2) variants: loads complete on the LEADER's mbarrier, MMAs span both CTAs' TMEM ----
+constexpr uint32_t PAIR_LEADER_MASK = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address (pair)
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+            "r"(dst),
+        "l"(map), "r"(bar & PAIR_LEADER_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+            "r"(dst),
+        "l"(map), "r"(bar & PAIR_LEADER_MASK), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap *map, int c0, int c1, int c2, int c3,
+                                                 uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
+            "r"(dst),
+        "l"(map), "r"(bar & PAIR_LEADER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void umma_pair(bool f16, uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    if (f16)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {        // arrives on the barrier of BOTH CTAs
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"((uint16_t)3)
+        : "memory");
+}
+// arrive on the leader CTA's copy of a barrier.  Relaxed: the TMEM hand-back it signals is ordered by
+// tcgen05.fence::before_thread_sync; a release at cluster scope compiles to MEMBAR.ALL.GPU + ERRBAR (measured: 30 % of
+// all stall samples of the first CTA-pair kernel).
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t local_bar) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(ra) : "r"(local_bar));
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
                  "r"(c0), "r"(c1)
