@@ -223,29 +223,50 @@ __global__ void __launch_bounds__(256) sab_finalize_kernel(const float *__restri
         t5[r] = m ? __shfl_sync(0xffffffffu, ci, src) : -1;
         t5v[r] = m ? __shfl_sync(0xffffffffu, cv, src) : 0.f;
     }
-    // local-window logits in fp32: lanes split D
+    // local-window logits in fp32: lanes split D (coalesced rows); four keys per round so that their loads and shuffle
+    // reductions overlap instead of forming one chain of 41 dependent L2 round trips
     const float *q = qn + (long long)qi * D;
     const float *kf = kn + (long long)f * k_fstride;
     float z[2] = {0.f, 0.f};
     int id[2] = {-1, -1};
-    for (int l = 0; l < NLOC; ++l) {
-        int dy, dx;
-        loc_offset(l, dy, dx);
-        const int ky = qy + dy, kx = qx + dx;
-        if (ky < 0 || ky >= Hg || kx < 0 || kx >= Wg) continue;       // warp-uniform
-        const int key = ky * Wg + kx;
-        const float *kr = kf + (long long)key * D;
-        float acc = 0.f;
-        for (int d = lane * 4; d < D; d += 128) {
-            float4 a = __ldg(reinterpret_cast<const float4 *>(q + d));
-            float4 b = __ldg(reinterpret_cast<const float4 *>(kr + d));
-            acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+    for (int l0 = 0; l0 < NLOC; l0 += 4) {
+        int key[4];
+        float acc[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            key[u] = -1;
+            acc[u] = 0.f;
+            if (l0 + u < NLOC) {
+                int dy, dx;
+                loc_offset(l0 + u, dy, dx);
+                const int ky = qy + dy, kx = qx + dx;
+                if (ky >= 0 && ky < Hg && kx >= 0 && kx < Wg) key[u] = ky * Wg + kx;       // warp-uniform
+            }
         }
-        acc = warp_sum(acc) * tau;
-        const bool dup = key == t5[0] || key == t5[1] || key == t5[2] || key == t5[3] || key == t5[4];
-        const int slot = 5 + l;
-        if (!dup && (slot & 31) == lane) {
-            if (slot < 32) { z[0] = acc; id[0] = key; } else { z[1] = acc; id[1] = key; }
+        for (int d = lane * 4; d < D; d += 128) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(q + d));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (key[u] >= 0) {
+                    const float4 b = __ldg(reinterpret_cast<const float4 *>(kf + (long long)key[u] * D + d));
+                    acc[u] = fmaf(a.x, b.x, acc[u]); acc[u] = fmaf(a.y, b.y, acc[u]);
+                    acc[u] = fmaf(a.z, b.z, acc[u]); acc[u] = fmaf(a.w, b.w, acc[u]);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (key[u] < 0) continue;
+            const bool dup = key[u] == t5[0] || key[u] == t5[1] || key[u] == t5[2] || key[u] == t5[3] || key[u] == t5[4];
+            const int slot = 5 + l0 + u;
+            if (!dup && (slot & 31) == lane) {
+                if (slot < 32) { z[0] = acc[u] * tau; id[0] = key[u]; } else { z[1] = acc[u] * tau; id[1] = key[u]; }
+            }
         }
     }
     if (lane < 5) {
