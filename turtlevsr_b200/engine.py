@@ -18,6 +18,7 @@ Schedule per block (each arrow is one kernel):
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -370,7 +371,7 @@ class FrameEngine:
         else:
             self.dwconv(_ptr(qkv), 3 * c, pre + "qkv_dwconv.weight", pre + "qkv_dwconv.bias", _ptr(qd), 3 * c, B, H, W,
                         3 * c)
-        nsplit = max(1, min((Pimg + 255) // 256, max(1, 296 // heads)))
+        nsplit = max(1, min((Pimg + 255) // 256, max(1, self.gram_ctas // heads)))
         temp = self._w(pre + "temperature")
         Wo = self._w(pre + "project_out.weight")
         gmode = 2 if h16 else self.mode
@@ -664,6 +665,7 @@ class FrameEngine:
         self.use_half = bool(getattr(m, "half_intermediates", True))
         self.fuse_ln = bool(getattr(m, "fuse_layernorm", True))
         self.sab_front_half = bool(getattr(m, "sab_front_half", True))
+        self.gram_ctas = int(os.environ.get("TURTLE_GRAM_CTAS", "296"))      # pixel splits x heads of the Gram kernel
         self._fused = None
         self.trace = {} if getattr(m, "record_trace", False) else None
         inp = inp.float().contiguous()
