@@ -51,6 +51,10 @@ extern "C" {
 
 int turtle_abi_version(void);          /* bumps when a signature changes */
 int turtle_sizeof_gemm_args(void);       /* sizeof(TurtleGemmArgs) as compiled: bindings check their mirror of the struct */
+
+/* fp32 -> fp16 copy of a dense buffer (n % 8 == 0): the residual stream as the fp16 A operand of the dense 3x3
+ * resampling convs (Downsample / Upsample, T1:136-154) in tensor-core mode. */
+int turtle_cast_f16(const float *x, void *y, int64_t n, void *stream);
 const char *turtle_build_info(void);   /* "sm_100a nvcc <ver> ..." */
 
 /* ---------------------------------------------------------------------------------------

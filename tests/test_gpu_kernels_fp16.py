@@ -182,3 +182,27 @@ def test_sab_window_reduce_fp16_map(ws, D):
     wk = w.reshape(D, -1).t().contiguous().cuda()
     call("turtle_sab_window_reduce_h16", t.data_ptr(), D, wk.data_ptr(), out.data_ptr(), N * D, B, H, W, D, ws, stream())
     assert (out.cpu() - want).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize("store", [capi.STORE_UNSHUFFLE2, capi.STORE_SHUFFLE2, capi.STORE_PLAIN])
+def test_conv3x3_im2col_fp16_operands(store):
+    """Dense 3x3 (Down/Upsample, T1:136-154) as a kind::f16 implicit GEMM on an fp16 copy of the map."""
+    B, Cin, H, W = 2, 64, 12, 20
+    Cout = 32 if store == capi.STORE_UNSHUFFLE2 else 128
+    x = rnd(B, H, W, Cin).cuda()
+    x16 = torch.full((B, H, W, Cin), float("nan"), device="cuda", dtype=torch.float16)
+    call("turtle_cast_f16", x.data_ptr(), x16.data_ptr(), x.numel(), stream())
+    assert torch.equal(x16, x.half())
+    w = (rnd(Cout, Cin, 3, 3, seed=1) / (9 * Cin) ** 0.5).half()
+    y = F.conv2d(x16.cpu().double().permute(0, 3, 1, 2), w.double(), padding=1)
+    want = F.pixel_unshuffle(y, 2) if store == capi.STORE_UNSHUFFLE2 else F.pixel_shuffle(y, 2) if store == capi.STORE_SHUFFLE2 else y
+    Bo, Co, Ho, Wo = want.shape
+    out = torch.full((Bo, Ho, Wo, Co), float("nan"), device="cuda")
+    wp = w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous().cuda()
+    a = GemmArgs()
+    a.mode, a.im2col, a.P, a.Cout, a.nseg, a.segw = capi.TF32, 1, B * H * W, Cout, 1, Cin
+    a.B, a.H, a.W = B, H, W
+    a.A[0], a.lda[0] = x16.data_ptr(), Cin
+    a.Wt, a.out, a.ldo, a.store, a.a_dtype = wp.data_ptr(), out.data_ptr(), Co, store, 1
+    call("turtle_gemm", C.byref(a), stream())
+    assert (out.cpu().double().permute(0, 3, 1, 2) - want).abs().max() < 1e-5 * max(1.0, float(want.abs().max()))

@@ -889,7 +889,7 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
     const bool a16 = a->a_dtype == 1, o16 = a->out_dtype == 1;
     const int es = a16 ? 2 : 4;                 // operand element size
     const int KE = 128 / es;                    // K elements per k-block
-    if (a16 && (a->im2col || (a->nseg > 1 && a->segw % KE))) return TURTLE_ENOTSUP;
+    if (a16 && ((a->im2col && a->segw % KE) || (!a->im2col && a->nseg > 1 && a->segw % KE))) return TURTLE_ENOTSUP;
     if (o16 && (a->res || a->store != TURTLE_STORE_PLAIN || NG % 32)) return TURTLE_ENOTSUP;
     long long tiles;
     if (a->im2col) {
@@ -901,12 +901,12 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
         p.tiles_x = a->W / BW;
         p.tiles_y = (a->H + p.BH - 1) / p.BH;
         p.nseg = 9;
-        p.kb_per_seg = a->segw / TK;
+        p.kb_per_seg = a->segw / KE;
         p.kb_per_sub = p.kb_per_seg;
         uint64_t dims[4] = {(uint64_t)a->segw, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->B};
-        uint64_t str[3] = {(uint64_t)a->segw * 4, (uint64_t)a->segw * 4 * a->W, (uint64_t)a->segw * 4 * a->W * a->H};
-        uint32_t box[4] = {TK, (uint32_t)BW, (uint32_t)p.BH, 1};
-        if (!get_map(&p.mapA[0], a->A[0], 4, dims, str, box)) return TURTLE_ENOTSUP;
+        uint64_t str[3] = {(uint64_t)a->segw * es, (uint64_t)a->segw * es * a->W, (uint64_t)a->segw * es * a->W * a->H};
+        uint32_t box[4] = {(uint32_t)KE, (uint32_t)BW, (uint32_t)p.BH, 1};
+        if (!turtle_get_tmap2(&p.mapA[0], a->A[0], 4, dims, str, box, 1, a16 ? 1 : 0)) return TURTLE_ENOTSUP;
         tiles = (long long)p.tiles_x * p.tiles_y * a->B;
     } else {
         // group the flat segment list into <= 8 runs of equally spaced column blocks (3-D tensor maps)
@@ -939,7 +939,7 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
         }
         tiles = (a->P + TM - 1) / TM;
     }
-    p.nkb = a->im2col ? K / TK : p.nseg * p.kb_per_seg;
+    p.nkb = a->im2col ? K / KE : p.nseg * p.kb_per_seg;
     // CTA pairs (one M256 MMA per two SMs) pay off once the K loop is long enough for the operand feed to matter;
     // the short-K full-resolution convs are bound by their output stream and stay on single CTAs
     static const bool no_pair = getenv("TURTLE_GEMM_NO_PAIR") != nullptr;

@@ -699,6 +699,31 @@ extern "C" int turtle_add_posenc(const float *x, float *y, int B, int H, int W, 
     return TURTLE_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// fp32 -> fp16 copy of a dense map (the residual stream as the fp16 A operand of the 3x3 resampling convs)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cast_f16_kernel(const float *__restrict__ x, __half *__restrict__ y, int64_t n8) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 a = ldg_stream(x + 8 * i), b = ldg_stream(x + 8 * i + 4);
+        const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(a.z, a.w);
+        const __half2 h2 = __floats2half2_rn(b.x, b.y), h3 = __floats2half2_rn(b.z, b.w);
+        *reinterpret_cast<uint4 *>(y + 8 * i) =
+            make_uint4(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1),
+                       *reinterpret_cast<const uint32_t *>(&h2), *reinterpret_cast<const uint32_t *>(&h3));
+    }
+}
+
+extern "C" int turtle_cast_f16(const float *x, void *y, int64_t n, void *stream) {
+    if (!x || !y || n < 0 || (n & 7) || (((uintptr_t)x | (uintptr_t)y) & 15)) return TURTLE_EINVAL;
+    if (n == 0) return TURTLE_OK;
+    const int64_t n8 = n >> 3;
+    const int64_t blocks = cdiv64(n8, 256);
+    cast_f16_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, as_stream(stream)>>>(
+        x, reinterpret_cast<__half *>(y), n8);
+    TURTLE_CHECK_LAUNCH();
+    return TURTLE_OK;
+}
+
 extern "C" int turtle_abi_version(void) { return 3; }
 extern "C" int turtle_sizeof_gemm_args(void) { return (int)sizeof(TurtleGemmArgs); }
 extern "C" const char *turtle_build_info(void) {
