@@ -350,6 +350,14 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
     __shared__ uint32_t tmem_base_sh;
     __shared__ float2 lnstat[2][4][2][32];      // fused LN: (mean, M2) of each row half, [tile parity][quarter][chalf][lane]
     pdl_trigger();
+    if (threadIdx.x == 32) {            // descriptor fetches overlap the barrier / TMEM set-up
+        tma_prefetch_map(&p.mapW);
+        for (int i = 0; i < (p.im2col ? 1 : p.nseg); ++i) tma_prefetch_map(&p.mapA[i]);
+        if (p.tma_epi) {
+            tma_prefetch_map(O16 ? &p.mapOut2 : &p.mapOut);
+            if (p.res) tma_prefetch_map(&p.mapRes);
+        }
+    }
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t b_bytes = (uint32_t)(PAIR ? p.NG / 2 : p.NG) * TK * 4;   // weight rows staged by THIS CTA
