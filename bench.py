@@ -7,8 +7,9 @@
 A *step* is one frame of the cached per-clip loop (VRM:110-129) at B=1: one forward of the
 drop-in arch on a synthetic 1280x720 frame with the history rings full (warm-up fills them).
   value        frames/s with the clip already resident in HBM, timed with CUDA events, max over ranks
-  e2e          the same loop through the public API from pinned host frames: H2D of the frame pair
-               and D2H of the restored frame inside the timed region, every step
+  e2e          the same clip through the public host-clip runner (clip.run_clip_streamed): every frame is copied
+               H2D from pinned memory and every restored frame D2H inside the timed region (on copy streams,
+               double-buffered), history starts empty for the timed clip
   roofline     dominant kernel (by device time, per-launch CUDA events in a separate profiled pass):
                algorithmic bytes or flops / its summed duration, against MEASURED_PEAKS.json
   cpu_baseline the oracle port of the reference's CPU path timed on this box's host cores on a
@@ -215,26 +216,25 @@ def main():
         launches = capi.launch_count - n0
         ms_dev = e0.elapsed_time(e1)
 
-        # ---- end to end: pinned host frames in, restored frame back to host, every step -----------
-        out_host = torch.empty(1, 3, Hh, Ww).pin_memory()
-        k = v = None
-        for j in range(Wm):
-            x = frame_pair(host_clip, j).pin_memory().to(dev, non_blocking=True)
-            o, k, v = net(x, k, v)
-            out_host.copy_(o, non_blocking=True)
+        # ---- end to end: pinned host frames in, restored frames back to host, every step --------------
+        # through the repo's public clip runner (clip.run_clip_streamed): every frame is uploaded once from pinned host
+        # memory on a copy stream and every restored frame is downloaded on another, all inside the timed region
+        from turtlevsr_b200.clip import run_clip_streamed
+        idx = [j % pool for j in range(Wm + K)]
+        warm_host = host_clip[idx[:Wm], 0].unsqueeze(0).contiguous().pin_memory()       # [1, Wm, 3, H, W]
+        timed_host = host_clip[idx[Wm:], 0].unsqueeze(0).contiguous().pin_memory()      # [1, K, 3, H, W]
+        out_host = torch.empty(1, K, 3, Hh, Ww).pin_memory()
+        _, k, v, last = run_clip_streamed(net, warm_host, torch.empty(1, Wm, 3, Hh, Ww).pin_memory(), dev)
         barrier()
-        pairs = [frame_pair(host_clip, j).pin_memory() for j in range(Wm, T)]
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2.record()
-        for x_h in pairs:
-            x = x_h.to(dev, non_blocking=True)
-            o, k, v = net(x, k, v)
-            out_host.copy_(o, non_blocking=True)
+        # continues the warm-up clip (history rings full); returns after the last download has completed
+        _, k, v, _ = run_clip_streamed(net, timed_host, out_host, dev, k=k, v=v, prev=last)
         e3.record()
         barrier()
         ms_e2e = e2.elapsed_time(e3)
-        h2d = pairs[0].numel() * 4
-        d2h = out_host.numel() * 4
+        h2d = timed_host[0, 0].numel() * 4
+        d2h = out_host[0, 0].numel() * 4
 
         # ---- per-kernel profile (separate pass, per-launch events) --------------------------------
         prof = None

@@ -216,3 +216,18 @@ def test_720p_benchmark_config_fast_mode_tracks_exact_mode():
     print(f"720p fast vs exact: per-frame max|d| {[f'{e:.2e}' for e in err.tolist()]}  dPSNR={dpsnr:.4f} dB")
     assert err.max() < 2e-3 and dpsnr < 0.02
     assert torch.isfinite(fast).all()
+
+
+def test_streamed_host_clip_matches_device_clip():
+    """clip.run_clip_streamed (pinned host frames, copy streams) == clip.run_clip on the same frames, bit for bit,
+    also when the clip is fed in two parts."""
+    from turtlevsr_b200.clip import run_clip_streamed
+    opt, sd, clip, _, _ = load_case("tiny_t1_live.npz")
+    g = torch.Generator().manual_seed(9)
+    clip = torch.rand(1, 7, 3, 32, 64, generator=g)
+    want, _, _ = run_clip(build(opt, sd, "tf32"), clip.cuda())
+    net = build(opt, sd, "tf32")
+    host = clip.pin_memory()
+    got, k, v, last = run_clip_streamed(net, host[:, :3])
+    got2, _, _, _ = run_clip_streamed(net, host[:, 3:], k=k, v=v, prev=last)
+    assert torch.equal(torch.cat([got, got2], 1), want.cpu())

@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(256, Cfg<FUSE>::CTAS) dwconv16_kernel(const __
     __shared__ __align__(16) __half wsm[NS * 9 * CK];
     __shared__ __align__(16) float bsm[NS * CK];
     pdl_trigger();
+    if (threadIdx.x == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&p.map) : "memory");
     extern __shared__ __align__(128) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES];
     __shared__ int4 coord[STAGES];

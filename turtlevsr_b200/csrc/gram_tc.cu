@@ -55,6 +55,10 @@ __global__ void __launch_bounds__(128) gram_tc_kernel(const __grid_constant__ Gr
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], accum_bar;
     pdl_trigger();
+    if (threadIdx.x == 0) {
+        tma_prefetch_map(&p.mapQ);
+        tma_prefetch_map(&p.mapK);
+    }
     __shared__ uint32_t tmem_base_sh;
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
