@@ -227,6 +227,22 @@ int turtle_sab_aggregate(const int32_t *idx, const float *wgt, const float *v, i
 /* T0 only: x + positionalencoding2d(c,h,w) (T0:412-439, 475-476), evaluated analytically. */
 int turtle_add_posenc(const float *x, float *y, int B, int H, int W, int C, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Training-step tail (cfg 5, VRM:78-108): one flat fp32 buffer holds all 59,079,548 parameters
+ * (and one each their gradients, exp_avg, exp_avg_sq), so the optimizer is two HBM-bound passes.
+ * ------------------------------------------------------------------------------------- */
+
+/* GradScaler.unscale_'s non-finite check (VRM:101): *found (device, zeroed by the caller) becomes 1.0f if any
+ * of the n gradients is inf/NaN.  g must be 16-byte aligned. */
+int turtle_grad_check_finite(const float *g, int64_t n, float *found, void *stream);
+
+/* torch.optim.AdamW single step on flat buffers (VRM:68-69, 104): g is multiplied by grad_scale first
+ * (1/loss_scale x 1/world_size), p *= 1-lr*weight_decay, m/v are the exp_avg / exp_avg_sq states, `step` >= 1 is
+ * the 1-based step count for the bias corrections.  found (nullable, device): the whole update is skipped when
+ * *found != 0 (GradScaler.step).  All four buffers 16-byte aligned. */
+int turtle_adamw_flat(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1, float beta2,
+                      float eps, float weight_decay, int step, float grad_scale, const float *found, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,7 +42,8 @@ def main(tag, path):
         d[r[mn]] = v
     ls = list(L.values())
     pf = [i for i, d in enumerate(ls) if d["name"].startswith("pack_frame")]
-    fr = ls[pf[0]:pf[1]]
+    # the LAST complete frame of the capture (earlier ones pack weights / run with a part-filled history)
+    fr = ls[pf[-2]:pf[-1]]
     agg = collections.OrderedDict()
     for d in fr:
         x = agg.setdefault(d["name"], [0, 0.0, 0.0])

@@ -19,6 +19,7 @@ ENOTSUP = -3
 
 _fp = C.c_void_p
 _i32, _i64 = C.c_int32, C.c_int64
+_f32 = C.c_float
 
 
 class GemmArgs(C.Structure):
@@ -57,6 +58,8 @@ _SIGS = {
     "turtle_sab_aggregate": ([_fp, _fp, _fp, _i64, _fp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _fp], C.c_int),
     "turtle_cast_f16": ([_fp, _fp, _i64, _fp], C.c_int),
     "turtle_add_posenc": ([_fp, _fp, _i32, _i32, _i32, _i32, _fp], C.c_int),
+    "turtle_grad_check_finite": ([_fp, _i64, _fp, _fp], C.c_int),
+    "turtle_adamw_flat": ([_fp, _fp, _fp, _fp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _fp, _fp], C.c_int),
 }
 
 EXPORTS = tuple(_SIGS)
