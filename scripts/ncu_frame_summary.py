@@ -1,6 +1,6 @@
 """One steady-state frame out of an ncu launch list (gpu__time_duration + dram bytes per launch).
 
-  python scripts/ncu_frame_summary.py <tag> gpurun_out/launches.csv
+  python scripts/ncu_frame_summary.py <tag> gpurun_out/launches.csv [frame-index, default 3]
 
 The list is cut between two consecutive pack_frame_kernel launches (= one forward of the arch).  Writes
 profiles/<tag>_launches_summary.txt (per-kernel launches, serialised cold-cache time, share, DRAM bytes) and
@@ -24,7 +24,7 @@ ENTRY = {
 }
 
 
-def main(tag, path):
+def main(tag, path, which=3):
     rows = list(csv.reader(open(path)))
     h = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
     hdr = rows[h]
@@ -42,8 +42,10 @@ def main(tag, path):
         d[r[mn]] = v
     ls = list(L.values())
     pf = [i for i, d in enumerate(ls) if d["name"].startswith("pack_frame")]
-    # the LAST complete frame of the capture (earlier ones pack weights / run with a part-filled history)
-    fr = ls[pf[-2]:pf[-1]]
+    # frame `which` of the capture (default 3 = bench.py's first timed frame after --warmup 3: weights packed,
+    # history rings full); earlier frames pack weights / run with a part-filled history
+    which = min(which, len(pf) - 2)
+    fr = ls[pf[which]:pf[which + 1]]
     agg = collections.OrderedDict()
     for d in fr:
         x = agg.setdefault(d["name"], [0, 0.0, 0.0])
@@ -75,4 +77,4 @@ def main(tag, path):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    main(sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 3)

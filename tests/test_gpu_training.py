@@ -1,0 +1,107 @@
+"""B200: the training step of cfg 5 -- flat AdamW / non-finite-check kernels through the C ABI against
+torch.optim.AdamW, and two full steps against parameters produced by the reference (tests/golden/train_*.npz)."""
+import numpy as np
+import pytest
+import torch
+
+from test_training_host import load_train_case
+from turtlevsr_b200 import capi
+from turtlevsr_b200.training import FlatAdamW, FlatParams, TrainStep
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+OPTIM = dict(type="Adam", lr=4e-4, weight_decay=0, betas=[0.9, 0.99])         # Turtle_Derain.yml:90-94
+
+
+@pytest.fixture(autouse=True)
+def true_fp32_library_kernels():
+    """The autograd graph runs on cuDNN/cuBLAS: for parity with the reference's CPU fp32 gradients switch their TF32
+    paths off ("oracle numerics")."""
+    old = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.parametrize("wd,n", [(0.0, 1 << 20), (0.05, 1000003)])
+def test_adamw_flat_kernel_matches_torch_adamw(wd, n):
+    g = torch.Generator(device=DEV).manual_seed(5)
+    p0 = torch.randn(n, device=DEV, generator=g)
+    ref_p = torch.nn.Parameter(p0.clone())
+    ref = torch.optim.AdamW([ref_p], lr=3e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=wd)
+    lin = torch.nn.Linear(1, 1, bias=False).to(DEV)
+    lin.weight = torch.nn.Parameter(p0.clone().view(n, 1))
+    flat = FlatParams(lin)
+    opt = FlatAdamW(flat, lr=3e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=wd)
+    for step in range(4):
+        grad = torch.randn(n, device=DEV, generator=g) * (10.0 ** (step - 2))
+        ref_p.grad = grad.clone()
+        ref.step()
+        flat.grad[:n].copy_(grad * 128.0)                       # as if the loss had been scaled by 128 on 1 rank
+        opt.step(grad_scale=1.0 / 128.0)
+        assert (flat.data[:n] - ref_p.detach()).abs().max().item() < 2e-6
+    assert opt.steps == 4
+    st = ref.state[ref_p]
+    assert torch.allclose(opt.exp_avg[:n], st["exp_avg"], rtol=1e-5, atol=1e-6)   # torch lerps, the kernel does b1*m+(1-b1)*g
+    assert torch.allclose(opt.exp_avg_sq[:n], st["exp_avg_sq"], rtol=1e-5, atol=1e-12)
+
+
+def test_non_finite_gradients_skip_the_update():
+    lin = torch.nn.Linear(1000, 37).to(DEV)
+    flat = FlatParams(lin)
+    opt = FlatAdamW(flat, lr=1e-2)
+    before = flat.data.clone()
+    flat.grad.normal_()
+    flat.grad[12345] = float("inf")
+    opt.step(check_finite=True)
+    assert opt.found_inf.item() == 1.0 and torch.equal(flat.data, before)
+    flat.grad[12345] = float("nan")
+    opt.step(check_finite=True)
+    assert opt.found_inf.item() == 1.0 and torch.equal(flat.data, before)
+    flat.grad[12345] = 0.5
+    opt.step(check_finite=True)
+    assert opt.found_inf.item() == 0.0 and not torch.equal(flat.data, before)
+
+
+@pytest.mark.parametrize("case", ["train_tiny_t0.npz", "train_tiny_t1.npz"])
+def test_two_training_steps_match_reference(case):
+    net, lq, gt, z = load_train_case(case)
+    net = net.to(DEV)
+    n0 = capi.launch_count
+    ts = TrainStep(net, OPTIM)
+    lq, gt = lq.to(DEV), gt.to(DEV)
+    l1 = ts.step(lq, gt).item()
+    l2 = ts.step(lq, gt).item()
+    assert capi.launch_count - n0 == 2                          # one AdamW launch per step on our library
+    assert abs(l1 - float(z["losses"][0])) < 1e-5
+    assert abs(l2 - float(z["losses"][1])) < 2e-5               # second loss is evaluated on the updated weights
+    lr = OPTIM["lr"]
+    worst, n_off, n_all = 0.0, 0, 0
+    for name, p in net.named_parameters():
+        want = torch.from_numpy(z["after2::" + name]).to(DEV)
+        d = (p.detach() - want).abs()
+        worst = max(worst, d.max().item())
+        n_off += int((d > 2e-5).sum())
+        n_all += d.numel()
+    # Adam normalises the step to ~lr per element whatever the gradient's size, so an element whose gradient is at
+    # rounding-noise level may move by up to 2 steps x lr differently; everything else is tight
+    assert worst <= 2.05 * 2 * lr, worst
+    assert n_off <= 0.01 * n_all, (n_off, n_all)
+
+
+def test_fp16_autocast_step_with_loss_scaler_and_eval_after_training():
+    net, lq, gt, z = load_train_case("train_tiny_t1.npz")
+    net = net.to(DEV)
+    ts = TrainStep(net, OPTIM, amp="fp16")
+    lq, gt = lq.to(DEV), gt.to(DEV)
+    losses = [ts.step(lq, gt).item() for _ in range(3)]
+    assert all(np.isfinite(losses)) and abs(losses[0] - float(z["losses"][0])) < 5e-3
+    assert ts.opt.steps + ts.skipped_steps == 3
+    # the inference engine picks up the updated (flat-buffer) weights: eval forward == autograd graph, no_grad
+    net.eval()
+    x = torch.stack([lq[:1, 0], lq[:1, 1]], 1)
+    with torch.no_grad():
+        got, _, _ = net.set_precision("fp32")(x)
+        from turtlevsr_b200.training import autograd_forward
+        want, _, _ = autograd_forward(net, x)
+    assert (got - want).abs().max().item() < 1e-4

@@ -312,9 +312,10 @@ class TurtleNet(nn.Module):
     def forward(self, inp_img_, k_cached: Optional[List] = None, v_cached: Optional[List] = None):
         from ..engine import FrameEngine
         if self.training and torch.is_grad_enabled():
-            raise RuntimeError(
-                "turtlevsr_b200 implements the inference hot path only; call under torch.no_grad() "
-                "or model.eval() (training-step kernels are a later scope row, SURVEY.md 8f).")
+            # training step (cfg 5, VRM:78-108): the differentiable graph of training.py (library autograd kernels);
+            # the hand-written inference kernels have no backward yet
+            from ..training import autograd_forward
+            return autograd_forward(self, inp_img_, k_cached, v_cached)
         if self._engine is None:
             self._engine = FrameEngine(self)
         return self._engine.forward(inp_img_, k_cached, v_cached)
