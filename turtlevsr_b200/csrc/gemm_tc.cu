@@ -327,7 +327,7 @@ struct alignas(64) Tc2Params {
     long long P;
     int Cout, NG, ngroups;
     long long total_units;
-    int tma_epi;
+    int tma_epi, epi_boxes;
     const float *bias, *scale, *res;
     int act, ldres;
     float *out;
@@ -336,7 +336,7 @@ struct alignas(64) Tc2Params {
 
 constexpr int EPI_WARPS = 8;
 constexpr int EPI_BUF = 32 * 128;                       // one 32-row x 32-column staging box (4 KB)
-constexpr int EPI_BYTES = EPI_WARPS * 2 * EPI_BUF;      // 64 KB
+constexpr int EPI_BYTES = EPI_WARPS * 2 * EPI_BUF;      // 64 KB with two boxes per warp (the minimum)
 
 // PAIR: the kernel runs as clusters of two CTAs sharing one M256 x NG MMA (tcgen05 cta_group::2).  Each CTA stages its
 // own 128 rows of A and HALF of the weight rows of the n-group (the tensor core reads the other half from the peer's
@@ -346,7 +346,7 @@ constexpr int EPI_BYTES = EPI_WARPS * 2 * EPI_BUF;      // 64 KB
 template <bool A16, bool O16, bool PAIR>
 __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant__ Tc2Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2], rfull_bar[EPI_WARPS][2];
+    __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2], rfull_bar[EPI_WARPS][4];
     __shared__ uint32_t tmem_base_sh;
     __shared__ float2 lnstat[2][4][2][32];      // fused LN: (mean, M2) of each row half, [tile parity][quarter][chalf][lane]
     pdl_trigger();
@@ -378,8 +378,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
             mbar_init(smem_u32(&tempty_bar[s]), EPI_WARPS * TPU);
         }
         for (int w = 0; w < EPI_WARPS; ++w) {
-            mbar_init(smem_u32(&rfull_bar[w][0]), 1);
-            mbar_init(smem_u32(&rfull_bar[w][1]), 1);
+            for (int b = 0; b < 4; ++b) mbar_init(smem_u32(&rfull_bar[w][b]), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -483,11 +482,39 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
         // parity ew>>2.  Each warp stages its own 32x32 boxes and issues its own TMA loads/stores,
         // so the only synchronisation inside the epilogue is __syncwarp.
         const int ew = warp - 4, quarter = ew & 3, chalf = ew >> 2;
-        const uint32_t mybuf = epi0 + ew * (2 * EPI_BUF);
+        const uint32_t mybuf = epi0 + ew * ((uint32_t)p.epi_boxes * EPI_BUF);
         const int eflags = (p.bias ? 1 : 0) | (p.act == TURTLE_ACT_GELU ? 2 : 0) | (p.scale ? 4 : 0);
         int it = 0;
-        uint32_t gw = 0;                                     // this warp's staging-box use counter
-        uint32_t rph = 0;                                    // fused-LN path: residual-barrier phase bit per box
+        uint32_t gw = 0;                                     // fp16-output path: this warp's staging-box use counter
+        uint32_t rph = 0;                                    // box ring: residual-barrier phase bit per box
+        // ---- box ring of the fp32-output paths (see the tma_epi branch below) ----
+        const int NB = p.epi_boxes;                          // 4 KB boxes owned by this warp
+        const int n_my = (NG / 32 - chalf + 1) / 2;          // 32-column chunks j = chalf, chalf+2, ... of this warp
+        const int spu = p.ln ? 2 * n_my : n_my;              // ring slots per work unit
+        int slot = 0, box = 0;                               // running slot index and its box (slot % NB)
+        // lane 0: cursor of the residual requests -- next slot, its position inside its unit, its box, and the unit's
+        // coordinates (kept incrementally: this runs once per chunk on the epilogue's critical path)
+        int next_r = 0, r_q = 0, r_box = 0, r_m0 = 0, r_n0 = 0;
+        long long r_u = u0;
+        auto issue_res = [&](int upto) {                     // request the residual boxes of slots <= upto
+            while (next_r <= upto) {
+                if (r_q == 0) {
+                    if (r_u >= p.total_units) { next_r = 0x7fffffff; break; }
+                    const long long grp = p.ngroups == 1 ? r_u : r_u / p.ngroups;
+                    r_n0 = p.ngroups == 1 ? 0 : (int)(r_u - grp * p.ngroups) * NG;
+                    r_m0 = (int)((grp * TPU + rank) * TM) + quarter * 32;
+                }
+                if (r_q < n_my) {                             // (LN output slots have nothing to load)
+                    const uint32_t rb = smem_u32(&rfull_bar[ew][r_box]);
+                    mbar_expect_tx(rb, EPI_BUF);
+                    tma_load_2d(mybuf + (uint32_t)r_box * EPI_BUF, &p.mapRes, r_n0 + (chalf + 2 * r_q) * 32, r_m0, rb);
+                }
+                ++next_r;
+                if (++r_box == NB) r_box = 0;
+                if (++r_q == spu) { r_q = 0; r_u += ustride; }
+            }
+        };
+        if (p.tma_epi && !O16 && p.res && lane == 0) issue_res(NB - 1);      // all boxes are free at the start
         for (long long u = u0; u < p.total_units; u += ustride, ++it) {
             const int ng = (int)(u % p.ngroups);
             const long long tile = (u / p.ngroups) * TPU + rank;
@@ -535,163 +562,113 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
                     }
                     j += nc;
                 }
-            } else if (!O16 && p.tma_epi && p.ln) {
-                // -------- residual update + fused LayerNorm of the updated rows (NG == Cout) --------
-                // pass 1: x = acc(+bias)(*scale) + res -> TMA store (fp32) ; x parked back in TMEM ; running (mean, M2)
-                // exchange the row statistics with the warp that owns the other chunk parity of the same rows
-                // pass 2: TMEM -> (x - mu) * rstd * w + b -> fp16 -> TMA store
-                const int m0 = (int)(tile * TM) + quarter * 32;
-                const int nch = NG / 32;
-                float mean = 0.f, M2 = 0.f, cnt = 0.f;
-                for (int j = chalf; j < nch; j += 2, ++gw) {
-                    const int b = gw & 1;
-                    const uint32_t buf = mybuf + b * EPI_BUF;
-                    const uint32_t rb = smem_u32(&rfull_bar[ew][b]);
-                    if (lane == 0) {
-                        if (gw >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                        mbar_expect_tx(rb, EPI_BUF);
-                        tma_load_2d(buf, &p.mapRes, n0 + j * 32, m0, rb);
-                    }
-                    __syncwarp();
-                    float v[32];
-                    tmem_ld32(trow + j * 32, v);
-                    epi_apply(eflags, v, p.bias, p.scale, n0 + j * 32);
-                    mbar_wait(rb, (rph >> b) & 1u);       // gw also counts pass-2 boxes here: track the phase per box
-                    rph ^= 1u << b;
-                    const uint32_t rowaddr = buf + lane * 128;
-                    float cs = 0.f;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const uint32_t addr = rowaddr + (((uint32_t)q ^ ((uint32_t)lane & 7u)) << 4);
-                        float4 r;
-                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                                     : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-                                     : "r"(addr));
-                        v[4 * q] += r.x; v[4 * q + 1] += r.y; v[4 * q + 2] += r.z; v[4 * q + 3] += r.w;
-                        cs += (v[4 * q] + v[4 * q + 1]) + (v[4 * q + 2] + v[4 * q + 3]);
-                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v[4 * q]), "f"(v[4 * q + 1]),
-                                     "f"(v[4 * q + 2]), "f"(v[4 * q + 3])
-                                     : "memory");
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_2d(&p.mapOut, buf, n0 + j * 32, m0);
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
-                    tmem_st32(trow + j * 32, v);
-                    // chunk statistics (two-pass inside the chunk), merged with Chan's formula
-                    const float cm = cs * (1.0f / 32.0f);
-                    float cM2 = 0.f;
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) cM2 = fmaf(v[e] - cm, v[e] - cm, cM2);
-                    const float tot = cnt + 32.0f, delta = cm - mean;
-                    mean = fmaf(delta, 32.0f / tot, mean);
-                    M2 += cM2 + delta * delta * (cnt * 32.0f / tot);
-                    cnt = tot;
-                }
-                tmem_wait_st();
-                lnstat[it & 1][quarter][chalf][lane] = make_float2(mean, M2);
-                asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-                const float2 o = lnstat[it & 1][quarter][chalf ^ 1][lane];
-                const float dl = o.x - mean;
-                const float mu = fmaf(0.5f, dl, mean);
-                const float var = (M2 + o.y + dl * dl * cnt * 0.5f) / (2.0f * cnt);
-                const float rstd = rsqrtf(var + 1e-5f);
-                for (int j = chalf; j < nch; j += 2, ++gw) {
-                    const int b = gw & 1;
-                    const uint32_t buf = mybuf + b * EPI_BUF;
-                    if (lane == 0 && gw >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    __syncwarp();
-                    float v[32];
-                    tmem_ld32(trow + j * 32, v);
-                    const int o0 = n0 + j * 32;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 w4 = __ldg(reinterpret_cast<const float4 *>(p.ln_w + o0 + 4 * q));
-                        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.ln_b + o0 + 4 * q));
-                        v[4 * q] = fmaf((v[4 * q] - mu) * rstd, w4.x, b4.x);
-                        v[4 * q + 1] = fmaf((v[4 * q + 1] - mu) * rstd, w4.y, b4.y);
-                        v[4 * q + 2] = fmaf((v[4 * q + 2] - mu) * rstd, w4.z, b4.z);
-                        v[4 * q + 3] = fmaf((v[4 * q + 3] - mu) * rstd, w4.w, b4.w);
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {     // 32 rows x 64 B, SWIZZLE_64B (16 B chunk ^= (row>>1)&3)
-                        const uint32_t addr = buf + lane * 64 + (((uint32_t)q ^ (((uint32_t)lane >> 1) & 3u)) << 4);
-                        __half2 h0 = __floats2half2_rn(v[8 * q + 0], v[8 * q + 1]);
-                        __half2 h1 = __floats2half2_rn(v[8 * q + 2], v[8 * q + 3]);
-                        __half2 h2 = __floats2half2_rn(v[8 * q + 4], v[8 * q + 5]);
-                        __half2 h3 = __floats2half2_rn(v[8 * q + 6], v[8 * q + 7]);
-                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(*reinterpret_cast<uint32_t *>(&h0)),
-                                     "r"(*reinterpret_cast<uint32_t *>(&h1)), "r"(*reinterpret_cast<uint32_t *>(&h2)),
-                                     "r"(*reinterpret_cast<uint32_t *>(&h3))
-                                     : "memory");
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_2d(&p.mapLN, buf, n0 + j * 32, m0);
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    }
-                }
             } else if (p.tma_epi) {
+                // -------- fp32 output (+ residual) (+ fused LayerNorm of the updated rows) through the box ring --------
+                // slots of this unit: n_my "R" slots (acc(+bias)(*scale) + res -> fp32 TMA store; with LN the updated row is
+                // parked back in TMEM with running (mean, M2)) and, with LN, n_my "O" slots (TMEM -> normalise -> fp16
+                // TMA store).  The residual box of slot s was requested NB-1 slots ago (see issue_res), so its DRAM
+                // round trip overlaps the chunks in between instead of being exposed once per chunk.
                 const int m0 = (int)(tile * TM) + quarter * 32;
-                for (int j = chalf; j < NG / 32; j += 2, ++gw) {
-                    const int b = gw & 1;
-                    const uint32_t buf = mybuf + b * EPI_BUF;
-                    const uint32_t rb = smem_u32(&rfull_bar[ew][b]);
-                    if (lane == 0) {
-                        if (gw >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // box b drained
-                        if (p.res) {
-                            mbar_expect_tx(rb, EPI_BUF);
-                            tma_load_2d(buf, &p.mapRes, n0 + j * 32, m0, rb);
-                        }
+                float mean = 0.f, M2 = 0.f, cnt = 0.f, mu = 0.f, rstd = 0.f;
+                for (int q = 0; q < spu; ++q, ++slot) {
+                    const int jj = q < n_my ? q : q - n_my;
+                    const int j = chalf + 2 * jj;
+                    const uint32_t buf = mybuf + (uint32_t)box * EPI_BUF;
+                    if (p.ln && q == n_my) {
+                        // exchange the row statistics with the warp that owns the other chunk parity of the same rows
+                        tmem_wait_st();
+                        lnstat[it & 1][quarter][chalf][lane] = make_float2(mean, M2);
+                        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+                        const float2 o = lnstat[it & 1][quarter][chalf ^ 1][lane];
+                        const float dl = o.x - mean;
+                        mu = fmaf(0.5f, dl, mean);
+                        const float var = (M2 + o.y + dl * dl * cnt * 0.5f) / (2.0f * cnt);
+                        rstd = rsqrtf(var + 1e-5f);
                     }
-                    __syncwarp();
+                    __syncwarp();        // lane 0's wait_group.read of the previous slot precedes our writes to `buf`
                     float v[32];
                     tmem_ld32(trow + j * 32, v);
-                    epi_apply(eflags, v, p.bias, p.scale, n0 + j * 32);
-                    if (O16) {
-                        // fp16 output: 32 rows x 64 B, SWIZZLE_64B (16 B chunk ^= (row>>1)&3)
-                        const uint32_t rowaddr = buf + lane * 64;
+                    if (q < n_my) {
+                        epi_apply(eflags, v, p.bias, p.scale, n0 + j * 32);
+                        if (p.res) {
+                            mbar_wait(smem_u32(&rfull_bar[ew][box]), (rph >> box) & 1u);
+                            rph ^= 1u << box;
+                        }
+                        const uint32_t rowaddr = buf + lane * 128;
+                        float cs = 0.f;
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint32_t addr = rowaddr + (((uint32_t)q ^ (((uint32_t)lane >> 1) & 3u)) << 4);
-                            __half2 h0 = __floats2half2_rn(v[8 * q + 0], v[8 * q + 1]);
-                            __half2 h1 = __floats2half2_rn(v[8 * q + 2], v[8 * q + 3]);
-                            __half2 h2 = __floats2half2_rn(v[8 * q + 4], v[8 * q + 5]);
-                            __half2 h3 = __floats2half2_rn(v[8 * q + 6], v[8 * q + 7]);
+                        for (int e = 0; e < 8; ++e) {
+                            const uint32_t addr = rowaddr + (((uint32_t)e ^ ((uint32_t)lane & 7u)) << 4);
+                            float4 t = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                            if (p.res) {
+                                float4 r;
+                                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                             : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                                             : "r"(addr));
+                                t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
+                            }
+                            if (p.round_out) t = rna_tf32(t);
+                            v[4 * e] = t.x; v[4 * e + 1] = t.y; v[4 * e + 2] = t.z; v[4 * e + 3] = t.w;
+                            cs += (t.x + t.y) + (t.z + t.w);
+                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(t.x), "f"(t.y), "f"(t.z),
+                                         "f"(t.w)
+                                         : "memory");
+                        }
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&p.mapOut, buf, n0 + j * 32, m0);
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                        if (p.ln) {
+                            tmem_st32(trow + j * 32, v);
+                            // chunk statistics (two-pass inside the chunk), merged with Chan's formula
+                            const float cm = cs * (1.0f / 32.0f);
+                            float cM2 = 0.f;
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) cM2 = fmaf(v[e] - cm, v[e] - cm, cM2);
+                            const float tot = cnt + 32.0f, delta = cm - mean;
+                            mean = fmaf(delta, 32.0f / tot, mean);
+                            M2 += cM2 + delta * delta * (cnt * 32.0f / tot);
+                            cnt = tot;
+                        }
+                    } else {
+                        const int o0 = n0 + j * 32;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const float4 w4 = __ldg(reinterpret_cast<const float4 *>(p.ln_w + o0 + 4 * e));
+                            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.ln_b + o0 + 4 * e));
+                            v[4 * e] = fmaf((v[4 * e] - mu) * rstd, w4.x, b4.x);
+                            v[4 * e + 1] = fmaf((v[4 * e + 1] - mu) * rstd, w4.y, b4.y);
+                            v[4 * e + 2] = fmaf((v[4 * e + 2] - mu) * rstd, w4.z, b4.z);
+                            v[4 * e + 3] = fmaf((v[4 * e + 3] - mu) * rstd, w4.w, b4.w);
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {     // 32 rows x 64 B, SWIZZLE_64B (16 B chunk ^= (row>>1)&3)
+                            const uint32_t addr = buf + lane * 64 + (((uint32_t)e ^ (((uint32_t)lane >> 1) & 3u)) << 4);
+                            __half2 h0 = __floats2half2_rn(v[8 * e + 0], v[8 * e + 1]);
+                            __half2 h1 = __floats2half2_rn(v[8 * e + 2], v[8 * e + 3]);
+                            __half2 h2 = __floats2half2_rn(v[8 * e + 4], v[8 * e + 5]);
+                            __half2 h3 = __floats2half2_rn(v[8 * e + 6], v[8 * e + 7]);
                             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(*reinterpret_cast<uint32_t *>(&h0)),
                                          "r"(*reinterpret_cast<uint32_t *>(&h1)), "r"(*reinterpret_cast<uint32_t *>(&h2)),
                                          "r"(*reinterpret_cast<uint32_t *>(&h3))
                                          : "memory");
                         }
-                    } else {
-                    if (p.res) mbar_wait(rb, (gw >> 1) & 1);
-                    const uint32_t rowaddr = buf + lane * 128;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const uint32_t addr = rowaddr + (((uint32_t)q ^ ((uint32_t)lane & 7u)) << 4);
-                        float4 t = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                        if (p.res) {
-                            float4 r;
-                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                                         : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-                                         : "r"(addr));
-                            t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&p.mapLN, buf, n0 + j * 32, m0);
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         }
-                        if (p.round_out) t = rna_tf32(t);
-                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(t.x), "f"(t.y), "f"(t.z),
-                                     "f"(t.w)
-                                     : "memory");
                     }
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
                     if (lane == 0) {
-                        tma_store_2d(&p.mapOut, buf, n0 + j * 32, m0);
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        // every store but the one just committed has left shared memory: the boxes of slots <= slot-1 are
+                        // free, so residual boxes up to slot+NB-1 can be requested
+                        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        if (p.res) issue_res(slot + NB - 1);
                     }
+                    if (++box == NB) box = 0;
                 }
             } else {
                 const int row = quarter * 32 + lane;
@@ -965,7 +942,25 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
     p.total_units = (pair ? (tiles + 1) / 2 : tiles) * p.ngroups;
     const size_t stage_bytes = A_STAGE_BYTES + (size_t)(pair ? NG / 2 : NG) * TK * 4;
     const size_t max_smem = 232448 - 6144;   // 227 KB opt-in limit minus the kernel's static smem (barriers, LN statistics)
-    int stages = (int)((max_smem - 1024 - EPI_BYTES) / stage_bytes);
+    // staging boxes per epilogue warp: the fp32-output paths that read a residual keep NB-1 residual boxes in flight
+    // per warp, so take 4 (or 3) boxes where the operand ring still holds min(nkb, 3) stages
+    static const int box_cap = getenv("TURTLE_GEMM_EPIBOX") ? atoi(getenv("TURTLE_GEMM_EPIBOX")) : 4;
+    // stages the operand ring must keep: short K loops (<= 4 k-blocks) run on 2, long ones want the depth
+    // (measured, scripts/gemm_micro.py: 256->256+res+LN @58880 53.4 -> 47.7 us with 3 boxes / 2 stages; 256->128 @235520
+    //  87.1 -> 74.3 us and 128->64 @942080 160.7 -> 138.0 us with 3-4 boxes at >= 3 stages; 1280->512 loses with < 4 stages)
+    static const int min_st_short = getenv("TURTLE_GEMM_MINST_SHORT") ? atoi(getenv("TURTLE_GEMM_MINST_SHORT")) : 0;
+    static const int min_st_long = getenv("TURTLE_GEMM_MINST_LONG") ? atoi(getenv("TURTLE_GEMM_MINST_LONG")) : 4;
+    const int min_st = p.nkb <= 4 ? (min_st_short ? min_st_short : (NG == 256 ? 2 : 3)) : min_st_long;
+    int boxes = 2;
+    if (a->res && !o16)
+        for (int cand = box_cap < 4 ? box_cap : 4; cand > 2; --cand)
+            if ((long long)((max_smem - 1024 - (size_t)EPI_WARPS * cand * EPI_BUF) / stage_bytes) >= (p.nkb < min_st ? p.nkb : min_st)) {
+                boxes = cand;
+                break;
+            }
+    p.epi_boxes = boxes;
+    const size_t epi_bytes = (size_t)EPI_WARPS * boxes * EPI_BUF;
+    int stages = (int)((max_smem - 1024 - epi_bytes) / stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) return TURTLE_ENOTSUP;
     p.stages = stages;
@@ -996,7 +991,7 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
         if (!p.tma_epi || o16 || !a->res || p.ngroups != 1 || (NG != 64 && NG != 128 && NG != 256)) return TURTLE_ENOTSUP;
         p.ln = 1; p.ln_w = a->ln_w; p.ln_b = a->ln_b;
     }
-    const size_t smem = stages * stage_bytes + EPI_BYTES + 1024;
+    const size_t smem = stages * stage_bytes + epi_bytes + 1024;
     if (o16 && !p.tma_epi) return TURTLE_ENOTSUP;
     static bool configured = false;
     static int nsm = 148;
