@@ -228,6 +228,7 @@ def main():
     ap.add_argument("--height", type=int, default=H720)
     ap.add_argument("--width", type=int, default=W720)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="issue every frame launch by launch (no CUDA-graph replay)")
     ap.add_argument("--workload", default="infer", choices=["infer", "train"],
                     help="infer = the BASELINE metric (default); train = cfg 5's DDP training step (secondary line)")
     args = ap.parse_args()
@@ -270,6 +271,8 @@ def main():
     if args.workload == "train":
         return train_arm(args, rank, world, local_rank, dev, dist, barrier)
     net, opt = build_model(args.precision, dev)
+    use_graphs = not args.no_graphs
+    net.enable_cuda_graphs(use_graphs)
     K, Wm = args.steps, max(args.warmup, 3)
     T = K + Wm
     g = torch.Generator().manual_seed(1000 + rank)            # every rank restores its own clip
@@ -283,7 +286,15 @@ def main():
         return torch.stack([pre, cur], 1)
 
     k = v = None
+    primed = 0
     with torch.no_grad():
+        if use_graphs:
+            # untimed priming: fill the history rings and capture one CUDA graph per joint ring state (RING_PERIOD + 1
+            # of them); the warm-up and timed frames below then replay exactly the work an eager frame launches
+            from turtlevsr_b200.history import RING_PERIOD
+            for j in range(3 * RING_PERIOD + 4):
+                _, k, v = net(frame_pair(dev_clip, j), k, v)
+                primed += 1
         for j in range(Wm):
             _, k, v = net(frame_pair(dev_clip, j), k, v)
         barrier()
@@ -306,7 +317,9 @@ def main():
         warm_host = host_clip[idx[:Wm], 0].unsqueeze(0).contiguous().pin_memory()       # [1, Wm, 3, H, W]
         timed_host = host_clip[idx[Wm:], 0].unsqueeze(0).contiguous().pin_memory()      # [1, K, 3, H, W]
         out_host = torch.empty(1, K, 3, Hh, Ww).pin_memory()
-        _, k, v, last = run_clip_streamed(net, warm_host, torch.empty(1, Wm, 3, Hh, Ww).pin_memory(), dev)
+        # (continues the device-resident clip's history, so its rings -- and the graphs captured for them -- are reused)
+        _, k, v, last = run_clip_streamed(net, warm_host, torch.empty(1, Wm, 3, Hh, Ww).pin_memory(), dev, k=k, v=v,
+                                          prev=dev_clip[(T - 1) % pool])
         barrier()
         e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e2.record()
@@ -373,7 +386,9 @@ def main():
                        "storage": ("fp32 channels-last residual stream and history rings; fp16 block intermediates, "
                                    "TF32/fp16 tensor-core operands, fp32 accumulation" if args.precision == "tf32"
                                    else "fp32 channels-last"),
-                       "l2": "per-frame working set (several GB) >> 126 MB L2; no explicit flush"},
+                       "l2": "per-frame working set (several GB) >> 126 MB L2; no explicit flush",
+                       "launch": (f"CUDA-graph replay, one graph per joint history-ring state ({net._engine.graph_captures} "
+                                  f"captured in {primed} untimed priming frames)" if use_graphs else "eager launches")},
             "clocks": clk.summary(),
             "e2e": {"value": world * K / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h},

@@ -282,6 +282,7 @@ class TurtleNet(nn.Module):
         self.padder_size = (2 ** 3) * 4
         # execution state (not part of the state dict)
         self.precision = "fp32"        # "fp32": CUDA-core fp32 everywhere; "tf32": tcgen05 TF32 contractions
+        self.cuda_graphs = False
         self.half_intermediates = True  # tf32 mode: FFN-side intermediates stored fp16 (same 10-bit mantissa as TF32)
         self._engine = None
 
@@ -291,6 +292,13 @@ class TurtleNet(nn.Module):
         if mode not in ("fp32", "tf32"):
             raise ValueError(mode)
         self.precision = mode
+        return self
+
+    def enable_cuda_graphs(self, flag: bool = True) -> "TurtleNet":
+        """Replay steady-state frames (all history rings full, caches passed back unchanged) from CUDA graphs, one per
+        joint ring state (history.RING_PERIOD of them per clip); other frames run eagerly.  Results are bit-identical to
+        the eager path -- the same kernels in the same order."""
+        self.cuda_graphs = bool(flag)
         return self
 
     def invalidate_packed_weights(self) -> None:

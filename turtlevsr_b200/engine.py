@@ -68,6 +68,12 @@ class FrameEngine:
         self.profile: Optional[dict] = None
         self.profile_shapes = False
         self._meta = (0, 0)
+        # CUDA-graph replay (see _graph_forward): joint ring state -> captured frame
+        self.graphs: Dict[tuple, tuple] = {}
+        self._graph_pool = None
+        self._graph_seen = set()
+        self.graph_captures = 0
+        self.graph_replays = 0
 
     def _call(self, name, *args):
         if self.dry_run:
@@ -106,6 +112,8 @@ class FrameEngine:
 
     def invalidate(self):
         self.packed.clear()
+        self.graphs.clear()          # captured graphs hold the packed-weight addresses
+        self._graph_seen.clear()
 
     # ------------------------------------------------------------------------------------
     # parameters
@@ -657,8 +665,77 @@ class FrameEngine:
     # ------------------------------------------------------------------------------------
     # whole frame
     # ------------------------------------------------------------------------------------
+    # ------------------------------------------------------------------------------------
+    # CUDA-graph replay of the steady-state frame (model.enable_cuda_graphs())
+    #
+    # A frame is ~520 dependent launches; at small frame sizes (256x256 crops, the 320x320 tiles of tiled inference)
+    # the host cannot issue them as fast as the GPU retires them, and even at 1280x720 the per-launch gaps add up.
+    # Once every history ring of the clip is full, the device addresses a frame touches depend only on the joint ring
+    # state, which repeats every history.RING_PERIOD frames, so each state is captured once and replayed afterwards.
+    # The key holds the ring identities, so independent histories (clips, tiles) get their own graphs.
+    # ------------------------------------------------------------------------------------
+    MAX_GRAPHS = 256
+
+    @torch.no_grad()
+    def _graph_forward(self, inp, k_cached, v_cached):
+        if k_cached is None or v_cached is None:
+            return None
+        rings = []
+        for k, v in zip(k_cached, v_cached):
+            if k is None and v is None:
+                continue
+            r = resolve_ring(k, v)
+            if r is None or r.count < r.keep:
+                return None                       # foreign caches or a history still filling up: eager frame
+            rings.append(r)
+        if not rings or not self.packed:
+            return None                           # weights not packed yet (first frame after load/.to())
+        m = self.model
+        key = (tuple(inp.shape), inp.device.index, m.precision, self.use_half, self.fuse_ln, self.sab_front_half,
+               tuple((id(r), r.pos) for r in rings))
+        ent = self.graphs.get(key)
+        if ent is None:
+            if key not in self._graph_seen:
+                # first visit of this state: run it eagerly, so that every lazily built host-side object it needs (flag
+                # tensors, tensor maps, workspace growth) exists before the capture of its second visit
+                if len(self._graph_seen) > 4 * self.MAX_GRAPHS:
+                    self._graph_seen.clear()
+                self._graph_seen.add(key)
+                return None
+            if len(self.graphs) >= self.MAX_GRAPHS:
+                self.graphs.pop(next(iter(self.graphs)))
+            static_in = torch.empty_like(inp, memory_format=torch.contiguous_format)
+            static_in.copy_(inp)
+            n0 = capi.launch_count
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=self._graph_pool):
+                out, ks, vs = self._forward_eager(static_in, k_cached, v_cached)
+            if self._graph_pool is None:
+                self._graph_pool = g.pool()
+            post = [(r.pos, r.count, r._sig) for r in rings]
+            ent = self.graphs[key] = (g, static_in, out, ks, vs, rings, post, capi.launch_count - n0)
+            self.graph_captures += 1
+        else:
+            g, static_in, out, ks, vs, rings, post, nl = ent
+            static_in.copy_(inp)
+            for r, (pos, count, sig) in zip(rings, post):
+                r.pos, r.count, r._sig = pos, count, sig
+            capi.launch_count += nl
+        ent[0].replay()
+        self.graph_replays += 1
+        return ent[2].clone(), list(ent[3]), list(ent[4])
+
     @torch.no_grad()
     def forward(self, inp: torch.Tensor, k_cached=None, v_cached=None):
+        if (getattr(self.model, "cuda_graphs", False) and not self.dry_run and self.profile is None
+                and not getattr(self.model, "record_trace", False) and inp.is_cuda and inp.dim() == 5):
+            r = self._graph_forward(inp.float(), k_cached, v_cached)
+            if r is not None:
+                return r
+        return self._forward_eager(inp, k_cached, v_cached)
+
+    @torch.no_grad()
+    def _forward_eager(self, inp: torch.Tensor, k_cached=None, v_cached=None):
         m = self.model
         if not inp.is_cuda and not self.dry_run:
             raise RuntimeError("turtlevsr_b200 runs on CUDA tensors only (no CPU fallback)")

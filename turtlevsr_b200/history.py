@@ -26,6 +26,14 @@ from typing import Optional, Tuple
 import torch
 
 RING_SLOTS = int(os.environ.get("TURTLE_RING_SLOTS", "8"))
+# Every ring compacts once per RING_PERIOD frames whatever its depth K (slots = K + period by default), so the joint
+# state of all rings of a clip -- and with it the set of device addresses a frame touches -- repeats with that period:
+# the frame can be replayed from RING_PERIOD CUDA graphs (engine.FrameEngine, cuda_graphs mode).
+RING_PERIOD = max(RING_SLOTS - 3, 2)
+
+
+def default_slots(keep: int) -> int:
+    return max(keep + RING_PERIOD, 2 * keep + 2)
 
 
 class _RingBase:
@@ -70,8 +78,8 @@ def _sig(t: torch.Tensor):
 class SabRing(_RingBase):
     """History of a StateAlignBlock: k rows [N,Dk] and v patch rows [N,Dv] per frame."""
 
-    def __init__(self, B, N, Dk, Dv, keep, device, slots=RING_SLOTS):
-        super().__init__(keep, slots)
+    def __init__(self, B, N, Dk, Dv, keep, device, slots=None):
+        super().__init__(keep, slots or default_slots(keep))
         self.B, self.N, self.Dk, self.Dv = B, N, Dk, Dv
         self.kbuf = torch.empty(B, self.slots, N, Dk, device=device, dtype=torch.float32)
         self.vbuf = torch.empty(B, self.slots, N, Dv, device=device, dtype=torch.float32)
@@ -107,8 +115,8 @@ class FhrRing(_RingBase):
     channels-last map [P, C].  Stored as [B, P, heads, M*ch] so that the reference-shaped window
     [B, heads, Fc*ch, P] is a plain strided view (frames are contiguous inside a head)."""
 
-    def __init__(self, B, P, heads, ch, keep, device, slots=RING_SLOTS):
-        super().__init__(keep, slots)
+    def __init__(self, B, P, heads, ch, keep, device, slots=None):
+        super().__init__(keep, slots or default_slots(keep))
         self.B, self.P, self.heads, self.ch = B, P, heads, ch
         self.kbuf = torch.empty(B, P, heads, self.slots * ch, device=device, dtype=torch.float32)
         self.vbuf = torch.empty(B, P, heads, self.slots * ch, device=device, dtype=torch.float32)
