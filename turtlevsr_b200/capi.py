@@ -72,7 +72,8 @@ class TurtleKernelError(RuntimeError):
 
 
 def lib_path() -> str:
-    return _build.LIB
+    """The in-tree library; TURTLE_LIB_PATH points at another build of the same ABI (A/B measurements)."""
+    return os.environ.get("TURTLE_LIB_PATH") or _build.LIB
 
 
 def load():

@@ -327,7 +327,7 @@ struct alignas(64) Tc2Params {
     long long P;
     int Cout, NG, ngroups;
     long long total_units;
-    int tma_epi, epi_boxes;
+    int tma_epi, epi_boxes, dbg_skip;
     const float *bias, *scale, *res;
     int act, ldres;
     float *out;
@@ -523,7 +523,9 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
             mbar_wait(smem_u32(&tfull_bar[acc]), (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * 256;
-            if (p.tma_epi && O16) {
+            if (p.dbg_skip) {
+                // (debug, TURTLE_DBG_SKIP_EPI: drain nothing -- measures the producer/MMA side alone)
+            } else if (p.tma_epi && O16) {
                 // fp16 output: contiguous chunk range per warp, two 32-column chunks (= one 128-byte row) per TMA
                 // store where possible -- TMA store cost scales with the number of row segments, not bytes.
                 const int m0 = (int)(tile * TM) + quarter * 32;
@@ -959,6 +961,8 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
                 break;
             }
     p.epi_boxes = boxes;
+    static const int dbg_skip = getenv("TURTLE_DBG_SKIP_EPI") ? atoi(getenv("TURTLE_DBG_SKIP_EPI")) : 0;
+    p.dbg_skip = dbg_skip;
     const size_t epi_bytes = (size_t)EPI_WARPS * boxes * EPI_BUF;
     int stages = (int)((max_smem - 1024 - epi_bytes) / stage_bytes);
     if (stages > 8) stages = 8;
