@@ -599,22 +599,27 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
                         const uint32_t rowaddr = buf + lane * 128;
                         float cs = 0.f;
 #pragma unroll
-                        for (int e = 0; e < 8; ++e) {
-                            const uint32_t addr = rowaddr + (((uint32_t)e ^ ((uint32_t)lane & 7u)) << 4);
-                            float4 t = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                        for (int e0 = 0; e0 < 8; e0 += 4) {      // four residual vectors in flight per batch
+                            float4 r[4];
                             if (p.res) {
-                                float4 r;
-                                asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                                             : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
-                                             : "r"(addr));
-                                t.x += r.x; t.y += r.y; t.z += r.z; t.w += r.w;
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                                 : "=f"(r[e].x), "=f"(r[e].y), "=f"(r[e].z), "=f"(r[e].w)
+                                                 : "r"(rowaddr + (((uint32_t)(e0 + e) ^ ((uint32_t)lane & 7u)) << 4)));
                             }
-                            if (p.round_out) t = rna_tf32(t);
-                            v[4 * e] = t.x; v[4 * e + 1] = t.y; v[4 * e + 2] = t.z; v[4 * e + 3] = t.w;
-                            cs += (t.x + t.y) + (t.z + t.w);
-                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(t.x), "f"(t.y), "f"(t.z),
-                                         "f"(t.w)
-                                         : "memory");
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const int i = 4 * (e0 + e);
+                                float4 t = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                                if (p.res) { t.x += r[e].x; t.y += r[e].y; t.z += r[e].z; t.w += r[e].w; }
+                                if (p.round_out) t = rna_tf32(t);
+                                v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+                                cs += (t.x + t.y) + (t.z + t.w);
+                                asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(rowaddr + (((uint32_t)(e0 + e) ^ ((uint32_t)lane & 7u)) << 4)),
+                                             "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w)
+                                             : "memory");
+                            }
                         }
                         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                         __syncwarp();
