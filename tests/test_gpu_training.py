@@ -75,18 +75,13 @@ def test_two_training_steps_match_reference(case):
     assert capi.launch_count - n0 == 2                          # one AdamW launch per step on our library
     assert abs(l1 - float(z["losses"][0])) < 1e-5
     assert abs(l2 - float(z["losses"][1])) < 2e-5               # second loss is evaluated on the updated weights
-    lr = OPTIM["lr"]
-    worst, n_off, n_all = 0.0, 0, 0
+    worst = 0.0
     for name, p in net.named_parameters():
         want = torch.from_numpy(z["after2::" + name]).to(DEV)
-        d = (p.detach() - want).abs()
-        worst = max(worst, d.max().item())
-        n_off += int((d > 2e-5).sum())
-        n_all += d.numel()
-    # Adam normalises the step to ~lr per element whatever the gradient's size, so an element whose gradient is at
-    # rounding-noise level may move by up to 2 steps x lr differently; everything else is tight
-    assert worst <= 2.05 * 2 * lr, worst
-    assert n_off <= 0.01 * n_all, (n_off, n_all)
+        worst = max(worst, (p.detach() - want).abs().max().item())
+    # measured 2.6e-7 (t0) / 1.5e-7 (t1) on B200 with the library TF32 paths off; one Adam step moves a weight by ~4e-4,
+    # so 5e-6 still pins every element's update direction and size
+    assert worst <= 5e-6, worst
 
 
 def test_autocast_steps_loss_scaler_and_eval_after_training():
