@@ -147,6 +147,31 @@ def test_tiled_inference_matches_oracle_tiling():
     assert len(dk) == 2 * 4 and all(t is None or t.is_cuda for t in dk["0-0"])
 
 
+def test_tiled_inference_batched_tiles_match_tile_by_tile():
+    """All tiles of a frame as one batch (one forward, rings with B = #tiles) == the tile-by-tile loop."""
+    import turtlevsr_b200.tiling as tl
+    opt, sd, _, _, _ = load_case("tiny_t1_live.npz")
+    loop_net, batch_net = build(opt, sd), build(opt, sd)
+    batch_net.enable_cuda_graphs()
+    g = torch.Generator().manual_seed(22)
+    clip = torch.rand(1, 16, 3, 90, 150, generator=g).cuda()     # long enough for second visits of the ring states
+    dk = dv = bk = bv = None
+    for j in range(clip.shape[1]):
+        prev, cur = clip[:, max(j - 1, 0)], clip[:, j]
+        want, dk, dv = tl.run_inference_patched(prev, cur, loop_net, "cuda", 64, 32, prev_patch_dict_k=dk,
+                                                prev_patch_dict_v=dv, model_type="t1")
+        got, bk, bv = tl.run_inference_patched(prev, cur, batch_net, "cuda", 64, 32, prev_patch_dict_k=bk,
+                                               prev_patch_dict_v=bv, model_type="t1", batch_tiles=True)
+        assert (got - want).abs().max() < 1e-5
+    assert set(bk) == set(dk) | {tl.BATCH_KEY}
+    for key in dk:                                          # per-tile slices of the batched rings == per-tile rings
+        for a, c in zip(dk[key], bk[key]):
+            assert (a is None) == (c is None)
+            if a is not None:
+                assert a.shape == c.shape and (a - c).abs().max() < 1e-5
+    assert batch_net._engine.graph_replays > 0              # steady-state batched frames replay from CUDA graphs
+
+
 def test_davis_config_480p_fp32_topk_exact():
     """Config 3: Turtle_Denoise_Davis.yml (MEST/CTS aliases), 854x480, sigma=50 noise (unclamped), fp32 mode."""
     from turtlevsr_b200.configs import shipped
