@@ -473,6 +473,8 @@ class FrameEngine:
         # --- q/k/v feature maps -----------------------------------------------------------
         src = xn
         if t0:
+            if c % 4 != 0:           # same failure as positionalencoding2d, T0:424-426
+                raise ValueError("Cannot use sin/cos positional encoding with odd dimension (got dim={:d})".format(c))
             src = self.ws.get("xpe", P, c)
             self._call("turtle_add_posenc", _ptr(xn), _ptr(src), B, H, W, c, self.stream)
         # selection front end in fp16 (tensor-core mode): qk map, its depthwise, the k2 / q2 maps; sums stay fp32
