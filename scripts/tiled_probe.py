@@ -11,7 +11,7 @@ clip = torch.rand(6, 1, 3, 720, 1280, generator=g).to(dev)
 for name, graphs, batch in [("tile by tile, eager", False, False), ("tile by tile, graphs", True, False),
                             ("batched tiles, eager", False, True), ("batched tiles, graphs", True, True)]:
     net, _ = build_model("tf32", dev)
-    net.enable_cuda_graphs(graphs)
+    net.enable_cuda_graphs(graphs, max_graphs=160)            # 24 tile histories x 6 ring states
     dk = dv = None
     n_warm, n = 14, 6
     with torch.no_grad():

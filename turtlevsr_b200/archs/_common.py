@@ -294,11 +294,17 @@ class TurtleNet(nn.Module):
         self.precision = mode
         return self
 
-    def enable_cuda_graphs(self, flag: bool = True) -> "TurtleNet":
+    def enable_cuda_graphs(self, flag: bool = True, max_graphs: int = 0) -> "TurtleNet":
         """Replay steady-state frames (all history rings full, caches passed back unchanged) from CUDA graphs, one per
         joint ring state (history.RING_PERIOD of them per clip); other frames run eagerly.  Results are bit-identical to
         the eager path -- the same kernels in the same order."""
         self.cuda_graphs = bool(flag)
+        if max_graphs:
+            # each history (clip, or tile of the tile-by-tile loop) needs RING_PERIOD + 1 graphs; a cached graph pins its
+            # history's rings in HBM until it is evicted (oldest first), so keep this near 6 x the histories in flight
+            self.cuda_graph_limit = int(max_graphs)
+            if self._engine is not None:
+                self._engine.max_graphs = int(max_graphs)
         return self
 
     def invalidate_packed_weights(self) -> None:

@@ -70,8 +70,8 @@ class FrameEngine:
         self._meta = (0, 0)
         # CUDA-graph replay (see _graph_forward): joint ring state -> captured frame
         self.graphs: Dict[tuple, tuple] = {}
-        self._graph_pool = None
         self._graph_seen = set()
+        self.max_graphs = int(getattr(model, "cuda_graph_limit", 0) or self.MAX_GRAPHS)
         self.graph_captures = 0
         self.graph_replays = 0
 
@@ -676,7 +676,8 @@ class FrameEngine:
     # state, which repeats every history.RING_PERIOD frames, so each state is captured once and replayed afterwards.
     # The key holds the ring identities, so independent histories (clips, tiles) get their own graphs.
     # ------------------------------------------------------------------------------------
-    MAX_GRAPHS = 256
+    MAX_GRAPHS = 48      # default cap (8 histories x 6 states); a cached graph keeps its history rings alive, so the
+                         # cap also bounds the HBM held for clips that have ended (oldest graphs are dropped first)
 
     @torch.no_grad()
     def _graph_forward(self, inp, k_cached, v_cached):
@@ -694,26 +695,24 @@ class FrameEngine:
             return None                           # weights not packed yet (first frame after load/.to())
         m = self.model
         key = (tuple(inp.shape), inp.device.index, m.precision, self.use_half, self.fuse_ln, self.sab_front_half,
-               tuple((id(r), r.pos) for r in rings))
+               tuple((r.serial, r.pos) for r in rings))
         ent = self.graphs.get(key)
         if ent is None:
             if key not in self._graph_seen:
                 # first visit of this state: run it eagerly, so that every lazily built host-side object it needs (flag
                 # tensors, tensor maps, workspace growth) exists before the capture of its second visit
-                if len(self._graph_seen) > 4 * self.MAX_GRAPHS:
+                if len(self._graph_seen) > 4 * self.max_graphs:
                     self._graph_seen.clear()
                 self._graph_seen.add(key)
                 return None
-            if len(self.graphs) >= self.MAX_GRAPHS:
+            while len(self.graphs) >= self.max_graphs:
                 self.graphs.pop(next(iter(self.graphs)))
             static_in = torch.empty_like(inp, memory_format=torch.contiguous_format)
             static_in.copy_(inp)
             n0 = capi.launch_count
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, pool=self._graph_pool):
+            with torch.cuda.graph(g):        # private memory pool per graph: replay order is free, eviction frees it
                 out, ks, vs = self._forward_eager(static_in, k_cached, v_cached)
-            if self._graph_pool is None:
-                self._graph_pool = g.pool()
             post = [(r.pos, r.count, r._sig) for r in rings]
             ent = self.graphs[key] = (g, static_in, out, ks, vs, rings, post, capi.launch_count - n0)
             self.graph_captures += 1

@@ -36,8 +36,12 @@ def default_slots(keep: int) -> int:
     return max(keep + RING_PERIOD, 2 * keep + 2)
 
 
+_ring_serial = iter(range(1, 1 << 62))
+
+
 class _RingBase:
     def __init__(self, keep: int, slots: int):
+        self.serial = next(_ring_serial)     # never reused (unlike id()): part of the CUDA-graph cache key
         self.keep = keep                     # K = num_frames_tocache of the owning block
         self.slots = max(slots, 2 * keep + 2)
         self.pos = -1                        # newest committed slot
