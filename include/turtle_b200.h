@@ -243,6 +243,18 @@ int turtle_grad_check_finite(const float *g, int64_t n, float *found, void *stre
 int turtle_adamw_flat(float *p, const float *g, float *m, float *v, int64_t n, float lr, float beta1, float beta2,
                       float eps, float weight_decay, int step, float grad_scale, const float *found, void *stream);
 
+/* Channel LayerNorm of the TRAINING graph (WithBias_LayerNorm, T1:83-112, as autograd sees it) on NCHW maps
+ * x [B,C,H,W] dense, x_dtype 0 = fp32, 1 = fp16, 2 = bf16 (the autocast residual stream); HW = H*W.
+ * fwd: y fp32 [B,C,H,W] = (x - mean) * rstd * w + b, mean / rstd [B*HW] saved for the backward (biased variance,
+ *      eps 1e-5).  Replaces the reference's to_3d / mean / var / sqrt / div / mul / add / to_4d chain (T1:96-112).
+ * bwd: dx (x's dtype), dw[C], db[C] from dy fp32; workspace of turtle_ln2d_bwd_workspace(C, B*HW) bytes holds the
+ *      per-block partial sums, reduced in a fixed order (deterministic dw / db).  C <= 768. */
+long long turtle_ln2d_bwd_workspace(int C, long long n_pixels);
+int turtle_ln2d_fwd(const void *x, int x_dtype, const float *w, const float *b, float *y, float *mean, float *rstd,
+                    int B, int C, long long HW, void *stream);
+int turtle_ln2d_bwd(const float *dy, const void *x, int x_dtype, const float *w, const float *mean, const float *rstd,
+                    void *dx, float *dw, float *db, void *workspace, int B, int C, long long HW, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

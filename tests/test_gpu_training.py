@@ -46,6 +46,39 @@ def test_adamw_flat_kernel_matches_torch_adamw(wd, n):
     assert torch.allclose(opt.exp_avg_sq[:n], st["exp_avg_sq"], rtol=1e-5, atol=1e-12)
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
+@pytest.mark.parametrize("B,C,H,W", [(2, 64, 17, 33), (1, 512, 8, 8), (3, 8, 5, 300)])
+def test_channel_layernorm_forward_backward_kernels(dtype, tol, B, C, H, W):
+    """turtle_ln2d_fwd / turtle_ln2d_bwd behind autograd vs the reference's formula (T1:96-112) in float64."""
+    from turtlevsr_b200.training import _ChannelLayerNorm
+    g = torch.Generator(device=DEV).manual_seed(B * C + H)
+    x = (torch.randn(B, C, H, W, device=DEV, generator=g) * 1.7 + 0.4).to(dtype).requires_grad_()
+    w = (torch.rand(C, device=DEV, generator=g) + 0.5).requires_grad_()
+    b = torch.randn(C, device=DEV, generator=g).requires_grad_()
+    dy = torch.randn(B, C, H, W, device=DEV, generator=g)
+    y = _ChannelLayerNorm.apply(x, w, b)
+    assert y.dtype == torch.float32
+    y.backward(dy)
+    xd = x.detach().double().requires_grad_()
+    wd, bd = w.detach().double().requires_grad_(), b.detach().double().requires_grad_()
+    mu = xd.mean(1, keepdim=True)
+    var = (xd - mu).pow(2).mean(1, keepdim=True)
+    yd = (xd - mu) / torch.sqrt(var + 1e-5) * wd.view(1, -1, 1, 1) + bd.view(1, -1, 1, 1)
+    yd.backward(dy.double())
+    assert (y.double() - yd).abs().max() < 1e-5                      # x is the same (already rounded) tensor on both sides
+    assert (x.grad.double() - xd.grad).abs().max() < tol * max(1.0, xd.grad.abs().max().item())
+    n = B * H * W
+    assert (w.grad.double() - wd.grad).abs().max() < 1e-5 * n ** 0.5 * 4
+    assert (b.grad.double() - bd.grad).abs().max() < 1e-5 * n ** 0.5 * 4
+    y2 = _ChannelLayerNorm.apply(x, w, b)                            # deterministic weight gradients
+    w.grad = None
+    y2.backward(dy)
+    w1 = w.grad.clone()
+    w.grad = None
+    _ChannelLayerNorm.apply(x, w, b).backward(dy)
+    assert torch.equal(w1, w.grad)
+
+
 def test_non_finite_gradients_skip_the_update():
     lin = torch.nn.Linear(1000, 37).to(DEV)
     flat = FlatParams(lin)
@@ -72,7 +105,7 @@ def test_two_training_steps_match_reference(case):
     lq, gt = lq.to(DEV), gt.to(DEV)
     l1 = ts.step(lq, gt).item()
     l2 = ts.step(lq, gt).item()
-    assert capi.launch_count - n0 == 2                          # one AdamW launch per step on our library
+    assert capi.launch_count - n0 > 2                           # LayerNorm fwd/bwd launches + one AdamW launch per step
     assert abs(l1 - float(z["losses"][0])) < 1e-5
     assert abs(l2 - float(z["losses"][1])) < 2e-5               # second loss is evaluated on the updated weights
     worst = 0.0

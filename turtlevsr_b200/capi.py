@@ -58,6 +58,9 @@ _SIGS = {
     "turtle_sab_aggregate": ([_fp, _fp, _fp, _i64, _fp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _fp], C.c_int),
     "turtle_cast_f16": ([_fp, _fp, _i64, _fp], C.c_int),
     "turtle_add_posenc": ([_fp, _fp, _i32, _i32, _i32, _i32, _fp], C.c_int),
+    "turtle_ln2d_bwd_workspace": ([_i32, C.c_longlong], C.c_longlong),
+    "turtle_ln2d_fwd": ([_fp, _i32, _fp, _fp, _fp, _fp, _fp, _i32, _i32, C.c_longlong, _fp], C.c_int),
+    "turtle_ln2d_bwd": ([_fp, _fp, _i32, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i32, _i32, C.c_longlong, _fp], C.c_int),
     "turtle_grad_check_finite": ([_fp, _i64, _fp, _fp], C.c_int),
     "turtle_adamw_flat": ([_fp, _fp, _fp, _fp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _fp, _fp], C.c_int),
 }

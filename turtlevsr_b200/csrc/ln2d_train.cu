@@ -1,0 +1,149 @@
+// Channel LayerNorm of the training graph (WithBias_LayerNorm, T1:83-112) on NCHW maps: forward and backward as one
+// kernel each instead of the ~10 + ~20 ATen launches of the reference's mean / var / sqrt / div / mul / add chain
+// (98 LayerNorms per frame, 10 frames per training step).  A thread owns one pixel and walks the channels with stride
+// H*W, so every load and store of a warp is a contiguous 128-byte (fp32) or 64-byte (fp16 / bf16) row segment.
+//   forward : Welford over C  ->  y = (x - mean) * rstd * w + b  (fp32 out, as autocast leaves it), mean / rstd saved
+//   backward: g = dy * w; dx = rstd * (g - mean_c(g) - xhat * mean_c(g * xhat)); per-block partial sums of dy * xhat and dy
+//             per channel (warp shuffles -> fixed-order combine in shared memory), reduced over blocks by a second kernel
+//             in a fixed order: the weight / bias gradients are run-to-run deterministic.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int LT = 256;                 // threads (= pixels) per block
+constexpr int LW = LT / 32;
+
+template <int DT> struct Elem;
+template <> struct Elem<0> { using T = float; };
+template <> struct Elem<1> { using T = __half; };
+template <> struct Elem<2> { using T = __nv_bfloat16; };
+__device__ __forceinline__ float ldf(const float *p) { return *p; }
+__device__ __forceinline__ float ldf(const __half *p) { return __half2float(*p); }
+__device__ __forceinline__ float ldf(const __nv_bfloat16 *p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void stf(float *p, float v) { *p = v; }
+__device__ __forceinline__ void stf(__half *p, float v) { *p = __float2half_rn(v); }
+__device__ __forceinline__ void stf(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
+
+template <int DT>
+__global__ void __launch_bounds__(LT) ln2d_fwd_kernel(const void *__restrict__ xv, const float *__restrict__ w,
+                                                      const float *__restrict__ b, float *__restrict__ y,
+                                                      float *__restrict__ mean_out, float *__restrict__ rstd_out,
+                                                      int C, int64_t HW, int64_t NP) {
+    using T = typename Elem<DT>::T;
+    const T *x = reinterpret_cast<const T *>(xv);
+    const int64_t pix = blockIdx.x * (int64_t)LT + threadIdx.x;
+    if (pix >= NP) return;
+    const int64_t base = (pix / HW) * C * HW + (pix % HW);
+    float mean = 0.f, m2 = 0.f;
+    for (int c = 0; c < C; ++c) {                      // Welford
+        const float v = ldf(x + base + c * HW);
+        const float d = v - mean;
+        mean += __fdividef(d, (float)(c + 1));
+        m2 = fmaf(d, v - mean, m2);
+    }
+    const float rstd = rsqrtf(m2 / (float)C + 1e-5f);
+    mean_out[pix] = mean;
+    rstd_out[pix] = rstd;
+    for (int c = 0; c < C; ++c) {
+        const float v = ldf(x + base + c * HW);
+        y[base + c * HW] = fmaf((v - mean) * rstd, __ldg(w + c), __ldg(b + c));
+    }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(LT) ln2d_bwd_kernel(const float *__restrict__ dy, const void *__restrict__ xv,
+                                                      const float *__restrict__ w, const float *__restrict__ mean_in,
+                                                      const float *__restrict__ rstd_in, void *__restrict__ dxv,
+                                                      float *__restrict__ part, int C, int64_t HW, int64_t NP) {
+    using T = typename Elem<DT>::T;
+    extern __shared__ float sm[];                      // [LW][C][2]: per-warp sums of (dy * xhat, dy) per channel
+    const T *x = reinterpret_cast<const T *>(xv);
+    T *dx = reinterpret_cast<T *>(dxv);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t pix = blockIdx.x * (int64_t)LT + tid;
+    const bool live = pix < NP;
+    const int64_t base = live ? (pix / HW) * C * HW + (pix % HW) : 0;
+    const float mean = live ? mean_in[pix] : 0.f, rstd = live ? rstd_in[pix] : 0.f;
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = 0; c < C; ++c) {
+        const float g = live ? dy[base + c * HW] * __ldg(w + c) : 0.f;
+        const float xh = live ? (ldf(x + base + c * HW) - mean) * rstd : 0.f;
+        s1 += g;
+        s2 = fmaf(g, xh, s2);
+    }
+    const float inv_c = 1.0f / (float)C;
+    s1 *= inv_c;
+    s2 *= inv_c;
+    for (int c = 0; c < C; ++c) {
+        const float d = live ? dy[base + c * HW] : 0.f;
+        const float xh = live ? (ldf(x + base + c * HW) - mean) * rstd : 0.f;
+        if (live) stf(dx + base + c * HW, rstd * (d * __ldg(w + c) - s1 - xh * s2));
+        const float a = warp_sum(d * xh), bsum = warp_sum(d);
+        if (lane == 0) {
+            sm[(warp * C + c) * 2] = a;
+            sm[(warp * C + c) * 2 + 1] = bsum;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < 2 * C; i += LT) {            // fixed-order combine of the warps
+        float t = 0.f;
+#pragma unroll
+        for (int wv = 0; wv < LW; ++wv) t += sm[wv * C * 2 + i];
+        part[(int64_t)blockIdx.x * 2 * C + i] = t;
+    }
+}
+
+// dw[c] = sum over blocks of part[blk][c][0], db[c] likewise: one warp per (channel, kind), lanes stride the blocks
+__global__ void __launch_bounds__(256) ln2d_reduce_kernel(const float *__restrict__ part, int nblk, int C,
+                                                          float *__restrict__ dw, float *__restrict__ db) {
+    const int gw = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (gw >= 2 * C) return;
+    float t = 0.f;
+    for (int k = lane; k < nblk; k += 32) t += part[(int64_t)k * 2 * C + gw];
+    t = warp_sum(t);
+    if (lane == 0) (gw & 1 ? db : dw)[gw >> 1] = t;
+}
+
+}  // namespace
+
+extern "C" long long turtle_ln2d_bwd_workspace(int C, long long n_pixels) {
+    if (C < 1 || n_pixels < 1) return -1;
+    return (long long)cdiv64(n_pixels, LT) * 2 * C * (long long)sizeof(float);
+}
+
+extern "C" int turtle_ln2d_fwd(const void *x, int x_dtype, const float *w, const float *b, float *y, float *mean,
+                               float *rstd, int B, int C, long long HW, void *stream) {
+    if (!x || !w || !b || !y || !mean || !rstd || B < 1 || C < 1 || HW < 1 || x_dtype < 0 || x_dtype > 2) return TURTLE_EINVAL;
+    const int64_t NP = (int64_t)B * HW;
+    const unsigned grid = (unsigned)cdiv64(NP, LT);
+    cudaStream_t s = as_stream(stream);
+    if (x_dtype == 0) ln2d_fwd_kernel<0><<<grid, LT, 0, s>>>(x, w, b, y, mean, rstd, C, HW, NP);
+    else if (x_dtype == 1) ln2d_fwd_kernel<1><<<grid, LT, 0, s>>>(x, w, b, y, mean, rstd, C, HW, NP);
+    else ln2d_fwd_kernel<2><<<grid, LT, 0, s>>>(x, w, b, y, mean, rstd, C, HW, NP);
+    TURTLE_CHECK_LAUNCH();
+    return TURTLE_OK;
+}
+
+extern "C" int turtle_ln2d_bwd(const float *dy, const void *x, int x_dtype, const float *w, const float *mean,
+                               const float *rstd, void *dx, float *dw, float *db, void *workspace, int B, int C,
+                               long long HW, void *stream) {
+    if (!dy || !x || !w || !mean || !rstd || !dx || !dw || !db || !workspace || B < 1 || C < 1 || HW < 1 || x_dtype < 0 ||
+        x_dtype > 2)
+        return TURTLE_EINVAL;
+    const size_t smem = (size_t)LW * C * 2 * sizeof(float);
+    if (smem > 48 * 1024) return TURTLE_ENOTSUP;       // C <= 768
+    const int64_t NP = (int64_t)B * HW;
+    const unsigned grid = (unsigned)cdiv64(NP, LT);
+    float *part = reinterpret_cast<float *>(workspace);
+    cudaStream_t s = as_stream(stream);
+    if (x_dtype == 0) ln2d_bwd_kernel<0><<<grid, LT, smem, s>>>(dy, x, w, mean, rstd, dx, part, C, HW, NP);
+    else if (x_dtype == 1) ln2d_bwd_kernel<1><<<grid, LT, smem, s>>>(dy, x, w, mean, rstd, dx, part, C, HW, NP);
+    else ln2d_bwd_kernel<2><<<grid, LT, smem, s>>>(dy, x, w, mean, rstd, dx, part, C, HW, NP);
+    TURTLE_CHECK_LAUNCH();
+    ln2d_reduce_kernel<<<(unsigned)cdiv64((int64_t)2 * C * 32, 256), 256, 0, s>>>(part, (int)grid, C, dw, db);
+    TURTLE_CHECK_LAUNCH();
+    return TURTLE_OK;
+}

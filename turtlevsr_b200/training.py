@@ -5,7 +5,8 @@ backward pass, and the optimizer as two passes over ONE flat fp32 buffer on hand
 What runs where (stated plainly):
 
 * forward + backward: ``autograd_forward`` below -- the same arch tree evaluated with differentiable torch ops
-  (cuDNN / cuBLAS / ATen library kernels on the GPU; BPTT through the history caches exactly as the reference does it,
+  (cuDNN / cuBLAS / ATen library kernels on the GPU, except the channel LayerNorm, whose forward and backward are the
+  hand-written ``turtle_ln2d_fwd`` / ``turtle_ln2d_bwd`` kernels of csrc/ln2d_train.cu; BPTT through the history caches exactly as the reference does it,
   the caches stay attached to the graph across the frames of a clip).  The hand-written inference kernels have no
   backward yet (SURVEY 8f rank 2), so ``TurtleNet.forward`` routes here when ``training and grad enabled``;
 * gradient exchange: ``GradBuckets`` -- every ``.grad`` is a view of one flat buffer cut into ~32 MB buckets in reverse
@@ -30,9 +31,50 @@ Tensor = torch.Tensor
 # ----------------------------------------------------------------------------------------
 # differentiable frame forward over the parameter-holder tree (archs/_common.py)
 # ----------------------------------------------------------------------------------------
+_LN_DTYPES = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
+class _ChannelLayerNorm(torch.autograd.Function):
+    """WithBias_LayerNorm (T1:83-112) on the sm_100a kernels turtle_ln2d_fwd / turtle_ln2d_bwd: one launch forward, two
+    backward, instead of the ~30 ATen launches autograd records for the mean / var / sqrt / div / mul / add chain."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        from . import capi
+        x = x.contiguous()
+        B, C, H, W = x.shape
+        y = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+        mean = torch.empty(B * H * W, device=x.device, dtype=torch.float32)
+        rstd = torch.empty_like(mean)
+        wf, bf = w.detach().float().contiguous(), b.detach().float().contiguous()
+        capi.call("turtle_ln2d_fwd", x.data_ptr(), _LN_DTYPES[x.dtype], wf.data_ptr(), bf.data_ptr(), y.data_ptr(),
+                  mean.data_ptr(), rstd.data_ptr(), B, C, H * W, torch.cuda.current_stream(x.device).cuda_stream)
+        ctx.save_for_backward(x, wf, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import capi
+        x, wf, mean, rstd = ctx.saved_tensors
+        B, C, H, W = x.shape
+        dy = dy.float().contiguous()
+        dx = torch.empty_like(x)
+        dw = torch.empty(C, device=x.device, dtype=torch.float32)
+        db = torch.empty_like(dw)
+        nbytes = capi.load().turtle_ln2d_bwd_workspace(C, B * H * W)
+        wsp = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32)
+        capi.call("turtle_ln2d_bwd", dy.data_ptr(), x.data_ptr(), _LN_DTYPES[x.dtype], wf.data_ptr(), mean.data_ptr(),
+                  rstd.data_ptr(), dx.data_ptr(), dw.data_ptr(), db.data_ptr(), wsp.data_ptr(), B, C, H * W,
+                  torch.cuda.current_stream(x.device).cuda_stream)
+        return dx, dw, db
+
+
 def _layernorm(norm, x: Tensor) -> Tensor:                      # T1:83-112
-    w = norm.body.weight.view(1, -1, 1, 1)
     b = getattr(norm.body, "bias", None)
+    if x.is_cuda and b is not None and x.dtype in _LN_DTYPES and x.shape[1] <= 768:
+        return _ChannelLayerNorm.apply(x, norm.body.weight, b)
+    # BiasFree variant (unused by the shipped ymls) and the CPU host-logic tests: the reference's formula on torch ops
+    w = norm.body.weight.view(1, -1, 1, 1)
     mu = x.mean(dim=1, keepdim=True)
     var = (x - mu).pow(2).mean(dim=1, keepdim=True)
     if b is None:
