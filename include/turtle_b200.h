@@ -248,12 +248,25 @@ int turtle_adamw_flat(float *p, const float *g, float *m, float *v, int64_t n, f
  * fwd: y fp32 [B,C,H,W] = (x - mean) * rstd * w + b, mean / rstd [B*HW] saved for the backward (biased variance,
  *      eps 1e-5).  Replaces the reference's to_3d / mean / var / sqrt / div / mul / add / to_4d chain (T1:96-112).
  * bwd: dx (x's dtype), dw[C], db[C] from dy fp32; workspace of turtle_ln2d_bwd_workspace(C, B*HW) bytes holds the
- *      per-block partial sums, reduced in a fixed order (deterministic dw / db).  C <= 768. */
+ *      per-block partial sums, reduced in a fixed order (deterministic dw / db). */
 long long turtle_ln2d_bwd_workspace(int C, long long n_pixels);
 int turtle_ln2d_fwd(const void *x, int x_dtype, const float *w, const float *b, float *y, float *mean, float *rstd,
                     int B, int C, long long HW, void *stream);
 int turtle_ln2d_bwd(const float *dy, const void *x, int x_dtype, const float *w, const float *mean, const float *rstd,
                     void *dx, float *dw, float *db, void *workspace, int B, int C, long long HW, void *stream);
+
+/* Depthwise 3x3 (stride 1, zero pad 1, groups = C) of the TRAINING graph on NCHW maps x [B,C,H,W] dense; dtype as in
+ * turtle_ln2d_fwd; w9 [C,9] fp32 taps (row-major 3x3), bias [C] fp32 or NULL.  Replaces nn.Conv2d(groups=C).forward
+ * (e.g. GatedFeedForward.dwconv T1:163, qkv_dwconv T1:674) and the three kernels autograd runs for it:
+ *   turtle_dwconv3x3_nchw(flip=0)          forward, y in x's dtype
+ *   turtle_dwconv3x3_nchw(dy, flip=1)      input gradient (taps flipped, bias NULL)
+ *   turtle_dwconv3x3_nchw_wgrad            dw9 [C,9] and db [C] (nullable); workspace of ..._wgrad_workspace bytes;
+ *                                          tile partials are reduced in a fixed order (deterministic). */
+int turtle_dwconv3x3_nchw(const void *x, int dtype, const float *w9, const float *bias, void *y, int B, int C, int H,
+                          int W, int flip, void *stream);
+long long turtle_dwconv3x3_nchw_wgrad_workspace(int B, int C, int H, int W);
+int turtle_dwconv3x3_nchw_wgrad(const void *x, const void *dy, int dtype, float *dw9, float *db, void *workspace, int B,
+                                int C, int H, int W, void *stream);
 
 #ifdef __cplusplus
 }

@@ -79,6 +79,36 @@ def test_channel_layernorm_forward_backward_kernels(dtype, tol, B, C, H, W):
     assert torch.equal(w1, w.grad)
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 3e-6), (torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
+@pytest.mark.parametrize("B,C,H,W,bias", [(2, 24, 37, 70, True), (1, 640, 32, 32, False), (3, 5, 64, 33, True)])
+def test_depthwise3x3_forward_backward_kernels(dtype, tol, B, C, H, W, bias):
+    """turtle_dwconv3x3_nchw / _wgrad behind autograd vs F.conv2d(groups=C) in float64."""
+    import torch.nn.functional as F
+    from turtlevsr_b200.training import _Depthwise3x3
+    g = torch.Generator(device=DEV).manual_seed(C + H)
+    x = torch.randn(B, C, H, W, device=DEV, generator=g).to(dtype).requires_grad_()
+    w = (torch.randn(C, 1, 3, 3, device=DEV, generator=g) / 3).requires_grad_()
+    b = torch.randn(C, device=DEV, generator=g).requires_grad_() if bias else None
+    dy = torch.randn(B, C, H, W, device=DEV, generator=g).to(dtype)
+    y = _Depthwise3x3.apply(x, w, b)
+    assert y.dtype == dtype
+    y.backward(dy)
+    xd, wd = x.detach().double().requires_grad_(), w.detach().double().requires_grad_()
+    bd = b.detach().double().requires_grad_() if bias else None
+    yd = F.conv2d(xd, wd, bd, padding=1, groups=C)
+    yd.backward(dy.double())
+    assert (y.double() - yd).abs().max() < tol * max(1.0, yd.abs().max().item())
+    assert (x.grad.double() - xd.grad).abs().max() < tol * max(1.0, xd.grad.abs().max().item())
+    n = B * H * W
+    assert (w.grad.double() - wd.grad).abs().max() < 2e-5 * n ** 0.5 * 4
+    if bias:
+        assert (b.grad.double() - bd.grad).abs().max() < 2e-5 * n ** 0.5 * 4
+    w1 = w.grad.clone()
+    w.grad = None
+    _Depthwise3x3.apply(x, w, b).backward(dy)
+    assert torch.equal(w1, w.grad)                                   # deterministic weight gradient
+
+
 def test_non_finite_gradients_skip_the_update():
     lin = torch.nn.Linear(1000, 37).to(DEV)
     flat = FlatParams(lin)

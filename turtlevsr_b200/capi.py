@@ -61,6 +61,9 @@ _SIGS = {
     "turtle_ln2d_bwd_workspace": ([_i32, C.c_longlong], C.c_longlong),
     "turtle_ln2d_fwd": ([_fp, _i32, _fp, _fp, _fp, _fp, _fp, _i32, _i32, C.c_longlong, _fp], C.c_int),
     "turtle_ln2d_bwd": ([_fp, _fp, _i32, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i32, _i32, C.c_longlong, _fp], C.c_int),
+    "turtle_dwconv3x3_nchw": ([_fp, _i32, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _i32, _fp], C.c_int),
+    "turtle_dwconv3x3_nchw_wgrad_workspace": ([_i32, _i32, _i32, _i32], C.c_longlong),
+    "turtle_dwconv3x3_nchw_wgrad": ([_fp, _fp, _i32, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _fp], C.c_int),
     "turtle_grad_check_finite": ([_fp, _i64, _fp, _fp], C.c_int),
     "turtle_adamw_flat": ([_fp, _fp, _fp, _fp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _fp, _fp], C.c_int),
 }

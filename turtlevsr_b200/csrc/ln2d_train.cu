@@ -1,10 +1,10 @@
 // Channel LayerNorm of the training graph (WithBias_LayerNorm, T1:83-112) on NCHW maps: forward and backward as one
 // kernel each instead of the ~10 + ~20 ATen launches of the reference's mean / var / sqrt / div / mul / add chain
-// (98 LayerNorms per frame, 10 frames per training step).  A thread owns one pixel and walks the channels with stride
+// (98 LayerNorms per frame, 10 frames per training step).  A lane owns one pixel and walks every 8th channel with stride
 // H*W, so every load and store of a warp is a contiguous 128-byte (fp32) or 64-byte (fp16 / bf16) row segment.
 //   forward : Welford over C  ->  y = (x - mean) * rstd * w + b  (fp32 out, as autocast leaves it), mean / rstd saved
 //   backward: g = dy * w; dx = rstd * (g - mean_c(g) - xhat * mean_c(g * xhat)); per-block partial sums of dy * xhat and dy
-//             per channel (warp shuffles -> fixed-order combine in shared memory), reduced over blocks by a second kernel
+//             per channel (warp shuffles over the block's 32 pixels), reduced over blocks by a second kernel
 //             in a fixed order: the weight / bias gradients are run-to-run deterministic.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -13,8 +13,9 @@
 
 namespace {
 
-constexpr int LT = 256;                 // threads (= pixels) per block
-constexpr int LW = LT / 32;
+constexpr int LP = 32;                  // pixels per block (one per lane)
+constexpr int LG = 8;                   // channel groups per block (one per warp): channel c belongs to warp c % LG
+constexpr int LT = LP * LG;
 
 template <int DT> struct Elem;
 template <> struct Elem<0> { using T = float; };
@@ -27,27 +28,46 @@ __device__ __forceinline__ void stf(float *p, float v) { *p = v; }
 __device__ __forceinline__ void stf(__half *p, float v) { *p = __float2half_rn(v); }
 __device__ __forceinline__ void stf(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
 
+// Block = 32 consecutive pixels (lanes) x 8 channel groups (warps): every load / store of a warp is one contiguous
+// row segment, a thread walks only C/8 channels, and even the 32x32 latent map of a 256x256 crop fills 64 CTAs.
 template <int DT>
 __global__ void __launch_bounds__(LT) ln2d_fwd_kernel(const void *__restrict__ xv, const float *__restrict__ w,
                                                       const float *__restrict__ b, float *__restrict__ y,
                                                       float *__restrict__ mean_out, float *__restrict__ rstd_out,
                                                       int C, int64_t HW, int64_t NP) {
     using T = typename Elem<DT>::T;
+    __shared__ float sm_mean[LG][LP], sm_m2[LG][LP], sm_n[LG][LP];
     const T *x = reinterpret_cast<const T *>(xv);
-    const int64_t pix = blockIdx.x * (int64_t)LT + threadIdx.x;
-    if (pix >= NP) return;
-    const int64_t base = (pix / HW) * C * HW + (pix % HW);
-    float mean = 0.f, m2 = 0.f;
-    for (int c = 0; c < C; ++c) {                      // Welford
-        const float v = ldf(x + base + c * HW);
-        const float d = v - mean;
-        mean += __fdividef(d, (float)(c + 1));
-        m2 = fmaf(d, v - mean, m2);
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int64_t pix = blockIdx.x * (int64_t)LP + lane;
+    const bool live = pix < NP;
+    const int64_t base = live ? (pix / HW) * C * HW + (pix % HW) : 0;
+    float mean = 0.f, m2 = 0.f, n = 0.f;
+    if (live)
+        for (int c = grp; c < C; c += LG) {            // Welford over this warp's channels
+            const float v = ldf(x + base + c * HW);
+            const float d = v - mean;
+            n += 1.0f;
+            mean += __fdividef(d, n);
+            m2 = fmaf(d, v - mean, m2);
+        }
+    sm_mean[grp][lane] = mean, sm_m2[grp][lane] = m2, sm_n[grp][lane] = n;
+    __syncthreads();
+    mean = sm_mean[0][lane], m2 = sm_m2[0][lane], n = sm_n[0][lane];
+#pragma unroll
+    for (int g = 1; g < LG; ++g) {                     // Chan's merge, fixed order
+        const float nb = sm_n[g][lane];
+        if (nb > 0.f) {
+            const float tot = n + nb, delta = sm_mean[g][lane] - mean;
+            mean += delta * (nb / tot);
+            m2 += sm_m2[g][lane] + delta * delta * (n * nb / tot);
+            n = tot;
+        }
     }
+    if (!live) return;
     const float rstd = rsqrtf(m2 / (float)C + 1e-5f);
-    mean_out[pix] = mean;
-    rstd_out[pix] = rstd;
-    for (int c = 0; c < C; ++c) {
+    if (grp == 0) mean_out[pix] = mean, rstd_out[pix] = rstd;
+    for (int c = grp; c < C; c += LG) {
         const float v = ldf(x + base + c * HW);
         y[base + c * HW] = fmaf((v - mean) * rstd, __ldg(w + c), __ldg(b + c));
     }
@@ -59,40 +79,39 @@ __global__ void __launch_bounds__(LT) ln2d_bwd_kernel(const float *__restrict__ 
                                                       const float *__restrict__ rstd_in, void *__restrict__ dxv,
                                                       float *__restrict__ part, int C, int64_t HW, int64_t NP) {
     using T = typename Elem<DT>::T;
-    extern __shared__ float sm[];                      // [LW][C][2]: per-warp sums of (dy * xhat, dy) per channel
+    __shared__ float sm1[LG][LP], sm2[LG][LP];
     const T *x = reinterpret_cast<const T *>(xv);
     T *dx = reinterpret_cast<T *>(dxv);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int64_t pix = blockIdx.x * (int64_t)LT + tid;
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+    const int64_t pix = blockIdx.x * (int64_t)LP + lane;
     const bool live = pix < NP;
     const int64_t base = live ? (pix / HW) * C * HW + (pix % HW) : 0;
     const float mean = live ? mean_in[pix] : 0.f, rstd = live ? rstd_in[pix] : 0.f;
     float s1 = 0.f, s2 = 0.f;
-    for (int c = 0; c < C; ++c) {
-        const float g = live ? dy[base + c * HW] * __ldg(w + c) : 0.f;
-        const float xh = live ? (ldf(x + base + c * HW) - mean) * rstd : 0.f;
-        s1 += g;
-        s2 = fmaf(g, xh, s2);
-    }
+    if (live)
+        for (int c = grp; c < C; c += LG) {
+            const float g = dy[base + c * HW] * __ldg(w + c);
+            const float xh = (ldf(x + base + c * HW) - mean) * rstd;
+            s1 += g;
+            s2 = fmaf(g, xh, s2);
+        }
+    sm1[grp][lane] = s1, sm2[grp][lane] = s2;
+    __syncthreads();
+    s1 = s2 = 0.f;
+#pragma unroll
+    for (int g = 0; g < LG; ++g) s1 += sm1[g][lane], s2 += sm2[g][lane];
     const float inv_c = 1.0f / (float)C;
     s1 *= inv_c;
     s2 *= inv_c;
-    for (int c = 0; c < C; ++c) {
+    for (int c = grp; c < C; c += LG) {                // (warp-uniform trip count: the shuffles below are convergent)
         const float d = live ? dy[base + c * HW] : 0.f;
         const float xh = live ? (ldf(x + base + c * HW) - mean) * rstd : 0.f;
         if (live) stf(dx + base + c * HW, rstd * (d * __ldg(w + c) - s1 - xh * s2));
         const float a = warp_sum(d * xh), bsum = warp_sum(d);
-        if (lane == 0) {
-            sm[(warp * C + c) * 2] = a;
-            sm[(warp * C + c) * 2 + 1] = bsum;
+        if (lane == 0) {                               // this warp alone owns channel c of the block
+            part[((int64_t)blockIdx.x * C + c) * 2] = a;
+            part[((int64_t)blockIdx.x * C + c) * 2 + 1] = bsum;
         }
-    }
-    __syncthreads();
-    for (int i = tid; i < 2 * C; i += LT) {            // fixed-order combine of the warps
-        float t = 0.f;
-#pragma unroll
-        for (int wv = 0; wv < LW; ++wv) t += sm[wv * C * 2 + i];
-        part[(int64_t)blockIdx.x * 2 * C + i] = t;
     }
 }
 
@@ -111,14 +130,14 @@ __global__ void __launch_bounds__(256) ln2d_reduce_kernel(const float *__restric
 
 extern "C" long long turtle_ln2d_bwd_workspace(int C, long long n_pixels) {
     if (C < 1 || n_pixels < 1) return -1;
-    return (long long)cdiv64(n_pixels, LT) * 2 * C * (long long)sizeof(float);
+    return (long long)cdiv64(n_pixels, LP) * 2 * C * (long long)sizeof(float);
 }
 
 extern "C" int turtle_ln2d_fwd(const void *x, int x_dtype, const float *w, const float *b, float *y, float *mean,
                                float *rstd, int B, int C, long long HW, void *stream) {
     if (!x || !w || !b || !y || !mean || !rstd || B < 1 || C < 1 || HW < 1 || x_dtype < 0 || x_dtype > 2) return TURTLE_EINVAL;
     const int64_t NP = (int64_t)B * HW;
-    const unsigned grid = (unsigned)cdiv64(NP, LT);
+    const unsigned grid = (unsigned)cdiv64(NP, LP);
     cudaStream_t s = as_stream(stream);
     if (x_dtype == 0) ln2d_fwd_kernel<0><<<grid, LT, 0, s>>>(x, w, b, y, mean, rstd, C, HW, NP);
     else if (x_dtype == 1) ln2d_fwd_kernel<1><<<grid, LT, 0, s>>>(x, w, b, y, mean, rstd, C, HW, NP);
@@ -133,15 +152,13 @@ extern "C" int turtle_ln2d_bwd(const float *dy, const void *x, int x_dtype, cons
     if (!dy || !x || !w || !mean || !rstd || !dx || !dw || !db || !workspace || B < 1 || C < 1 || HW < 1 || x_dtype < 0 ||
         x_dtype > 2)
         return TURTLE_EINVAL;
-    const size_t smem = (size_t)LW * C * 2 * sizeof(float);
-    if (smem > 48 * 1024) return TURTLE_ENOTSUP;       // C <= 768
     const int64_t NP = (int64_t)B * HW;
-    const unsigned grid = (unsigned)cdiv64(NP, LT);
+    const unsigned grid = (unsigned)cdiv64(NP, LP);
     float *part = reinterpret_cast<float *>(workspace);
     cudaStream_t s = as_stream(stream);
-    if (x_dtype == 0) ln2d_bwd_kernel<0><<<grid, LT, smem, s>>>(dy, x, w, mean, rstd, dx, part, C, HW, NP);
-    else if (x_dtype == 1) ln2d_bwd_kernel<1><<<grid, LT, smem, s>>>(dy, x, w, mean, rstd, dx, part, C, HW, NP);
-    else ln2d_bwd_kernel<2><<<grid, LT, smem, s>>>(dy, x, w, mean, rstd, dx, part, C, HW, NP);
+    if (x_dtype == 0) ln2d_bwd_kernel<0><<<grid, LT, 0, s>>>(dy, x, w, mean, rstd, dx, part, C, HW, NP);
+    else if (x_dtype == 1) ln2d_bwd_kernel<1><<<grid, LT, 0, s>>>(dy, x, w, mean, rstd, dx, part, C, HW, NP);
+    else ln2d_bwd_kernel<2><<<grid, LT, 0, s>>>(dy, x, w, mean, rstd, dx, part, C, HW, NP);
     TURTLE_CHECK_LAUNCH();
     ln2d_reduce_kernel<<<(unsigned)cdiv64((int64_t)2 * C * 32, 256), 256, 0, s>>>(part, (int)grid, C, dw, db);
     TURTLE_CHECK_LAUNCH();

@@ -5,8 +5,8 @@ backward pass, and the optimizer as two passes over ONE flat fp32 buffer on hand
 What runs where (stated plainly):
 
 * forward + backward: ``autograd_forward`` below -- the same arch tree evaluated with differentiable torch ops
-  (cuDNN / cuBLAS / ATen library kernels on the GPU, except the channel LayerNorm, whose forward and backward are the
-  hand-written ``turtle_ln2d_fwd`` / ``turtle_ln2d_bwd`` kernels of csrc/ln2d_train.cu; BPTT through the history caches exactly as the reference does it,
+  (cuDNN / cuBLAS / ATen library kernels on the GPU, except the channel LayerNorm and the depthwise 3x3 convs, whose
+  forward and backward are hand-written: csrc/ln2d_train.cu, csrc/dwconv_train.cu; BPTT through the history caches exactly as the reference does it,
   the caches stay attached to the graph across the frames of a clip).  The hand-written inference kernels have no
   backward yet (SURVEY 8f rank 2), so ``TurtleNet.forward`` routes here when ``training and grad enabled``;
 * gradient exchange: ``GradBuckets`` -- every ``.grad`` is a view of one flat buffer cut into ~32 MB buckets in reverse
@@ -69,9 +69,59 @@ class _ChannelLayerNorm(torch.autograd.Function):
         return dx, dw, db
 
 
+class _Depthwise3x3(torch.autograd.Function):
+    """nn.Conv2d(C, C, 3, 1, 1, groups=C) on turtle_dwconv3x3_nchw / _wgrad: forward, input gradient and weight / bias
+    gradient as one launch each (+ a tiny fixed-order reduction) instead of ATen's three depthwise kernels."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        from . import capi
+        x = x.contiguous()
+        B, C, H, W = x.shape
+        w9 = w.detach().float().reshape(C, 9).contiguous()
+        bf = None if b is None else b.detach().float().contiguous()
+        y = torch.empty_like(x)
+        capi.call("turtle_dwconv3x3_nchw", x.data_ptr(), _LN_DTYPES[x.dtype], w9.data_ptr(),
+                  None if bf is None else bf.data_ptr(), y.data_ptr(), B, C, H, W, 0,
+                  torch.cuda.current_stream(x.device).cuda_stream)
+        ctx.save_for_backward(x, w9)
+        ctx.has_bias = b is not None
+        ctx.w_shape = w.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import capi
+        x, w9 = ctx.saved_tensors
+        B, C, H, W = x.shape
+        dy = dy.to(x.dtype).contiguous()
+        st = torch.cuda.current_stream(x.device).cuda_stream
+        dx = torch.empty_like(x)
+        capi.call("turtle_dwconv3x3_nchw", dy.data_ptr(), _LN_DTYPES[x.dtype], w9.data_ptr(), None, dx.data_ptr(),
+                  B, C, H, W, 1, st)
+        dw9 = torch.empty(C, 9, device=x.device, dtype=torch.float32)
+        db = torch.empty(C, device=x.device, dtype=torch.float32) if ctx.has_bias else None
+        nbytes = capi.load().turtle_dwconv3x3_nchw_wgrad_workspace(B, C, H, W)
+        wsp = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32)
+        capi.call("turtle_dwconv3x3_nchw_wgrad", x.data_ptr(), dy.data_ptr(), _LN_DTYPES[x.dtype], dw9.data_ptr(),
+                  None if db is None else db.data_ptr(), wsp.data_ptr(), B, C, H, W, st)
+        return dx, dw9.view(ctx.w_shape), db
+
+
+def _dw(conv, x: Tensor) -> Tensor:
+    """A depthwise conv module of the arch tree: the hand-written kernels for the 3x3 / stride 1 / pad 1 case on CUDA."""
+    if (x.is_cuda and x.dtype in _LN_DTYPES and conv.kernel_size == (3, 3) and conv.stride == (1, 1)
+            and conv.padding == (1, 1) and conv.groups == conv.in_channels == conv.out_channels
+            and x.shape[0] * x.shape[1] <= 65535):
+        if torch.is_autocast_enabled("cuda"):                    # what autocast would do to conv2d's input
+            x = x.to(torch.get_autocast_dtype("cuda"))
+        return _Depthwise3x3.apply(x, conv.weight, conv.bias)
+    return conv(x)
+
+
 def _layernorm(norm, x: Tensor) -> Tensor:                      # T1:83-112
     b = getattr(norm.body, "bias", None)
-    if x.is_cuda and b is not None and x.dtype in _LN_DTYPES and x.shape[1] <= 768:
+    if x.is_cuda and b is not None and x.dtype in _LN_DTYPES:
         return _ChannelLayerNorm.apply(x, norm.body.weight, b)
     # BiasFree variant (unused by the shipped ymls) and the CPU host-logic tests: the reference's formula on torch ops
     w = norm.body.weight.view(1, -1, 1, 1)
@@ -128,7 +178,7 @@ def _clipped_softmax(z: Tensor) -> Tensor:                      # T1:115-132
 
 
 def _gated_ffw(m, x):                                           # T1:173-178
-    a, g = m.dwconv(m.project_in(x)).chunk(2, dim=1)
+    a, g = _dw(m.dwconv, m.project_in(x)).chunk(2, dim=1)
     return m.project_out(F.gelu(a) * g)
 
 
@@ -137,13 +187,13 @@ def _plain_ffw(m, x):                                           # T1:204-210
 
 
 def _reduced_attn(m, x):                                        # T1:736-742
-    return m.conv3(F.gelu(m.conv2(m.conv1(x)))) * m.beta
+    return m.conv3(F.gelu(_dw(m.conv2, m.conv1(x)))) * m.beta
 
 
 def _channel_attn(m, x, k_hist=None, v_hist=None, keep_frames=None):   # T1:680-702, 243-286
     b, c, h, w = x.shape
     hd = m.num_heads
-    q, k, v = (t.reshape(b, hd, c // hd, h * w) for t in m.qkv_dwconv(m.qkv(x)).chunk(3, dim=1))
+    q, k, v = (t.reshape(b, hd, c // hd, h * w) for t in _dw(m.qkv_dwconv, m.qkv(x)).chunk(3, dim=1))
     q, k = _unit_rows(q), _unit_rows(k)
     if k_hist is not None and v_hist is not None:
         k, v = torch.cat([k_hist, k], dim=2), torch.cat([v_hist, v], dim=2)
@@ -160,8 +210,8 @@ def _state_align(m, x, variant, k_hist, v_hist):                # T1:548-610 / T
     ws, keep = m.window_size, m.num_frames_tocache
     t0 = variant == "t0"
     x_qk = x + _posenc(c, h, w, x.device, x.dtype) if t0 else x
-    q, k = m.qk_dwconv(m.qk(x_qk)).chunk(2, dim=1)
-    v = _patches(m.v_dwconv(m.v(x)), ws)[:, None, None]          # b 1 1 N ws*ws*c
+    q, k = _dw(m.qk_dwconv, m.qk(x_qk)).chunk(2, dim=1)
+    v = _patches(_dw(m.v_dwconv, m.v(x)), ws)[:, None, None]          # b 1 1 N ws*ws*c
     if t0:
         q, k = _patches(q, ws), _patches(k, ws)
     else:
@@ -188,7 +238,7 @@ def _causal_history(m, x, variant, k_hist, v_hist):             # T1:627-662
     hd = m.num_heads
     xs, k_new, v_new = _state_align(m.spatial_aligner, x, variant, k_hist, v_hist)
     nf = xs.shape[1]
-    k, v = m.kv_dwconv(m.kv(xs.reshape(b * nf, c, h, w))).chunk(2, dim=1)
+    k, v = _dw(m.kv_dwconv, m.kv(xs.reshape(b * nf, c, h, w))).chunk(2, dim=1)
 
     def rows(t):                                                 # '(b f) (head c) h w -> b head (f c) (h w)'
         return t.reshape(b, nf, hd, c // hd, h * w).permute(0, 2, 1, 3, 4).reshape(b, hd, nf * (c // hd), h * w)
