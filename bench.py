@@ -152,7 +152,8 @@ def train_arm(args, rank, world, local_rank, dev, dist, barrier):
     opt = shipped("Turtle_Derain")
     torch.manual_seed(opt["manual_seed"])
     net = create_video_model(opt).to(dev)
-    ts = TrainStep(net, dict(type="Adam", lr=4e-4, weight_decay=0, betas=[0.9, 0.99]), amp="fp16")
+    ts = TrainStep(net, dict(type="Adam", lr=4e-4, weight_decay=0, betas=[0.9, 0.99]), amp="fp16",
+                   cuda_graph=not args.no_graphs)
     g = torch.Generator().manual_seed(2000 + rank)
     B, T, S = 2, 5, 256
     lq_h = torch.rand(B, T, 3, S, S, generator=g).pin_memory()
@@ -163,7 +164,7 @@ def train_arm(args, rank, world, local_rank, dev, dist, barrier):
         lq, gt = lq_h.to(dev, non_blocking=True), gt_h.to(dev, non_blocking=True)
         return ts.step(lq, gt).item()
 
-    for _ in range(Wm):
+    for _ in range(Wm + (TrainStep.GRAPH_WARMUP + 1 if ts.cuda_graph else 0)):     # eager steps, then the capture
         one()
     barrier()
     n0 = capi.launch_count
@@ -203,7 +204,9 @@ def train_arm(args, rank, world, local_rank, dev, dist, barrier):
                                        "256x256, L1, AdamW lr 4e-4",
                            "parallelism": f"data parallel x{world}, bucketed NCCL all-reduce of "
                                           f"{4 * ts.flat.numel / 1e6:.1f} MB of fp32 gradients per step",
-                           "forward_backward": "library autograd graph (cuDNN/cuBLAS); optimizer on libturtle_b200"},
+                           "forward_backward": "autograd graph: cuDNN/cuBLAS/ATen convs and matmuls, hand-written LayerNorm "
+                                               "and depthwise 3x3 forward/backward; optimizer on libturtle_b200",
+                           "launch": "forward+backward replayed from one CUDA graph" if ts.cuda_graph else "eager"},
                 "clocks": clk.summary(), "loss": loss, "skipped_steps": ts.skipped_steps,
                 "e2e": {"value": world * K * B * T / (ms * 1e-3), "unit": "frames/s",
                         "h2d_bytes_per_step": 2 * lq_h.numel() * 4, "d2h_bytes_per_step": 4},

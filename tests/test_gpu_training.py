@@ -147,6 +147,27 @@ def test_two_training_steps_match_reference(case):
     assert worst <= 5e-6, worst
 
 
+def test_graph_replayed_steps_match_eager_steps():
+    """TrainStep(cuda_graph=True): forward+backward replayed from one CUDA graph == the eager step, step by step."""
+    nets = []
+    for _ in range(2):
+        net, lq, gt, _ = load_train_case("train_tiny_t1.npz")
+        nets.append(net.to(DEV))
+    lq, gt = lq.to(DEV), gt.to(DEV)
+    eager, graphed = TrainStep(nets[0], OPTIM), TrainStep(nets[1], OPTIM, cuda_graph=True)
+    g = torch.Generator(device=DEV).manual_seed(3)
+    for i in range(TrainStep.GRAPH_WARMUP + 3):
+        a = torch.rand(lq.shape, device=DEV, generator=g)
+        b = torch.rand(gt.shape, device=DEV, generator=g)
+        le, lg = eager.step(a, b).item(), graphed.step(a, b).item()
+        assert abs(le - lg) < 1e-6, i
+    assert graphed._graph is not None and eager._graph is None
+    # same kernels, but cuDNN may pick another algorithm under capture: gradients agree to rounding, and Adam turns a
+    # rounding-level gradient difference on a near-zero gradient into a fraction of its lr = 4e-4 step
+    for (n, p), (_, q) in zip(nets[0].named_parameters(), nets[1].named_parameters()):
+        assert (p - q).abs().max().item() < 5e-5, n
+
+
 def test_autocast_steps_loss_scaler_and_eval_after_training():
     net, lq, gt, z = load_train_case("train_tiny_t1.npz")
     net = net.to(DEV)

@@ -150,7 +150,17 @@ def _unpatch(o: Tensor, ws: int, d: int, h: int, w: int) -> Tensor:
     return o.reshape(b, f, gh, gw, ws, ws, d).permute(0, 1, 6, 4, 2, 5, 3).reshape(b, f, d, h, w)
 
 
+_POSENC_CACHE: dict = {}
+
+
 def _posenc(c: int, h: int, w: int, device, dtype) -> Tensor:   # T0:412-439
+    key = (c, h, w, str(device), dtype)
+    if key not in _POSENC_CACHE:        # built on the host once (also keeps the H2D copy out of CUDA-graph captures)
+        _POSENC_CACHE[key] = _posenc_build(c, h, w, device, dtype)
+    return _POSENC_CACHE[key]
+
+
+def _posenc_build(c: int, h: int, w: int, device, dtype) -> Tensor:
     if c % 4 != 0:
         raise ValueError("Cannot use sin/cos positional encoding with odd dimension (got dim={:d})".format(c))
     half = c // 2
@@ -392,12 +402,15 @@ class GradBuckets:
         self.launched = [False] * len(self.ranges)
         self.works = []
         self.bytes_reduced = 0
+        self.defer = False           # True: the hooks stay silent and finish() launches every bucket (graph replay)
         if self.world > 1:
             for i, p in enumerate(flat.params):
                 p.register_post_accumulate_grad_hook(self._make_hook(i))
 
     def _make_hook(self, i):
         def hook(_p):
+            if self.defer:
+                return
             b = self.bucket_of[i]
             self.pending[b] -= 1
             if self.pending[b] == 0:
@@ -484,7 +497,7 @@ class TrainStep:
     or "bf16" (autocast, no scaler)."""
 
     def __init__(self, net, optim: Optional[dict] = None, amp: Optional[str] = None, group=None,
-                 bucket_bytes: int = 32 << 20):
+                 bucket_bytes: int = 32 << 20, cuda_graph: bool = False):
         if amp not in (None, "fp16", "bf16"):
             raise ValueError(amp)
         optim = dict(optim or {})
@@ -496,6 +509,13 @@ class TrainStep:
         self.amp = amp
         self.scaler = LossScaler() if amp == "fp16" else None
         self.skipped_steps = 0
+        # cuda_graph: after GRAPH_WARMUP eager steps the forward + backward of a step (several thousand launches issued
+        # from Python; the step is bound by the host's launch rate) is captured once for the batch shape and replayed;
+        # the gradient all-reduce and the optimizer stay outside the graph (the loss scale enters as a device scalar).
+        self.cuda_graph = bool(cuda_graph)
+        self._graph = None
+        self._eager_steps = 0
+        self._scale_t = torch.ones((), device=self.flat.data.device)
 
     def loss_of_clip(self, lq: Tensor, gt: Tensor) -> Tensor:
         dev = lq.device.type
@@ -511,11 +531,42 @@ class TrainStep:
                 total = total + F.l1_loss(out.float(), gt[:, j])
         return total / n
 
+    GRAPH_WARMUP = 3
+
+    def _replay(self, lq: Tensor, gt: Tensor) -> Tensor:
+        if self._graph is None or self._g_lq.shape != lq.shape or self._g_lq.dtype != lq.dtype:
+            self._g_lq, self._g_gt = lq.clone(), gt.clone()
+            self.buckets.defer = True
+            from . import capi
+            n0 = capi.launch_count
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.flat.grad.zero_()
+                loss = self.loss_of_clip(self._g_lq, self._g_gt)
+                (loss * self._scale_t).backward()
+                self._g_loss = loss.detach()
+            self._graph = g
+            self._g_launches = capi.launch_count - n0          # our LayerNorm / depthwise launches inside the graph
+            capi.launch_count = n0
+        from . import capi
+        self._g_lq.copy_(lq)
+        self._g_gt.copy_(gt)
+        self._graph.replay()
+        capi.launch_count += self._g_launches
+        return self._g_loss.clone()
+
     def step(self, lq: Tensor, gt: Tensor) -> Tensor:
-        self.flat.zero_grad()
-        loss = self.loss_of_clip(lq, gt)
         scale = self.scaler.scale if self.scaler else 1.0
-        (loss * scale).backward()                                # bucket all-reduces start from the grad hooks
+        if self.cuda_graph and lq.is_cuda and self._eager_steps >= self.GRAPH_WARMUP:
+            self._scale_t.fill_(scale)
+            loss = self._replay(lq, gt)
+        else:
+            self._eager_steps += 1
+            self.buckets.defer = False
+            self.flat.zero_grad()
+            loss = self.loss_of_clip(lq, gt)
+            (loss * scale).backward()                            # bucket all-reduces start from the grad hooks
+            loss = loss.detach()
         self.buckets.finish()
         self.opt.step(grad_scale=self.buckets.scale / scale, check_finite=self.scaler is not None)
         if self.scaler is not None:
@@ -524,4 +575,4 @@ class TrainStep:
             self.scaler.update(found)
             self.skipped_steps += int(found)
         self.net.invalidate_packed_weights()                     # the inference engine repacks lazily
-        return loss.detach()
+        return loss
