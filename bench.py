@@ -37,6 +37,29 @@ METRIC = "frames/sec at 1280x720"
 WORKLOAD = "Turtle_Deblur_Gopro.yml (Turtle_t1, random init seed 10), synthetic 1280x720 clip, B=1"
 
 
+# The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout when the
+# box sets NCCL_DEBUG), so file descriptor 1 is pointed at stderr for the duration of the run and the JSON line goes to
+# the saved original.
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -215,7 +238,7 @@ def train_arm(args, rank, world, local_rank, dev, dist, barrier):
                              "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
                              "traffic": None, "kernel_ms_per_step": opt_ms,
                              "algorithmic_per_launch": by / 2}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
@@ -236,6 +259,7 @@ def main():
                     help="infer = the BASELINE metric (default); train = cfg 5's DDP training step (secondary line)")
     args = ap.parse_args()
 
+    _claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -252,7 +276,7 @@ def main():
                 "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     if not torch.cuda.is_available():
@@ -399,7 +423,7 @@ def main():
             "roofline": roof,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
