@@ -939,7 +939,8 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
     // measured per shape (profile_shapes A/B): pairs win where the weight slab dominates the feed (NG = 256: 256->1280,
     // 256->768, 512->2560, 1280->512, the 3x3 up-convs: -5..-10 %), lose a few % on narrow n-groups and on the two-pass LN
     // epilogue, whose longer accumulator hold now stalls two SMs
-    const bool pair = !no_pair && p.nkb >= pair_min_kb && NG == 256 && !a->ln_out && tiles >= 8;
+    static const bool pair_ln = getenv("TURTLE_GEMM_PAIR_LN") != nullptr;      // A/B knob: CTA pairs for the fused-LN GEMMs too
+    const bool pair = !no_pair && p.nkb >= pair_min_kb && NG == 256 && (!a->ln_out || pair_ln) && tiles >= 8;
     {
         uint64_t dims[2] = {(uint64_t)K, (uint64_t)Cout};
         uint64_t str[1] = {(uint64_t)K * es};
