@@ -19,8 +19,13 @@ for _ in range(3):
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     ts.step(lq, gt); torch.cuda.synchronize()
-ka = prof.key_averages()
-tot = sum(e.device_time_total for e in ka) / 1e3
-print(f"sum of device kernel time {tot:.1f} ms")
-for e in sorted(ka, key=lambda e: -e.device_time_total)[:14]:
-    print(f"  {e.key[:70]:70s} {e.device_time_total/1e3:8.2f} ms  x{e.count}")
+evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+agg = {}
+for e in evs:
+    d = agg.setdefault(e.name, [0.0, 0])
+    d[0] += e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total
+    d[1] += 1
+tot = sum(v[0] for v in agg.values()) / 1e3
+print(f"sum of device kernel time {tot:.1f} ms over {sum(v[1] for v in agg.values())} kernels")
+for name, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:28]:
+    print(f"  {name[:86]:86s} {t/1e3:8.2f} ms  x{n}")
