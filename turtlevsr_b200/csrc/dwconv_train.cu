@@ -1,7 +1,7 @@
 // Depthwise 3x3 (stride 1, zero pad 1) of the TRAINING graph on NCHW maps: forward, input gradient and weight / bias
 // gradient.  In the cfg-5 step the three ATen depthwise kernels (conv_depthwise2d_forward / _backward / _grad_weight)
-// were 197 of 492 ms; every (image, channel) plane is independent, so a block stages a 32x32 tile of one plane with its
-// halo in shared memory once and every tap is then a conflict-free shared-memory read.
+// were 197 of 492 ms; every (image, channel) plane is independent, so a block stages a 32x32 or 32x64 tile of one plane
+// with its halo in shared memory once; a thread then walks 4 or 8 output rows of its column with a sliding 3-row window.
 //   forward      y  = sum_t w[c,t] * x[.., h+dy, w+dx] (+ bias[c])                      (x's dtype in and out)
 //   input grad   dx = the same kernel on dy with the taps flipped, no bias
 //   weight grad  dw[c,t] = sum_{b,h,w} dy * x[.., h+dy, w+dx],  db[c] = sum dy: per-tile partial sums (warp shuffles,
@@ -13,9 +13,9 @@
 
 namespace {
 
-constexpr int TS = 32;                  // tile edge
+constexpr int TS = 32;                  // tile width (one column per lane)
 constexpr int HS = TS + 2;              // with halo
-constexpr int NT = 256;                 // 32 x 8 threads, 4 output rows each
+constexpr int NT = 256;                 // 32 x 8 threads; a thread owns TH/8 consecutive output rows of its column
 
 template <int DT> struct El;
 template <> struct El<0> { using T = float; };
@@ -28,26 +28,35 @@ __device__ __forceinline__ void stv(float *p, float v) { *p = v; }
 __device__ __forceinline__ void stv(__half *p, float v) { *p = __float2half_rn(v); }
 __device__ __forceinline__ void stv(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
 
-template <typename T>
-__device__ __forceinline__ void load_halo(float (&t)[HS][HS + 1], const T *plane, int ty0, int tx0, int H, int W) {
-    for (int i = threadIdx.x; i < HS * HS; i += NT) {
-        const int r = i / HS, q = i - r * HS;
-        const int gy = ty0 + r - 1, gx = tx0 + q - 1;
-        t[r][q] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? ldv(plane + (int64_t)gy * W + gx) : 0.f;
+// halo tile (TH+2) x 34 of one plane: warp w stages rows w, w+8, ...; lanes walk the columns, so a row is two
+// coalesced segments and there is no index arithmetic beyond the bounds tests
+template <int TH, typename T>
+__device__ __forceinline__ void load_halo(float (&t)[TH + 2][HS + 1], const T *plane, int ty0, int tx0, int H, int W) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = warp; r < TH + 2; r += NT / 32) {
+        const int gy = ty0 + r - 1;
+        const bool rowok = gy >= 0 && gy < H;
+        const T *row = plane + (int64_t)gy * W + (tx0 - 1);
+#pragma unroll
+        for (int q = lane; q < HS; q += 32) {
+            const int gx = tx0 + q - 1;
+            t[r][q] = (rowok && gx >= 0 && gx < W) ? ldv(row + q) : 0.f;
+        }
     }
 }
 
-template <int DT>
+template <int DT, int TH>
 __global__ void __launch_bounds__(NT) dw3_apply_kernel(const void *__restrict__ xv, const float *__restrict__ w9,
                                                        const float *__restrict__ bias, void *__restrict__ yv, int C,
                                                        int H, int W, int tiles_x, int flip) {
     using T = typename El<DT>::T;
-    __shared__ float t[HS][HS + 1];
+    constexpr int RPT = TH / 8;
+    __shared__ float t[TH + 2][HS + 1];
     const int plane = blockIdx.y, c = plane % C;
-    const int ty0 = (blockIdx.x / tiles_x) * TS, tx0 = (blockIdx.x % tiles_x) * TS;
+    const int ty0 = (blockIdx.x / tiles_x) * TH, tx0 = (blockIdx.x % tiles_x) * TS;
     const T *x = reinterpret_cast<const T *>(xv) + (int64_t)plane * H * W;
     T *y = reinterpret_cast<T *>(yv) + (int64_t)plane * H * W;
-    load_halo(t, x, ty0, tx0, H, W);
+    load_halo<TH>(t, x, ty0, tx0, H, W);
     float k[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) k[i] = __ldg(w9 + c * 9 + (flip ? 8 - i : i));
@@ -56,47 +65,70 @@ __global__ void __launch_bounds__(NT) dw3_apply_kernel(const void *__restrict__ 
     const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
     const int gx = tx0 + lx;
     if (gx >= W) return;
+    const int oy0 = ly * RPT;
+    float r0[3], r1[3], r2[3];                 // sliding 3-row window of the column's neighbourhood
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int oy = ly * 4 + i, gy = ty0 + oy;
-        if (gy >= H) break;
+    for (int kx = 0; kx < 3; ++kx) r0[kx] = t[oy0][lx + kx], r1[kx] = t[oy0 + 1][lx + kx];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const int gy = ty0 + oy0 + i;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) r2[kx] = t[oy0 + i + 2][lx + kx];
         float a = b0;
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+        for (int kx = 0; kx < 3; ++kx) {
+            a = fmaf(k[kx], r0[kx], a);
+            a = fmaf(k[3 + kx], r1[kx], a);
+            a = fmaf(k[6 + kx], r2[kx], a);
+        }
+        if (gy < H) stv(y + (int64_t)gy * W + gx, a);
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) a = fmaf(k[ky * 3 + kx], t[oy + ky][lx + kx], a);
-        stv(y + (int64_t)gy * W + gx, a);
+        for (int kx = 0; kx < 3; ++kx) r0[kx] = r1[kx], r1[kx] = r2[kx];
     }
 }
 
-template <int DT>
+template <int DT, int TH>
 __global__ void __launch_bounds__(NT) dw3_wgrad_kernel(const void *__restrict__ xv, const void *__restrict__ dyv,
                                                        float *__restrict__ part, int C, int H, int W, int tiles_x,
                                                        int tiles) {
     using T = typename El<DT>::T;
-    __shared__ float t[HS][HS + 1];
+    constexpr int RPT = TH / 8;
+    __shared__ float t[TH + 2][HS + 1];
     __shared__ float red[NT / 32][10];
     const int c = blockIdx.y, img = blockIdx.x / tiles, tile = blockIdx.x - img * tiles;
-    const int ty0 = (tile / tiles_x) * TS, tx0 = (tile % tiles_x) * TS;
+    const int ty0 = (tile / tiles_x) * TH, tx0 = (tile % tiles_x) * TS;
     const int64_t off = ((int64_t)img * C + c) * H * W;
     const T *x = reinterpret_cast<const T *>(xv) + off;
     const T *dy = reinterpret_cast<const T *>(dyv) + off;
-    load_halo(t, x, ty0, tx0, H, W);
-    __syncthreads();
     const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5, lane = lx, warp = ly;
-    const int gx = tx0 + lx;
+    const int gx = tx0 + lx, oy0 = ly * RPT;
+    float d[RPT];                              // this thread's dy values: requested before the halo barrier
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const int gy = ty0 + oy0 + i;
+        d[i] = (gx < W && gy < H) ? ldv(dy + (int64_t)gy * W + gx) : 0.f;
+    }
+    load_halo<TH>(t, x, ty0, tx0, H, W);
+    __syncthreads();
     float acc[10];
 #pragma unroll
     for (int i = 0; i < 10; ++i) acc[i] = 0.f;
+    float r0[3], r1[3], r2[3];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int oy = ly * 4 + i, gy = ty0 + oy;
-        const float d = (gx < W && gy < H) ? ldv(dy + (int64_t)gy * W + gx) : 0.f;
+    for (int kx = 0; kx < 3; ++kx) r0[kx] = t[oy0][lx + kx], r1[kx] = t[oy0 + 1][lx + kx];
 #pragma unroll
-        for (int ky = 0; ky < 3; ++ky)
+    for (int i = 0; i < RPT; ++i) {
 #pragma unroll
-            for (int kx = 0; kx < 3; ++kx) acc[ky * 3 + kx] = fmaf(d, t[oy + ky][lx + kx], acc[ky * 3 + kx]);
-        acc[9] += d;
+        for (int kx = 0; kx < 3; ++kx) r2[kx] = t[oy0 + i + 2][lx + kx];
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+            acc[kx] = fmaf(d[i], r0[kx], acc[kx]);
+            acc[3 + kx] = fmaf(d[i], r1[kx], acc[3 + kx]);
+            acc[6 + kx] = fmaf(d[i], r2[kx], acc[6 + kx]);
+        }
+        acc[9] += d[i];
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) r0[kx] = r1[kx], r1[kx] = r2[kx];
     }
 #pragma unroll
     for (int i = 0; i < 10; ++i) {
@@ -127,7 +159,8 @@ __global__ void __launch_bounds__(256) dw3_wgrad_reduce_kernel(const float *__re
     }
 }
 
-inline int tiles_of(int n) { return (n + TS - 1) / TS; }
+inline int tiles_of(int n, int t = TS) { return (n + t - 1) / t; }
+inline int tile_h(int H) { return H >= 64 ? 64 : 32; }
 
 }  // namespace
 
@@ -135,32 +168,44 @@ extern "C" int turtle_dwconv3x3_nchw(const void *x, int dtype, const float *w9, 
                                      int H, int W, int flip, void *stream) {
     if (!x || !w9 || !y || B < 1 || C < 1 || H < 1 || W < 1 || dtype < 0 || dtype > 2) return TURTLE_EINVAL;
     if ((int64_t)B * C > 65535) return TURTLE_ENOTSUP;
-    const int tx = tiles_of(W), ty = tiles_of(H);
+    const int th = tile_h(H), tx = tiles_of(W), ty = tiles_of(H, th);
     dim3 grid(tx * ty, B * C);
     cudaStream_t s = as_stream(stream);
-    if (dtype == 0) dw3_apply_kernel<0><<<grid, NT, 0, s>>>(x, w9, bias, y, C, H, W, tx, flip);
-    else if (dtype == 1) dw3_apply_kernel<1><<<grid, NT, 0, s>>>(x, w9, bias, y, C, H, W, tx, flip);
-    else dw3_apply_kernel<2><<<grid, NT, 0, s>>>(x, w9, bias, y, C, H, W, tx, flip);
+#define TURTLE_DW3_APPLY(DT)                                                                              \
+    do {                                                                                                  \
+        if (th == 64) dw3_apply_kernel<DT, 64><<<grid, NT, 0, s>>>(x, w9, bias, y, C, H, W, tx, flip);    \
+        else dw3_apply_kernel<DT, 32><<<grid, NT, 0, s>>>(x, w9, bias, y, C, H, W, tx, flip);             \
+    } while (0)
+    if (dtype == 0) TURTLE_DW3_APPLY(0);
+    else if (dtype == 1) TURTLE_DW3_APPLY(1);
+    else TURTLE_DW3_APPLY(2);
+#undef TURTLE_DW3_APPLY
     TURTLE_CHECK_LAUNCH();
     return TURTLE_OK;
 }
 
 extern "C" long long turtle_dwconv3x3_nchw_wgrad_workspace(int B, int C, int H, int W) {
     if (B < 1 || C < 1 || H < 1 || W < 1) return -1;
-    return (long long)C * B * tiles_of(W) * tiles_of(H) * 10 * (long long)sizeof(float);
+    return (long long)C * B * tiles_of(W) * tiles_of(H, tile_h(H)) * 10 * (long long)sizeof(float);
 }
 
 extern "C" int turtle_dwconv3x3_nchw_wgrad(const void *x, const void *dy, int dtype, float *dw9, float *db,
                                            void *workspace, int B, int C, int H, int W, void *stream) {
     if (!x || !dy || !dw9 || !workspace || B < 1 || C < 1 || H < 1 || W < 1 || dtype < 0 || dtype > 2) return TURTLE_EINVAL;
     if (C > 65535) return TURTLE_ENOTSUP;
-    const int tx = tiles_of(W), ty = tiles_of(H), tiles = tx * ty;
+    const int th = tile_h(H), tx = tiles_of(W), ty = tiles_of(H, th), tiles = tx * ty;
     dim3 grid(B * tiles, C);
     float *part = reinterpret_cast<float *>(workspace);
     cudaStream_t s = as_stream(stream);
-    if (dtype == 0) dw3_wgrad_kernel<0><<<grid, NT, 0, s>>>(x, dy, part, C, H, W, tx, tiles);
-    else if (dtype == 1) dw3_wgrad_kernel<1><<<grid, NT, 0, s>>>(x, dy, part, C, H, W, tx, tiles);
-    else dw3_wgrad_kernel<2><<<grid, NT, 0, s>>>(x, dy, part, C, H, W, tx, tiles);
+#define TURTLE_DW3_WGRAD(DT)                                                                              \
+    do {                                                                                                  \
+        if (th == 64) dw3_wgrad_kernel<DT, 64><<<grid, NT, 0, s>>>(x, dy, part, C, H, W, tx, tiles);      \
+        else dw3_wgrad_kernel<DT, 32><<<grid, NT, 0, s>>>(x, dy, part, C, H, W, tx, tiles);               \
+    } while (0)
+    if (dtype == 0) TURTLE_DW3_WGRAD(0);
+    else if (dtype == 1) TURTLE_DW3_WGRAD(1);
+    else TURTLE_DW3_WGRAD(2);
+#undef TURTLE_DW3_WGRAD
     TURTLE_CHECK_LAUNCH();
     dw3_wgrad_reduce_kernel<<<(unsigned)cdiv64((int64_t)C * 10 * 32, 256), 256, 0, s>>>(part, B * tiles, C, dw9, db);
     TURTLE_CHECK_LAUNCH();
