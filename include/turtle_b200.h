@@ -268,6 +268,45 @@ long long turtle_dwconv3x3_nchw_wgrad_workspace(int B, int C, int H, int W);
 int turtle_dwconv3x3_nchw_wgrad(const void *x, const void *dy, int dtype, float *dw9, float *db, void *workspace, int B,
                                 int C, int H, int W, void *stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Frame side of the per-clip loop: decode/normalise, quantise/encode, metrics, tiling.
+ * Frames are planar fp32 [C,H,W] (what the arch's forward takes and returns); 8-bit images are interleaved
+ * [H,W,C] with a row pitch in bytes (cv2 / PNG layout).
+ * ------------------------------------------------------------------------------------- */
+
+/* uint8 HWC -> fp32 CHW / 255 (swap_rb: BGR source, RGB planes).  Replaces the dataset path of
+ * inference_no_ground_truth.py (cv2.imread -> cvtColor -> /255 -> permute(2,0,1), INFN:88-120) so that only
+ * 1 byte per sample crosses PCIe. */
+int turtle_u8_to_frame(const void *src_u8, long long src_pitch, float *dst, int H, int W, int C, int swap_rb, void *stream);
+
+/* fp32 CHW -> clamp(0,1) -> x255 -> uint8 HWC.  round_mode 1 = round half to even (tensor2img, utils/img_util.py:73,99);
+ * 0 = truncate ((x*255).astype(np.uint8), INFN:268-269).  swap_rb writes BGR (cv2.cvtColor(RGB2BGR), INFN:272). */
+int turtle_frame_to_u8(const float *src, void *dst_u8, long long dst_pitch, int H, int W, int C, int swap_rb, int round_mode,
+                       void *stream);
+
+#define TURTLE_METRICS_INFERENCE 0 /* inference.py:33-61,313-327: uint8 frames, calc_PSNR, scipy-gaussian SSIM */
+#define TURTLE_METRICS_BASICSR 1   /* VRM:171-200 -> metrics/psnr_ssim.py:13-68,136-180,229 on uint8 frames    */
+#define TURTLE_METRICS_FLOAT 2     /* the same formulas on un-quantised [0,1] data, peak 1                        */
+/* PSNR and SSIM of restored vs gt, both fp32 [C,H,W] dense on the device (C <= 4).  result (device, 4 doubles) =
+ * {PSNR dB (+inf if identical), SSIM, MSE, element count}; workspace of turtle_frame_metrics_workspace(H, W) bytes.
+ * Two launches, deterministic (fixed-order double reductions), no host round trip: the reference converts both
+ * frames to numpy uint8 on the CPU every frame (INF:313-327). */
+long long turtle_frame_metrics_workspace(int H, int W);
+int turtle_frame_metrics(const float *restored, const float *gt, int C, int H, int W, int flavour, double *result,
+                         void *workspace, void *stream);
+
+/* Tiled inference (inference.py:172-246).  y0[ny] / x0[nx] are HOST arrays: the tile origins per axis in the
+ * reflect-padded frame (h_idx_list / w_idx_list, INF:196-197), ny, nx <= 64; tiles are numbered row-major.
+ * gather: out [ny*nx, 2, C, tile, tile] = (previous, current) frame pairs cut from prev / cur [C,H,W]; coordinates
+ *         beyond H, W are reflect-padded on the fly (F.pad(..., 'reflect'), INF:185-187), so the padded frame never
+ *         exists in memory.
+ * blend:  out [C,Ho,Wo] = clamp(mean of the tiles [ny*nx, C, tile, tile] covering each pixel, 0, 1): E.div_(W) and
+ *         torch.clamp of INF:239-245 as one gather pass (no accumulators, no atomics); clamp01 = 0 skips the clamp. */
+int turtle_tile_gather(const float *prev, const float *cur, float *out, int C, int H, int W, int tile, const int *y0,
+                       int ny, const int *x0, int nx, void *stream);
+int turtle_tile_blend(const float *tiles, float *out, int C, int Ho, int Wo, int tile, const int *y0, int ny,
+                      const int *x0, int nx, int clamp01, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

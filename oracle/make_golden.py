@@ -65,14 +65,21 @@ def sd_checksum(sd):
     return h.hexdigest()
 
 
+gaps = []
+
+
 def run_reference(net, clip, spy_topk):
-    """VRM:110-129 loop on the reference module, recording torch.topk indices (SAB only)."""
+    """VRM:110-129 loop on the reference module, recording torch.topk indices (SAB only) and, in ``gaps``, the
+    difference between the 5th and 6th largest score of each row."""
+    gaps.clear()
     tops = []
     orig = torch.topk
 
-    def spy(*a, **kw):
-        r = orig(*a, **kw)
+    def spy(inp, k, dim=-1, **kw):
+        r = orig(inp, k, dim=dim, **kw)
         tops.append(r.indices.clone())
+        six = orig(inp, min(k + 1, inp.shape[dim]), dim=dim).values       # 5th/6th score gap: classifies mismatches
+        gaps.append((six[..., k - 1] - six[..., k]).float() if six.shape[-1] > k else torch.zeros_like(six[..., 0]))
         return r
 
     outs, k, v = [], None, None
@@ -156,6 +163,10 @@ def make_case(variant, gates, tiny, frames, H, W, seed):
     for i, t in enumerate(ref_tops):
         fr, lvl = divmod(i, n_sab)
         tops[f"topk_f{fr}_l{lvl}"] = t[0, :, 0].to(torch.int32).numpy()       # [F,N,5]
+    ref_gaps = list(gaps)                           # the oracle below calls torch.topk un-spied
+    for i, gp in enumerate(ref_gaps):
+        fr, lvl = divmod(i, n_sab)
+        tops[f"gap_f{fr}_l{lvl}"] = gp[0, :, 0].numpy()                       # [F,N]
     data = dict(
         clip=clip.numpy(), ref_out=ref_out.numpy(), cache_digest=cache_digest(ref_caches),
         init_checksum=np.array(init_sum), gates=np.array(gates), variant=np.array(variant),

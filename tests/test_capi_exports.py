@@ -46,3 +46,43 @@ def test_bad_arguments_are_rejected_without_a_gpu():
     assert lib.turtle_dwconv3x3(None, 64, None, None, None, 64, 1, 8, 8, 64, 0, 0, 1, 0, None) == -1
     a = capi.GemmArgs()
     assert lib.turtle_gemm(ctypes.byref(a), None) == -1
+
+
+def test_every_kernel_entry_point_has_a_torch_custom_op():
+    """ops.py: one torch.ops.turtle_b200.<name> per kernel-launching prototype of the header, schema derived from it."""
+    import torch
+    from turtlevsr_b200 import ops
+    hdr = open(os.path.join(ROOT, "include", "turtle_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    launching = sorted(set(m.group(1) for m in re.finditer(r"\bint\s+(turtle_[a-z0-9_]+)\s*\(([^;]*?void \*stream[^;]*?)\)\s*;",
+                                                           hdr, flags=re.S)))
+    assert len(launching) >= 25
+    for n in launching:
+        op = getattr(torch.ops.turtle_b200, n[len("turtle_"):])
+        assert op is not None
+    # non-const pointers are declared mutated, const ones are not; the stream is not part of the schema
+    s = ops.SCHEMAS["layernorm"]
+    assert "Tensor(a!)? y" in s and "Tensor? x, int x_off" in s and "stream" not in s
+    assert "Tensor(a!) out" in ops.SCHEMAS["gemm"] and "Tensor[] A" in ops.SCHEMAS["gemm"]
+    assert "int[] y0" in ops.SCHEMAS["tile_blend"]
+
+
+def test_custom_ops_trace_with_fake_tensors_and_reject_cpu_tensors():
+    import pytest
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    from turtlevsr_b200 import ops
+    with FakeTensorMode():
+        x = torch.empty(100, 64, device="cuda")
+        w = torch.empty(64, device="cuda")
+        y = torch.empty(100, 64, device="cuda")
+        assert torch.ops.turtle_b200.layernorm(x, 0, 64, w, 0, w, 0, y, 0, 64, 100, 64, 0) is None
+    with pytest.raises((NotImplementedError, RuntimeError)):        # no CPU kernel is registered: there is no fallback
+        torch.ops.turtle_b200.layernorm(torch.zeros(4, 64), 0, 64, torch.ones(64), 0, None, 0, torch.zeros(4, 64), 0, 64,
+                                        4, 64, 0)
+    # an address handed to the op layer must know its tensor
+    t = torch.zeros(16)
+    p = ops.devptr(t, 4)
+    assert int(p) == t.data_ptr() + 16 and (p + 8).base is t and int(p + 8) == t.data_ptr() + 24
+    with pytest.raises(TypeError):
+        ops._split(12345)

@@ -60,3 +60,69 @@ def test_clipped_softmax_and_mask():
     assert w[0, 0] == 0 and w[0, 3] == 0 and abs(w.sum().item() - 1) < 1e-6
     m = local_l1_mask(46, 80, 4)
     assert int(m.sum(1).max()) == 41 and int(m.sum(1).min()) == 15
+
+
+# ----------------------------------------------------------------------------------------
+# named BASELINE.json configurations (oracle/make_golden_named.py): the fixtures record that the oracle
+# reproduced the reference at the full shapes when they were written; here a prefix of each affordable
+# clip is re-run on the CPU so a later edit of the oracle cannot drift away from them unnoticed
+# ----------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,frames", [("cfg4_sr_300.npz", 12), ("cfg1_gopro_256.npz", 2)])
+def test_oracle_matches_named_config_fixture(name, frames):
+    from helpers import classify_topk, frame_error, load_named
+    opt, sd, clip, _, z = load_named(name)
+    assert float(z["oracle_err"]) < 2e-5
+    orc = Oracle(ArchSpec.from_opt(opt, str(z["variant"])), sd)
+    orc.trace = {}
+    out, _, _ = orc.run_clip(clip[:, :frames])
+    for j in range(frames):
+        e, be = frame_error(out[0, j], z, j)
+        assert e < 2e-5 and be < 2e-5, (j, e, be)
+    for lvl, recs in enumerate(orc.trace.values()):
+        for fr, rec in enumerate(recs):
+            rows, ties, near, genuine = classify_topk(z, fr, lvl, rec["topk"][0, :, 0], tag=name)
+            assert ties == near == genuine == 0
+
+
+@pytest.mark.parametrize("name", ["cfg2_gopro_720p.npz", "cfg3_davis_480p.npz"])
+def test_named_fixture_records_oracle_agreement(name):
+    """720p / 480p are too slow for the CPU suite (25-90 s per frame); the fixture holds the agreement measured when
+    the reference and the oracle were run side by side at that shape."""
+    z = np.load(__import__("os").path.join(__import__("helpers").GOLDEN, name), allow_pickle=False)
+    assert float(z["oracle_err"]) < 2e-5 and float(z["oracle_cache_err"]) < 2e-5
+    # rows on which the two fp32 CPU implementations picked different 5th keys are all near-ties of the reference
+    from helpers import NEAR_TIE
+    assert int(z["oracle_topk_rows_differ"]) <= 8 and float(z["oracle_topk_max_gap"]) <= NEAR_TIE
+    assert int(z["oracle_frames"]) >= 4
+
+
+def test_metrics_oracle_matches_reference_functions_golden():
+    """oracle/metrics_oracle.py vs the values the reference's own calc_PSNR / ssim_calculate / _ssim_3d produced
+    (oracle/make_golden_metrics.py executed them from /root/reference)."""
+    import os
+    from helpers import GOLDEN
+    from oracle import metrics_oracle as mo
+    from oracle.make_golden_metrics import CASES, frame_pair
+    z = np.load(os.path.join(GOLDEN, "metrics_golden.npz"))
+    cols = list(z["columns"])
+    for row, (seed, H, W, noise) in zip(z["cases"], CASES):
+        out, gt = frame_pair(seed, H, W, noise)
+        p, s = mo.frame_metrics(out, gt, "inference")
+        assert abs(p - row[cols.index("inf_psnr")]) < 1e-9 and abs(s - row[cols.index("inf_ssim")]) < 1e-6
+        assert abs(mo.frame_metrics(out, gt, "basicsr")[1] - row[cols.index("bsr_ssim")]) < 1e-6
+        assert abs(mo.frame_metrics(out, gt, "float")[1] - row[cols.index("flt_ssim")]) < 1e-6
+
+
+def test_frame_folder_reader_decodes_in_order(tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    from turtlevsr_b200.frameio import FrameFolderReader
+    g = np.random.default_rng(0)
+    imgs, paths = [], []
+    for i in range(7):
+        im = g.integers(0, 256, (12, 20, 3), dtype=np.uint8)
+        p = str(tmp_path / f"Frame_{i:04d}.png")
+        cv2.imwrite(p, im)
+        imgs.append(im)
+        paths.append(p)
+    got = [t.clone().numpy() for t in FrameFolderReader(paths, depth=3)]
+    assert len(got) == 7 and all(np.array_equal(a, b) for a, b in zip(got, imgs))

@@ -16,6 +16,7 @@ FP32, TF32 = 0, 1
 ACT_NONE, ACT_GELU = 0, 1
 STORE_PLAIN, STORE_UNSHUFFLE2, STORE_SHUFFLE2 = 0, 1, 2
 ENOTSUP = -3
+METRICS_INFERENCE, METRICS_BASICSR, METRICS_FLOAT = 0, 1, 2
 
 _fp = C.c_void_p
 _i32, _i64 = C.c_int32, C.c_int64
@@ -64,6 +65,14 @@ _SIGS = {
     "turtle_dwconv3x3_nchw": ([_fp, _i32, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _i32, _fp], C.c_int),
     "turtle_dwconv3x3_nchw_wgrad_workspace": ([_i32, _i32, _i32, _i32], C.c_longlong),
     "turtle_dwconv3x3_nchw_wgrad": ([_fp, _fp, _i32, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _fp], C.c_int),
+    "turtle_u8_to_frame": ([_fp, C.c_longlong, _fp, _i32, _i32, _i32, _i32, _fp], C.c_int),
+    "turtle_frame_to_u8": ([_fp, _fp, C.c_longlong, _i32, _i32, _i32, _i32, _i32, _fp], C.c_int),
+    "turtle_frame_metrics_workspace": ([_i32, _i32], C.c_longlong),
+    "turtle_frame_metrics": ([_fp, _fp, _i32, _i32, _i32, _i32, _fp, _fp, _fp], C.c_int),
+    "turtle_tile_gather": ([_fp, _fp, _fp, _i32, _i32, _i32, _i32, C.POINTER(_i32), _i32, C.POINTER(_i32), _i32, _fp],
+                           C.c_int),
+    "turtle_tile_blend": ([_fp, _fp, _i32, _i32, _i32, _i32, C.POINTER(_i32), _i32, C.POINTER(_i32), _i32, _i32, _fp],
+                          C.c_int),
     "turtle_grad_check_finite": ([_fp, _i64, _fp, _fp], C.c_int),
     "turtle_adamw_flat": ([_fp, _fp, _fp, _fp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _fp, _fp], C.c_int),
 }

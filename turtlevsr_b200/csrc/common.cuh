@@ -10,6 +10,15 @@
         if (e__ != cudaSuccess) return TURTLE_ELAUNCH;          \
     } while (0)
 
+// one-time per-kernel configuration (opt-in shared memory size, SM count) is tracked per device ordinal: a process
+// that drives several GPUs would otherwise configure the first one only and fail every >48 KB launch on the others
+constexpr int TURTLE_MAX_DEVICES = 64;
+static inline int turtle_device() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d & (TURTLE_MAX_DEVICES - 1);
+}
+
 static inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -205,8 +205,11 @@ template <int FUSE>
 int launch16(const Dw16Params &p, cudaStream_t s) {
     constexpr int NS = Cfg<FUSE>::NS;
     const size_t smem = Cfg<FUSE>::STAGES * NS * BOXB + 128;
-    static bool configured = false;
-    static int nsm = 148;
+    static bool configured_[TURTLE_MAX_DEVICES] = {};      // cudaFuncSetAttribute is a per-device property
+    const int dev_ = turtle_device();
+    bool &configured = configured_[dev_];
+    static int nsm_[TURTLE_MAX_DEVICES];
+    int &nsm = nsm_[dev_];
     if (!configured) {
         if (cudaFuncSetAttribute(dwconv16_kernel<FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return TURTLE_ELAUNCH;

@@ -191,8 +191,11 @@ template <int FUSE, bool FAST, bool IO16>
 int launch(const DwParams &p, cudaStream_t s) {
     constexpr int NS = FUSE == 2 ? 2 : 1;
     const size_t smem = 2 * NS * (IO16 ? BOX_BYTES / 2 : BOX_BYTES) + 128;
-    static bool configured = false;
-    static int nsm = 148;
+    static bool configured_[TURTLE_MAX_DEVICES] = {};      // cudaFuncSetAttribute is a per-device property
+    const int dev_ = turtle_device();
+    bool &configured = configured_[dev_];
+    static int nsm_[TURTLE_MAX_DEVICES];
+    int &nsm = nsm_[dev_];
     if (!configured) {
         if (cudaFuncSetAttribute(dwconv_tma_kernel<FUSE, FAST, IO16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
             cudaSuccess)

@@ -846,7 +846,9 @@ inline bool get_map(CUtensorMap *out, const void *ptr, int rank, const uint64_t 
 
 template <int COLS>
 int launch(const TcParams &p, dim3 grid, size_t smem, cudaStream_t s) {
-    static bool configured = false;
+    static bool configured_[TURTLE_MAX_DEVICES] = {};      // cudaFuncSetAttribute is a per-device property
+    const int dev_ = turtle_device();
+    bool &configured = configured_[dev_];
     if (!configured) {
         if (cudaFuncSetAttribute(gemm_tc_kernel<COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024) !=
             cudaSuccess)
@@ -967,8 +969,12 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
                 break;
             }
     p.epi_boxes = boxes;
+#ifdef TURTLE_DEBUG_KNOBS       // ablation builds only: skipping the epilogue yields wrong output by design
     static const int dbg_skip = getenv("TURTLE_DBG_SKIP_EPI") ? atoi(getenv("TURTLE_DBG_SKIP_EPI")) : 0;
     p.dbg_skip = dbg_skip;
+#else
+    p.dbg_skip = 0;
+#endif
     const size_t epi_bytes = (size_t)EPI_WARPS * boxes * EPI_BUF;
     int stages = (int)((max_smem - 1024 - epi_bytes) / stage_bytes);
     if (stages > 8) stages = 8;
@@ -1003,8 +1009,11 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
     }
     const size_t smem = stages * stage_bytes + epi_bytes + 1024;
     if (o16 && !p.tma_epi) return TURTLE_ENOTSUP;
-    static bool configured = false;
-    static int nsm = 148;
+    static bool configured_[TURTLE_MAX_DEVICES] = {};      // cudaFuncSetAttribute is a per-device property
+    const int dev_ = turtle_device();
+    bool &configured = configured_[dev_];
+    static int nsm_[TURTLE_MAX_DEVICES];
+    int &nsm = nsm_[dev_];
     if (!configured) {
         bool ok = true;
         auto cfg = [&](auto kern) {

@@ -202,7 +202,9 @@ int turtle_chan_gram_tc(const float *q, int ldq, int q_hs, const float *k, int l
             return TURTLE_ENOTSUP;
     }
     const size_t smem = STAGES * STAGE_BYTES + 1024;
-    static bool configured = false;
+    static bool configured_[TURTLE_MAX_DEVICES] = {};      // cudaFuncSetAttribute is a per-device property
+    const int dev_ = turtle_device();
+    bool &configured = configured_[dev_];
     if (!configured) {
         if (cudaFuncSetAttribute(gram_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
             cudaFuncSetAttribute(gram_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)

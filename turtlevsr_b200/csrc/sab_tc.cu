@@ -332,7 +332,9 @@ extern "C" int turtle_sab_select_tc(const float *qn, const float *kn, int64_t k_
             return TURTLE_ENOTSUP;
     }
     const size_t smem = (size_t)p.stages * STAGE_BYTES + 1024;
-    static bool configured = false;
+    static bool configured_[TURTLE_MAX_DEVICES] = {};      // cudaFuncSetAttribute is a per-device property
+    const int dev_ = turtle_device();
+    bool &configured = configured_[dev_];
     if (!configured) {
         if (cudaFuncSetAttribute(sab_corr_top5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return TURTLE_ELAUNCH;

@@ -23,23 +23,26 @@ from typing import Dict, List, Optional
 
 import torch
 
-from . import capi
-from .capi import GemmArgs, call
+from . import capi, ops
+from .capi import GemmArgs
 from .history import FhrRing, SabRing, resolve_ring
 
 _NULL = None
 
 
 def _ptr(t: Optional[torch.Tensor], off: int = 0):
-    return None if t is None else t.data_ptr() + t.element_size() * off
+    """Device address of element ``off`` of ``t`` that remembers its tensor (ops.DevPtr): the launches go through the
+    torch custom-op layer (ops.py), which passes (tensor, byte offset) pairs to the dispatcher."""
+    return ops.devptr(t, off)
 
 
 class _Workspace:
     """Named, grow-only device scratch; steady-state frames allocate nothing."""
 
-    def __init__(self, device):
+    def __init__(self, device, on_realloc=None):
         self.device = device
         self.bufs: Dict[str, torch.Tensor] = {}
+        self.on_realloc = on_realloc          # called when a buffer that launches may already reference is replaced
 
     def get(self, name: str, *shape, dtype=torch.float32) -> torch.Tensor:
         n = 1
@@ -47,6 +50,8 @@ class _Workspace:
             n *= int(s)
         b = self.bufs.get(name)
         if b is None or b.numel() < n or b.dtype != dtype:
+            if b is not None and self.on_realloc is not None:
+                self.on_realloc()
             b = torch.empty(max(n, 1), device=self.device, dtype=dtype)
             self.bufs[name] = b
         return b[:n].view(*shape)
@@ -80,11 +85,11 @@ class FrameEngine:
             self.launch_log.append(name)
             return
         if self.profile is None:
-            call(name, *args)
+            ops.launch(name, *args)
             return
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        call(name, *args)
+        ops.launch(name, *args)
         e1.record()
         if self.profile_shapes and name in ("turtle_dwconv3x3", "turtle_layernorm"):
             if name == "turtle_dwconv3x3":      # (x, ldx, w, b, y, ldy, NB, H, W, C, fuse, layout, ws, rnd, stream)
@@ -112,8 +117,22 @@ class FrameEngine:
 
     def invalidate(self):
         self.packed.clear()
-        self.graphs.clear()          # captured graphs hold the packed-weight addresses
+        self.drop_graphs()           # captured graphs hold the packed-weight addresses
+
+    def drop_graphs(self):
+        """Forget every captured frame: called when something a graph has baked in goes away -- packed weights,
+        or a workspace buffer replaced by a larger one (a replayed graph would read and write freed memory)."""
+        self.graphs.clear()
         self._graph_seen.clear()
+
+    def _weights_fingerprint(self) -> int:
+        """Changes whenever a parameter is updated in place (optimizer step, ``p.data = ...``, ``copy_``): the packed
+        copies (fp16 / tap-major / TF32-rounded) and the graphs that hold their addresses are then stale.  A sum of
+        autograd version counters and storage addresses -- a few hundred attribute reads per frame."""
+        s = 0
+        for p in self._plist:
+            s += p._version + p.data_ptr()
+        return s
 
     # ------------------------------------------------------------------------------------
     # parameters
@@ -183,9 +202,12 @@ class FrameEngine:
         for i, (p, ld) in enumerate(segs):
             a.A[i] = p
             a.lda[i] = ld
-        a.Wt = _ptr(Wt) if isinstance(Wt, torch.Tensor) else Wt
+        wt = _ptr(Wt) if isinstance(Wt, torch.Tensor) else Wt
+        a.Wt = wt
         a.bias = _ptr(bias)
         a.scale = _ptr(scale)
+        # the owners of the addresses above, for the custom-op layer (a ctypes struct keeps plain integers)
+        a._ptrs = dict(A=[p for p, _ in segs], Wt=wt, bias=_ptr(bias), scale=_ptr(scale), res=res, out=out)
         a.act = act
         a.res = res
         a.ldres = ldres
@@ -197,7 +219,9 @@ class FrameEngine:
         a.out_dtype = 1 if o16 else 0
         if ln is not None:
             a.ln_out, a.ld_ln = ln[0], ln[1]
-            a.ln_w, a.ln_b = _ptr(self._w(ln[2] + "body.weight")), _ptr(self._w(ln[2] + "body.bias"))
+            lw, lb = _ptr(self._w(ln[2] + "body.weight")), _ptr(self._w(ln[2] + "body.bias"))
+            a.ln_w, a.ln_b = lw, lb
+            a._ptrs.update(ln_out=ln[0], ln_w=lw, ln_b=lb)
         if self.profile is not None:
             K = (9 if im2col else len(segs)) * segw
             ea, eo = (2 if a16 else 4), (2 if o16 else 4)
@@ -214,7 +238,7 @@ class FrameEngine:
 
     def _gemm_launch(self, a):
         try:
-            call("turtle_gemm", C.byref(a), self.stream)
+            ops.launch_gemm(a, a._ptrs, self.stream)
         except capi.TurtleKernelError as e:
             # the fused LayerNorm epilogue exists on the tensor-core kernel only: a shape that kernel does not cover
             # (sub-32 head widths of reduced configs) runs without it and the norm stays a launch of its own
@@ -222,7 +246,7 @@ class FrameEngine:
                 raise
             a.ln_out = None
             self._fused = None
-            call("turtle_gemm", C.byref(a), self.stream)
+            ops.launch_gemm(a, a._ptrs, self.stream)
 
     def _call_gemm(self, tag, a):
         if self.dry_run:
@@ -436,6 +460,10 @@ class FrameEngine:
                 ring = FhrRing.adopt(k_in, v_in, keep, ch, self.device)
             else:
                 ring = FhrRing(B, Pimg, heads, ch, keep, self.device)
+        if ring.geometry() != (B, Pimg, heads, ch):
+            # the reference fails in torch.cat here (T1:272-273); without the check the kernels would run off the ring
+            raise ValueError(f"{pre}: history caches were built for (batch, pixels, heads, head width) = "
+                             f"{ring.geometry()}, this frame has {(B, Pimg, heads, ch)}")
         slot = ring.begin_push()
         hist = []
         for b in range(B):
@@ -466,6 +494,10 @@ class FrameEngine:
                 ring = SabRing.adopt(k_in, v_in, keep, self.device)
             else:
                 ring = SabRing(B, N, Dk, Dv, keep, self.device)
+        if ring.geometry() != (B, N, Dk, Dv):
+            # the reference fails in torch.cat here (T1:581-582)
+            raise ValueError(f"{pre}: history caches were built for (batch, patches, key width, value width) = "
+                             f"{ring.geometry()}, this frame has {(B, N, Dk, Dv)}")
         slot = ring.begin_push()
         first = ring.first_live
         F_ = ring.count + 1
@@ -691,11 +723,12 @@ class FrameEngine:
             if r is None or r.count < r.keep:
                 return None                       # foreign caches or a history still filling up: eager frame
             rings.append(r)
-        if not rings or not self.packed:
-            return None                           # weights not packed yet (first frame after load/.to())
+        if not rings or not self.packed or self._weights_fingerprint() != self._weights_fp:
+            return None                           # weights not packed yet / updated in place since: eager frame repacks
         m = self.model
-        key = (tuple(inp.shape), inp.device.index, m.precision, self.use_half, self.fuse_ln, self.sab_front_half,
-               tuple((r.serial, r.pos) for r in rings))
+        key = (tuple(inp.shape), inp.device.index, m.precision, bool(getattr(m, "half_intermediates", True)),
+               bool(getattr(m, "fuse_layernorm", True)), bool(getattr(m, "sab_front_half", True)),
+               bool(getattr(m, "fuse_gffw", True)), tuple((r.serial, r.pos) for r in rings))
         ent = self.graphs.get(key)
         if ent is None:
             if key not in self._graph_seen:
@@ -747,9 +780,15 @@ class FrameEngine:
         if first_param.device != inp.device:
             raise RuntimeError(f"model is on {first_param.device}, input on {inp.device}")
         if self.ws is None or self.ws.device != inp.device:
-            self.ws = _Workspace(inp.device)
-            self.packed.clear()
+            self.ws = _Workspace(inp.device, on_realloc=self.drop_graphs)
+            self.invalidate()
         self._sd = dict(m.named_parameters())
+        self._plist = list(self._sd.values())
+        fp = self._weights_fingerprint()
+        if fp != getattr(self, "_weights_fp", None):
+            if self.packed:
+                self.invalidate()
+            self._weights_fp = fp
         self.mode = capi.TF32 if m.precision == "tf32" else capi.FP32
         self.rnd = 1 if self.mode == capi.TF32 else 0
         self.use_half = bool(getattr(m, "half_intermediates", True))

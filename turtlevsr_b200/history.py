@@ -15,12 +15,19 @@ caller is recognised as "our current window" by its storage pointer, offset, sha
 anything else (``.cpu().to(device)`` round trips of the tiled loop INF:227-237, clones, slices) is
 imported by copy into a fresh ring, so the list API stays fully general.
 
-Caveat (documented in DESIGN.md): a window view handed out earlier aliases ring memory and goes
-stale once the ring compacts; callers that need to keep an old history must ``.clone()`` it.
+Stale views.  A window view handed out earlier aliases ring memory.  Slots are only ever appended to
+between two compactions, so an older view stays intact (and is imported by copy like any foreign
+tensor) until the ring compacts; after that its memory has been overwritten.  Every ring therefore
+counts its compactions (``epoch``), every view it publishes carries the epoch it was cut in, and a
+view of an earlier epoch passed back to the model raises :class:`StaleCacheError` instead of being
+read -- callers that keep a history for more than RING_PERIOD frames must ``.clone()`` it (a clone
+is an ordinary foreign tensor).  Views that lost their tag (``.detach()``, slicing) are traced back
+to their ring through the storage registry and accepted only inside the area written this epoch.
 """
 from __future__ import annotations
 
 import os
+import weakref
 from typing import Optional, Tuple
 
 import torch
@@ -37,6 +44,12 @@ def default_slots(keep: int) -> int:
 
 
 _ring_serial = iter(range(1, 1 << 62))
+# storage address of every live ring buffer -> ring (finds the ring behind untagged views of its memory)
+_by_storage: "weakref.WeakValueDictionary[int, _RingBase]" = weakref.WeakValueDictionary()
+
+
+class StaleCacheError(RuntimeError):
+    """A cache tensor handed back to the model is a view of history-ring memory that has been overwritten since."""
 
 
 class _RingBase:
@@ -49,12 +62,18 @@ class _RingBase:
         # signature of the window last handed out (no tensor refs: the views own the ring, not
         # the other way round, so dropping the caches frees the ring without a GC cycle)
         self._sig = None
+        self.epoch = 0                       # number of compactions so far (see "Stale views" above)
+
+    def _register(self):
+        for buf in (self.kbuf, self.vbuf):
+            _by_storage[buf.untyped_storage().data_ptr()] = self
 
     # -- protocol ---------------------------------------------------------------------
     def begin_push(self) -> int:
         """Slot the producing kernels must write the new frame into (compacts first if needed)."""
         if self.pos + 1 >= self.slots:
             self._compact()
+            self.epoch += 1
         return self.pos + 1
 
     def commit(self) -> None:
@@ -71,8 +90,23 @@ class _RingBase:
 
     def _publish(self, k: torch.Tensor, v: torch.Tensor):
         k._turtle_ring = v._turtle_ring = self
+        k._turtle_epoch = v._turtle_epoch = self.epoch
         self._sig = (_sig(k), _sig(v))
         return k, v
+
+    def check_alive(self, t: torch.Tensor) -> None:
+        """``t`` aliases this ring's memory but is not its current window: raise unless its bytes are still the
+        frames it was cut from."""
+        ep = getattr(t, "_turtle_epoch", None)
+        if ep is None:
+            # untagged view (detach / slice): intact only if it lies inside the slots written since the last compaction
+            ok = self._inside_written(t)
+        else:
+            ok = ep == self.epoch
+        if not ok:
+            raise StaleCacheError(
+                "a history cache passed to the model is a view of ring memory that has been overwritten since it was "
+                "returned (the ring compacts every %d frames); .clone() caches that must outlive that" % RING_PERIOD)
 
 
 def _sig(t: torch.Tensor):
@@ -87,6 +121,10 @@ class SabRing(_RingBase):
         self.B, self.N, self.Dk, self.Dv = B, N, Dk, Dv
         self.kbuf = torch.empty(B, self.slots, N, Dk, device=device, dtype=torch.float32)
         self.vbuf = torch.empty(B, self.slots, N, Dv, device=device, dtype=torch.float32)
+        self._register()
+
+    def geometry(self):
+        return (self.B, self.N, self.Dk, self.Dv)
 
     def _compact(self):
         c, a = self.count, self.first_live
@@ -94,6 +132,13 @@ class SabRing(_RingBase):
             self.kbuf[:, :c].copy_(self.kbuf[:, a:a + c])
             self.vbuf[:, :c].copy_(self.vbuf[:, a:a + c])
         self.pos = c - 1
+
+    def _inside_written(self, t: torch.Tensor) -> bool:
+        buf = self.kbuf if t.untyped_storage().data_ptr() == self.kbuf.untyped_storage().data_ptr() else self.vbuf
+        per_slot = buf.stride(1)
+        off = t.storage_offset() % buf.stride(0)                     # offset inside one batch element
+        span = 1 + sum((n - 1) * st for n, st in zip(t.shape[1:], t.stride()[1:])) if t.numel() else 0
+        return off + span <= (self.pos + 1) * per_slot
 
     def views(self):
         a, b = self.first_live, self.pos + 1
@@ -104,6 +149,8 @@ class SabRing(_RingBase):
     @classmethod
     def adopt(cls, k: torch.Tensor, v: torch.Tensor, keep: int, device):
         """Import caller-owned cache tensors [B,Fc,1,N,D*] by copy."""
+        if k.dim() != 5 or v.dim() != 5 or k.shape[:4] != v.shape[:4] or k.shape[2] != 1:
+            raise ValueError(f"StateAlignBlock caches must be [B,F,1,N,D]; got k {tuple(k.shape)}, v {tuple(v.shape)}")
         B, Fc, _, N, Dk = k.shape
         Dv = v.shape[-1]
         r = cls(B, N, Dk, Dv, keep, device)
@@ -124,6 +171,18 @@ class FhrRing(_RingBase):
         self.B, self.P, self.heads, self.ch = B, P, heads, ch
         self.kbuf = torch.empty(B, P, heads, self.slots * ch, device=device, dtype=torch.float32)
         self.vbuf = torch.empty(B, P, heads, self.slots * ch, device=device, dtype=torch.float32)
+        self._register()
+
+    def geometry(self):
+        return (self.B, self.P, self.heads, self.ch)
+
+    def _inside_written(self, t: torch.Tensor) -> bool:
+        # frames are interleaved inside a pixel row ([.., heads, slots*ch]): a view is intact iff its channel range
+        # inside a head ends before the first unwritten slot
+        off = t.storage_offset() % (self.slots * self.ch)
+        width = max((n - 1) * st for n, st in zip(t.shape, t.stride()) if st < self.slots * self.ch) + 1 \
+            if t.numel() else 0
+        return off + width <= (self.pos + 1) * self.ch
 
     @property
     def ld(self) -> int:                     # row pitch of one pixel
@@ -141,7 +200,8 @@ class FhrRing(_RingBase):
         self.pos = c - 1
 
     def slot_ptr(self, buf: torch.Tensor, b: int, slot: int) -> int:
-        return buf.data_ptr() + 4 * (b * self.P * self.ld + slot * self.ch)
+        from .ops import DevPtr              # an int that remembers its tensor (the custom-op layer needs the owner)
+        return DevPtr(buf, 4 * (b * self.P * self.ld + slot * self.ch))
 
     def views(self):
         a, b, ch = self.first_live, self.pos + 1, self.ch
@@ -151,6 +211,9 @@ class FhrRing(_RingBase):
 
     @classmethod
     def adopt(cls, k: torch.Tensor, v: torch.Tensor, keep: int, ch: int, device):
+        if k.dim() != 4 or k.shape != v.shape or k.shape[2] % ch != 0:
+            raise ValueError(f"FrameHistoryRouter caches must be [B,heads,F*{ch},hw]; got k {tuple(k.shape)}, "
+                             f"v {tuple(v.shape)}")
         B, heads, rows, P = k.shape
         r = cls(B, P, heads, ch, keep, device)
         Fc = min(rows // ch, keep)
@@ -160,11 +223,24 @@ class FhrRing(_RingBase):
         return r
 
 
+def _ring_of(t: torch.Tensor):
+    ring = getattr(t, "_turtle_ring", None)
+    if ring is None:
+        ring = _by_storage.get(t.untyped_storage().data_ptr())
+    return ring
+
+
 def resolve_ring(k, v):
-    """Ring behind caller-supplied cache tensors if they are exactly its current window."""
+    """Ring behind caller-supplied cache tensors if they are exactly its current window (also after ``.detach()``).
+    Views of ring memory that are *not* the current window are checked for staleness (StaleCacheError) and then
+    treated like any foreign tensor: the caller imports them by copy."""
     if k is None or v is None:
         return None
-    ring = getattr(k, "_turtle_ring", None)
-    if ring is not None and ring is getattr(v, "_turtle_ring", None) and ring.matches(k, v):
-        return ring
+    rk, rv = _ring_of(k), _ring_of(v)
+    if rk is not None and rk is rv and rk.matches(k, v):
+        return rk
+    if rk is not None:
+        rk.check_alive(k)
+    if rv is not None:
+        rv.check_alive(v)
     return None

@@ -34,17 +34,50 @@ def run_inference_patched(img_lq_prev: torch.Tensor, img_lq_curr: torch.Tensor, 
     Hp, Wp = ((height + m) // m) * m, ((width + m) // m) * m
     padh = Hp - height if height % m != 0 else 0
     padw = Wp - width if width % m != 0 else 0
-    cur = F.pad(img_lq_curr.to(device), (0, padw, 0, padh), "reflect")
-    prev = F.pad(img_lq_prev.to(device), (0, padw, 0, padh), "reflect")
-    b, c, h, w = cur.shape
+    b, c = img_lq_curr.shape[:2]
+    h, w = height + padh, width + padw
     tile = min(tile, h, w)
     assert tile % 8 == 0, "tile size should be multiple of 8"
     stride = tile - tile_overlap
     h_idx_list = list(range(0, h - tile, stride)) + [h - tile]
     w_idx_list = list(range(0, w - tile, stride)) + [w - tile]
+    patch_dict_k, patch_dict_v = {}, {}
+    cur = img_lq_curr.to(device)
+    if batch_tiles and cur.is_cuda and model_type != "SR" and b == 1 and hasattr(model, "set_precision"):
+        # fused path: the reflect padding, the tile cut and the (previous, current) pairing are ONE gather kernel reading
+        # the un-padded frames, and the overlap average + clamp is ONE gather over the restored tiles (no E / W
+        # accumulators) -- turtle_tile_gather / turtle_tile_blend, csrc/frameio.cu
+        import ctypes as C_
+        from .capi import call
+        nt = len(h_idx_list) * len(w_idx_list)
+        ys = (C_.c_int32 * len(h_idx_list))(*h_idx_list)
+        xs = (C_.c_int32 * len(w_idx_list))(*w_idx_list)
+        src_c = cur.float().contiguous()
+        src_p = img_lq_prev.to(device).float().contiguous()
+        x = torch.empty(nt, 2, c, tile, tile, device=cur.device)
+        stream = torch.cuda.current_stream(cur.device).cuda_stream
+        with torch.cuda.device(cur.device):
+            call("turtle_tile_gather", src_p.data_ptr(), src_c.data_ptr(), x.data_ptr(), c, height, width, tile, ys,
+                 len(h_idx_list), xs, len(w_idx_list), stream)
+            old_k = old_v = None
+            if prev_patch_dict_k is not None and prev_patch_dict_v is not None:
+                old_k, old_v = prev_patch_dict_k[BATCH_KEY], prev_patch_dict_v[BATCH_KEY]
+            out, k_c, v_c = model(x, old_k, old_v)
+            res = torch.empty(1, out.shape[1], h, w, device=cur.device)
+            call("turtle_tile_blend", out.contiguous().data_ptr(), res.data_ptr(), out.shape[1], h, w, tile, ys,
+                 len(h_idx_list), xs, len(w_idx_list), 1, stream)
+        patch_dict_k[BATCH_KEY], patch_dict_v[BATCH_KEY] = k_c, v_c
+        i = 0
+        for hi in h_idx_list:
+            for wi in w_idx_list:
+                patch_dict_k[f"{hi}-{wi}"] = [None if t is None else t[i:i + 1] for t in k_c]
+                patch_dict_v[f"{hi}-{wi}"] = [None if t is None else t[i:i + 1] for t in v_c]
+                i += 1
+        return res, patch_dict_k, patch_dict_v
+    cur = F.pad(cur, (0, padw, 0, padh), "reflect")
+    prev = F.pad(img_lq_prev.to(device), (0, padw, 0, padh), "reflect")
     E = torch.zeros(b, c, h, w, device=device)
     Wt = torch.zeros_like(E)
-    patch_dict_k, patch_dict_v = {}, {}
     if batch_tiles:
         if b != 1:
             raise ValueError("batch_tiles stacks the tiles along the batch axis: frames must come one at a time (B=1)")
