@@ -14,8 +14,11 @@ drop-in arch on a synthetic 1280x720 frame with the history rings full (warm-up 
                algorithmic bytes or flops / its summed duration, against MEASURED_PEAKS.json
   cpu_baseline the oracle port of the reference's CPU path timed on this box's host cores on a
                bounded sample (rank 0, N=1 only)
---impl reference times that oracle port as the reference arm (the reference is PyTorch-on-CPU; its
-sources cannot travel to the GPU box).
+  gpu_eager_baseline  the reference itself in eager PyTorch on the same B200 (SURVEY 0's same-GPU bar), default TF32 and
+               fp16 autocast (rank 0, N=1 only)
+  roofline_shapes  the ten launch shapes that take the most device time, each against its own roof
+--impl reference times the reference's CPU path as the reference arm: the reference's own arch file staged under
+oracle/_ref by oracle/build_ref.py (kind "reference"), or the oracle port of it when that is absent (kind "port").
 """
 from __future__ import annotations
 
@@ -128,39 +131,95 @@ def build_model(precision: str, device):
     return net, opt
 
 
-def oracle_arm(steps: int, warmup: int, budget_s: float = 200.0):
-    """The reference's CPU path (oracle port), fp32, all host threads, on 1280x720 frames."""
+def reference_model(device="cpu"):
+    """-> (callable forward(x, k, v), kind): the REFERENCE's own Turtle_t1 (staged by oracle/build_ref.py under
+    oracle/_ref, kind "reference") when present, else the oracle port of it (kind "port").  Gopro yml, seed-10 init."""
+    from turtlevsr_b200.configs import shipped
+    from oracle import build_ref
+    if build_ref.available():
+        opt = build_ref.load_opt("Turtle_Deblur_Gopro.yml")
+        torch.manual_seed(opt.get("manual_seed", 10))
+        net = build_ref.load_arch("t1").make_model(opt).to(device).eval()
+        return net, "reference"
     from oracle.turtle_oracle import ArchSpec, Oracle
     from turtlevsr_b200.archs import create_video_model
-    from turtlevsr_b200.configs import shipped
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     opt = shipped("Turtle_Deblur_Gopro")
     torch.manual_seed(opt["manual_seed"])
     sd = {k: v.detach() for k, v in create_video_model(opt).state_dict().items()}
-    orc = Oracle(ArchSpec.from_opt(opt), sd)
+    return Oracle(ArchSpec.from_opt(opt), sd).forward, "port"
+
+
+def oracle_arm(steps: int, warmup: int, budget_s: float = 200.0):
+    """The reference's CPU path, fp32, all host threads, on 1280x720 frames (cached frame loop, VRM:110-129)."""
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    fwd, kind = reference_model("cpu")
     g = torch.Generator().manual_seed(0)
     t_start = time.perf_counter()
     k = v = None
     times = []
     n_warm = min(warmup, 1)
     j = 0
-    while True:
-        frame = torch.rand(1, 3, H720, W720, generator=g)
-        t0 = time.perf_counter()
-        _, k, v = orc.forward(torch.stack([frame, frame], 1), k, v)
-        dt = time.perf_counter() - t0
-        if j >= n_warm:
-            times.append(dt)
-        j += 1
-        if len(times) >= max(1, steps):
-            break
-        if time.perf_counter() - t_start + dt > budget_s and times:
-            break
+    with torch.no_grad():
+        while True:
+            frame = torch.rand(1, 3, H720, W720, generator=g)
+            t0 = time.perf_counter()
+            _, k, v = fwd(torch.stack([frame, frame], 1), k, v)
+            dt = time.perf_counter() - t0
+            if j >= n_warm:
+                times.append(dt)
+            j += 1
+            if len(times) >= max(1, steps):
+                break
+            if time.perf_counter() - t_start + dt > budget_s and times:
+                break
     fps = len(times) / sum(times)
     sample = (f"{len(times)} frame(s) of 1280x720 after {n_warm} warm-up frame(s), history depth "
               f"{min(j - 1, 3)}, bounded to ~{int(budget_s)} s")
-    return fps, cores, sample, len(times), n_warm, 1000.0 * sum(times) / len(times)
+    return fps, cores, sample, len(times), n_warm, 1000.0 * sum(times) / len(times), kind
+
+
+def gpu_eager_arm(dev, frames: int = 8, warm: int = 4):
+    """SURVEY 0's same-GPU bar: the reference itself (oracle/_ref; else the oracle port) run in eager PyTorch on this
+    B200 -- cuDNN / cuBLAS / ATen kernels issued from Python -- with PyTorch's default numerics (TF32 convolutions) and
+    under fp16 autocast as inference_no_ground_truth.py:134 runs it.  Baseline leg only: nothing of it is on the product
+    path."""
+    out = {}
+    try:
+        fwd, kind = reference_model(dev)
+    except Exception as e:                      # the port keeps its weights on the CPU: eager-GPU needs the staged reference
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    if kind != "reference":
+        return {"unavailable": "oracle/_ref is not staged (the oracle port is CPU-only)"}
+    g = torch.Generator().manual_seed(0)
+    clip = torch.rand(warm + frames, 1, 3, H720, W720, generator=g).to(dev)
+    for name, ctx in (("tf32_default", None), ("fp16_autocast", torch.autocast("cuda", dtype=torch.float16))):
+        try:
+            k = v = None
+            with torch.no_grad():
+                for j in range(warm + frames):
+                    if j == warm:
+                        torch.cuda.synchronize(dev)
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                    x = torch.stack([clip[max(j - 1, 0)], clip[j]], 1)
+                    if ctx is None:
+                        _, k, v = fwd(x, k, v)
+                    else:
+                        with ctx:
+                            _, k, v = fwd(x, k, v)
+                        k = [None if t is None else t.float() for t in k]
+                        v = [None if t is None else t.float() for t in v]
+                e1.record()
+                torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / frames
+            out[name] = {"value": 1000.0 / ms, "unit": "frames/s", "ms_per_frame": ms}
+        except Exception as e:
+            out[name] = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
+        torch.cuda.empty_cache()
+    out["kind"] = kind
+    out["sample"] = f"{frames} frames of 1280x720 after {warm} warm-up frames (history full), eager launches, torch {torch.__version__}"
+    return out
 
 
 def train_arm(args, rank, world, local_rank, dev, dist, barrier):
@@ -268,12 +327,14 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        fps, cores, sample, n, nw, ms = oracle_arm(args.steps, args.warmup)
+        fps, cores, sample, n, nw, ms, kind = oracle_arm(args.steps, args.warmup)
+        arm = ("the reference's own turtle_t1_arch.py (oracle/_ref), CPU, fp32" if kind == "reference"
+               else "reference CPU path (oracle port), fp32")
         line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
                 "steps": n, "warmup": nw, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "arm": "reference CPU path (oracle port), fp32"},
-                "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+                "config": {"workload": WORKLOAD, "arm": arm},
+                "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
                 "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         emit(line)
@@ -362,7 +423,7 @@ def main():
         prof = None
         if rank == 0:
             eng = net._engine
-            eng.profile_begin()
+            eng.profile_begin(shapes=True)
             nprof = 2
             for j in range(nprof):
                 _, k, v = net(frame_pair(dev_clip, j), k, v)
@@ -378,6 +439,13 @@ def main():
 
     if rank == 0:
         pk = peaks()
+        shapes = prof                                  # per launch shape ("turtle_gemm[1x1]|256->1280@58880|a16|o16")
+        prof = {}                                      # per C-ABI entry point
+        for name, d in shapes.items():
+            ent = name.split("|")[0].split("[")[0]
+            e = prof.setdefault(ent, dict(ms=0.0, launches=0, bytes=0, flops=0))
+            for key in e:
+                e[key] += d[key]
         total_ms = sum(d["ms"] for d in prof.values())
         top_name, top = max(prof.items(), key=lambda kv: kv[1]["ms"])
         ai = top["flops"] / max(top["bytes"], 1)
@@ -399,10 +467,29 @@ def main():
         roof.update(kernel=top_name, kernel_ms_per_frame=top["ms"], kernel_launches_per_frame=top["launches"],
                     kernel_share_of_frame=top["ms"] / total_ms,
                     per_kernel_ms={n: round(d["ms"], 3) for n, d in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])})
+        # every launch shape against its own roof: fp16-operand contractions against the bf16 tensor figure, TF32 ones
+        # against half of it, everything below the ridge against the copy bandwidth
+        rows = []
+        for name, d in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])[:10]:
+            if d["bytes"] <= 0 or d["ms"] <= 0:
+                rows.append({"shape": name, "launches": d["launches"], "ms": round(d["ms"], 3), "bound": None})
+                continue
+            tpk = pk["tf_sus"] if "a16" in name.split("|") else pk["tf_sus"] / 2
+            t_hbm, t_tc = d["bytes"] / (pk["hbm"] * 1e9), d["flops"] / (tpk * 1e12)
+            if t_tc > t_hbm:
+                a_ = d["flops"] / (d["ms"] * 1e-3) / 1e12
+                rows.append({"shape": name, "launches": d["launches"], "ms": round(d["ms"], 3), "bound": "tensor",
+                             "achieved": round(a_, 1), "peak": tpk, "unit": "TFLOP/s", "frac": round(a_ / tpk, 3)})
+            else:
+                a_ = d["bytes"] / (d["ms"] * 1e-3) / 1e9
+                rows.append({"shape": name, "launches": d["launches"], "ms": round(d["ms"], 3), "bound": "hbm",
+                             "achieved": round(a_, 1), "peak": pk["hbm"], "unit": "GB/s", "frac": round(a_ / pk["hbm"], 3)})
         cpu = None
+        eager = None
         if world == 1 and not args.no_cpu_baseline:
-            fps, cores, sample, n, nw, ms = oracle_arm(1, 1, budget_s=150.0)
-            cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+            eager = gpu_eager_arm(dev)
+            fps, cores, sample, n, nw, ms, kind = oracle_arm(1, 1, budget_s=150.0)
+            cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}
         line = {
             "metric": METRIC, "value": world * K / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world, "steps": K,
             "warmup": Wm, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -421,7 +508,9 @@ def main():
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "roofline": roof,
+            "roofline_shapes": rows,
             "cpu_baseline": cpu,
+            "gpu_eager_baseline": eager,
         }
         emit(line)
     if dist is not None:

@@ -268,6 +268,19 @@ long long turtle_dwconv3x3_nchw_wgrad_workspace(int B, int C, int H, int W);
 int turtle_dwconv3x3_nchw_wgrad(const void *x, const void *dy, int dtype, float *dw9, float *db, void *workspace, int B,
                                 int C, int H, int W, void *stream);
 
+/* GatedFeedForward (T1:159-178) as one kernel, tensor-core mode:  x += W_out . ( gelu(u1) * u2 ),
+ * [u1 | u2] = dw3x3( W_in . xn ), with the 5c-wide hidden map kept on the SM (project_in recomputed on the 1-pixel halo
+ * of each 8x16 tile, depthwise + gate feeding the second tcgen05 contraction through shared memory).
+ *   xn16    fp16 [B,H,W,C] dense: LayerNorm(x) (norm2 of the block)         w_in16  fp16 [2*hid, C]  (project_in.weight)
+ *   taps16  fp16 [hid/32][2][9][32]: dwconv.weight regrouped per chunk of 32 gated channels (u1 block, u2 block; tap-major)
+ *   w_out16 fp16 [C, hid] (project_out.weight)                                x       fp32 [B,H,W,C] dense, updated in place
+ *   ln_out16 (nullable) fp16 [B,H,W,C]: LayerNorm(x_new) with ln_w / ln_b [C] for the norm that reads x next (T1:96-112)
+ * C in {64, 128, 256}, hid % 32 == 0, no biases (the shipped ymls have bias = False); TURTLE_ENOTSUP otherwise -- the
+ * caller then runs turtle_gemm -> turtle_dwconv3x3(fuse = 2) -> turtle_gemm. */
+int turtle_gffw_fused(const void *xn16, const void *w_in16, const void *taps16, const void *w_out16, float *x,
+                      void *ln_out16, const float *ln_w, const float *ln_b, int B, int H, int W, int C, int hid,
+                      void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * Frame side of the per-clip loop: decode/normalise, quantise/encode, metrics, tiling.
  * Frames are planar fp32 [C,H,W] (what the arch's forward takes and returns); 8-bit images are interleaved

@@ -12,8 +12,7 @@ with torch.no_grad():
     for _ in range(4):
         _, k, v = net(x, k, v)
     eng = net._engine
-    eng.profile_shapes = True
-    eng.profile_begin()
+    eng.profile_begin(shapes=True)
     n = 2
     for _ in range(n):
         _, k, v = net(x, k, v)

@@ -99,8 +99,10 @@ class FrameEngine:
         self.profile.setdefault("_events", []).append((name, e0, e1, self._meta))
         self._meta = (0, 0)
 
-    def profile_begin(self):
+    def profile_begin(self, shapes: bool = False):
         self.profile = {}
+        self.profile_shapes = shapes
+        self._meta = (0, 0)          # a byte count noted while not profiling must not be billed to the first launch
 
     def profile_end(self) -> dict:
         """-> {kernel: dict(ms, launches, bytes, flops)} summed over the profiled frames."""
@@ -171,6 +173,9 @@ class FrameEngine:
             h = p.shape[0] // 2
             q = p[:h] if kind == "dw_lo" else p[h:]
             t = q.reshape(h, -1).t().contiguous()
+        elif kind == "dwgffw":            # GFFW depthwise taps per chunk of 32 gated channels: [hid/32][u1|u2][9][32] fp16
+            hid = p.shape[0] // 2
+            t = p.reshape(2, hid // 32, 32, 9).permute(1, 0, 3, 2).contiguous().half()
         elif kind == "conv3":             # [Cout,Cin,3,3] -> [Cout, 9*Cin] tap-major
             t = p.permute(0, 2, 3, 1).reshape(p.shape[0], -1).contiguous()
         elif kind == "conv316":           # the same, fp16 (kind::f16 im2col GEMM)
@@ -277,9 +282,13 @@ class FrameEngine:
         return (self.mode == capi.TF32 and self.use_half and self.fuse_ln and not self.dry_run and c in (64, 128, 256)
                 and (prefix + "body.bias") in self._sd)
 
-    def ln_target(self, P: int, c: int, prefix: str, b0: int = 0, Pimg: int = 0):
-        """-> (ptr, ld, prefix) of the fp16 buffer the fused LayerNorm writes (rows b0*Pimg.. of it)."""
+    def ln_target(self, P: int, c: int, prefix: str, b0: int = 0, Pimg: int = 0, avoid: Optional[torch.Tensor] = None):
+        """-> (ptr, ld, prefix) of the fp16 buffer the fused LayerNorm writes (rows b0*Pimg.. of it).
+        ``avoid``: a map the producing kernel is still reading while it writes (the fused GFFW kernel reads its fp16 input
+        tile by tile, halo included): the output then goes to the second buffer."""
         y = self.ws.get("xn16", P, c, dtype=torch.float16)
+        if avoid is not None and y.data_ptr() == avoid.data_ptr():
+            y = self.ws.get("xn16b", P, c, dtype=torch.float16)
         self._fused = (prefix, y)
         return (_ptr(y, b0 * Pimg * c), c, prefix)
 
@@ -318,6 +327,17 @@ class FrameEngine:
     def gated_ffw(self, pre, xn, x, P, c, H, W, B, ln=None):
         hid2 = self._sd[pre + "project_in.weight"].shape[0]
         hid = hid2 // 2
+        if (xn.dtype == torch.float16 and self.fuse_gffw and c in (64, 128, 256) and hid % 32 == 0
+                and (pre + "project_in.bias") not in self._sd and (pre + "dwconv.bias") not in self._sd
+                and (pre + "project_out.bias") not in self._sd):
+            # one kernel: the 5c-wide hidden map never leaves the SM (csrc/gffw_fused.cu)
+            lt = self.ln_target(P, c, ln, avoid=xn) if ln else None
+            self._meta = (P * c * (2 + 4 + 4 + (2 if ln else 0)) + 2 * 3 * hid * c, 2 * P * c * 3 * hid + 2 * 9 * P * hid2)
+            self._call("turtle_gffw_fused", _ptr(xn), _ptr(self._w(pre + "project_in.weight", "gemm16")),
+                       _ptr(self._w(pre + "dwconv.weight", "dwgffw")), _ptr(self._w(pre + "project_out.weight", "gemm16")),
+                       _ptr(x), lt[0] if lt else None, _ptr(self._w(ln + "body.weight")) if lt else None,
+                       _ptr(self._w(ln + "body.bias")) if lt else None, B, H, W, c, hid, self.stream)
+            return
         if xn.dtype == torch.float16:       # fp16 intermediates, kind::f16 MMAs
             t = self.ws.get("wide16", P, hid2, dtype=torch.float16)
             self.conv1x1(_ptr(xn), c, c, pre + "project_in.weight", _ptr(t), hid2, P, hid2,
@@ -794,6 +814,7 @@ class FrameEngine:
         self.use_half = bool(getattr(m, "half_intermediates", True))
         self.fuse_ln = bool(getattr(m, "fuse_layernorm", True))
         self.sab_front_half = bool(getattr(m, "sab_front_half", True))
+        self.fuse_gffw = bool(getattr(m, "fuse_gffw", True)) and os.environ.get("TURTLE_FUSE_GFFW", "1") != "0"
         self.gram_ctas = int(os.environ.get("TURTLE_GRAM_CTAS", "296"))      # pixel splits x heads of the Gram kernel
         self._fused = None
         self.trace = {} if getattr(m, "record_trace", False) else None
@@ -814,6 +835,7 @@ class FrameEngine:
             else:
                 Ci, src, bstride = Cc, _ptr(inp, Cc * Hs * Ws), 2 * Cc * Hs * Ws
             img = ws.get("img", B, Hp, Wp, Ci)
+            self._meta = (4 * B * Ci * (Hs * Ws + Hp * Wp), 0)
             self._call("turtle_pack_frame", src, bstride, _ptr(img), B, Ci, Hs, Ws, Hp, Wp, up, self.stream)
 
             ks: List[Optional[torch.Tensor]] = []
