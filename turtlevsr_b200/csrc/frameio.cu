@@ -371,9 +371,14 @@ int turtle_frame_metrics(const float *restored, const float *gt, int C, int H, i
     const size_t smem = (size_t)(2 * E * E * C + 5 * E * SS_T * C) * sizeof(float);
     dim3 grid((W + SS_T - 1) / SS_T, (H + SS_T - 1) / SS_T);
     cudaStream_t s = as_stream(stream);
-    if (smem > 48 * 1024 &&
-        cudaFuncSetAttribute(ssim_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return TURTLE_ELAUNCH;
+    // static (the reduction scratch) + dynamic shared memory exceeds the 48 KB default: opt in, once per device
+    static bool configured_[TURTLE_MAX_DEVICES] = {};
+    const int dev_ = turtle_device();
+    if (!configured_[dev_]) {
+        if (cudaFuncSetAttribute(ssim_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess)
+            return TURTLE_ELAUNCH;
+        configured_[dev_] = true;
+    }
     ssim_tile_kernel<<<grid, 256, smem, s>>>(p);
     TURTLE_CHECK_LAUNCH();
     metrics_finish_kernel<<<1, 256, 0, s>>>(p.partial, (long long)grid.x * grid.y, (double)C * H * W, p.psnr_peak, result);

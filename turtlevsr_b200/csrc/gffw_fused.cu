@@ -36,6 +36,8 @@ constexpr int NHALO = HR * HC;                 // 180 halo pixels
 constexpr int XSLAB = 192 * 128;               // one 64-channel k-block of the halo tile: 180 rows x 128 B, padded to 24 KB
 constexpr int HS_BYTES = 184 * 128;            // fp16 hidden halo tile: 180 pixels x 64 channels, padded (1 KB multiple)
 constexpr int A2_BYTES = 128 * 128;            // A tile of the second contraction: 128 pixels x 64 K (a chunk PAIR)
+constexpr int WIN_STAGE = 64 * 128;            // one W_in ring stage: 64 hidden rows (32 u1 + 32 u2) x 64 K
+constexpr int MAX_WST = 16;
 constexpr int NCW = 16;                        // compute warps
 constexpr int NTHREADS = 128 + NCW * 32;       // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warp 3 idle, warps 4.. compute
 constexpr int TMEM_H0 = 256;                   // TMEM columns: Y at [0, C), H buffers at [256, 384) and [384, 512)
@@ -70,44 +72,59 @@ __device__ __forceinline__ uint2 lds64(uint32_t a) {
     asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
     return v;
 }
+// XOR mask of the 16-byte chunk index inside a halo-tile row (pixel rr): a bijection of rr & 7, so the eight lanes
+// of a quarter-warp that store the same chunk of eight consecutive pixels hit eight different bank groups, and with
+// bit 2 = rr & 1, so the two pixels a half-warp reads in the depthwise pass lie in opposite 64-byte halves
+__device__ __forceinline__ int hs_mask(int rr) { return ((rr & 1) << 2) | ((rr >> 1) & 3); }
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<const uint32_t *>(&h);
 }
 
+// shared-memory plan per channel count: everything that is not the W_in ring, and the ring depth that fits beside it
+// (the ring is what hides the L2 latency of the weight stream: as many 8 KB stages as 227 KB per CTA allow)
+template <int C> struct Plan {
+    static constexpr int KB = C / 64, WOB = C <= 128 ? 2 : 1;
+    static constexpr size_t fixed = (size_t)KB * XSLAB + (size_t)WOB * C * 128 + A2_BYTES + HS_BYTES + 1024;
+    static constexpr int fit = (int)((232448 - 2048 - fixed) / WIN_STAGE);
+    static constexpr int WST = fit > MAX_WST ? MAX_WST : fit;
+    static constexpr size_t smem = fixed + (size_t)WST * WIN_STAGE;
+    static_assert(WST >= 6, "W_in ring too shallow");
+};
+
 template <int C>
 __global__ void __launch_bounds__(NTHREADS, 1) gffw_fused_kernel(const __grid_constant__ GffwParams p) {
     constexpr int KB = C / 64;                       // 64-channel k-blocks of the first contraction
-    constexpr int WIN_BYTES = KB * 64 * 128;         // one chunk of W_in: 64 rows x C
+    constexpr uint32_t NST = Plan<C>::WST;           // W_in ring stages
     constexpr int WOUT_BYTES = C * 128;              // one chunk PAIR of W_out: C rows x 64 K
     constexpr int WOB = C <= 128 ? 2 : 1;            // W_out pair buffers
     constexpr int CQ = C / 4;                        // output columns per epilogue warp
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t xfull, xempty, win_full, win_empty, wout_full[2], wout_empty[2], hfull[2], hfree[2],
-        a2_full[4], a2_empty[4], yfull, yempty;
+    __shared__ __align__(8) uint64_t xfull, xempty, win_full[MAX_WST], win_empty[MAX_WST], wout_full[2], wout_empty[2],
+        hfull[2], hfree[2], a2_full[2], a2_empty[2], yfull, yempty;
     __shared__ uint32_t tmem_base_sh;
     __shared__ float2 lnstat[4][4][32];              // [lane quarter][column quarter][lane]: (mean, M2) over CQ columns
 
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t sX = smem0;
     const uint32_t sWin = sX + KB * XSLAB;
-    const uint32_t sWout = sWin + WIN_BYTES;
+    const uint32_t sWout = sWin + NST * WIN_STAGE;
     const uint32_t sA2 = sWout + WOB * WOUT_BYTES;
-    const uint32_t sHs = sA2 + 2 * A2_BYTES;
+    const uint32_t sHs = sA2 + A2_BYTES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
         mbar_init(smem_u32(&xfull), 1);
         mbar_init(smem_u32(&xempty), 1);
-        mbar_init(smem_u32(&win_full), 1);
-        mbar_init(smem_u32(&win_empty), 1);
+        for (int i = 0; i < (int)NST; ++i) {
+            mbar_init(smem_u32(&win_full[i]), 1);
+            mbar_init(smem_u32(&win_empty[i]), 1);
+        }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&wout_full[i]), 1);
             mbar_init(smem_u32(&wout_empty[i]), 1);
             mbar_init(smem_u32(&hfull[i]), 1);
             mbar_init(smem_u32(&hfree[i]), NCW);
-        }
-        for (int i = 0; i < 4; ++i) {
             mbar_init(smem_u32(&a2_full[i]), NCW);
             mbar_init(smem_u32(&a2_empty[i]), 1);
         }
@@ -129,11 +146,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gffw_fused_kernel(const __grid_co
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_sh;
     const int nch = p.nch;
-    const int npair = (nch + 1) >> 1;
 
     if (warp == 0 && lane == 0) {
         // =========================== TMA producer ===========================
-        uint32_t g = 0, gp = 0;                      // chunks / W_out pairs issued so far (all tiles)
+        uint32_t ws = 0, gp = 0;                     // W_in stages / W_out pairs issued so far (all tiles)
         int it = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
             const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, tb = tile / (p.tiles_x * p.tiles_y);
@@ -141,12 +157,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) gffw_fused_kernel(const __grid_co
             mbar_expect_tx(smem_u32(&xfull), KB * NHALO * 128);
             for (int kb = 0; kb < KB; ++kb)
                 tma_load_4d(sX + kb * XSLAB, &p.mapX, kb * 64, tx * TW - 1, ty * TH - 1, tb, smem_u32(&xfull));
-            for (int j = 0; j < nch; ++j, ++g) {
-                mbar_wait(smem_u32(&win_empty), (g & 1) ^ 1);
-                mbar_expect_tx(smem_u32(&win_full), WIN_BYTES);
-                for (int kb = 0; kb < KB; ++kb) {
-                    tma_load_2d(sWin + kb * 8192, &p.mapWin, kb * 64, j * 32, smem_u32(&win_full));                 // u1 rows
-                    tma_load_2d(sWin + kb * 8192 + 4096, &p.mapWin, kb * 64, p.hid + j * 32, smem_u32(&win_full));   // u2 rows
+            for (int j = 0; j < nch; ++j) {
+                for (int kb = 0; kb < KB; ++kb, ++ws) {          // one ring stage per 64-channel k-block of the chunk
+                    const uint32_t st = ws % NST, fb = smem_u32(&win_full[st]);
+                    mbar_wait(smem_u32(&win_empty[st]), ((ws / NST) & 1) ^ 1);
+                    mbar_expect_tx(fb, WIN_STAGE);
+                    tma_load_2d(sWin + st * WIN_STAGE, &p.mapWin, kb * 64, j * 32, fb);                   // u1 rows
+                    tma_load_2d(sWin + st * WIN_STAGE + 4096, &p.mapWin, kb * 64, p.hid + j * 32, fb);     // u2 rows
                 }
                 if ((j & 1) == 0) {
                     const uint32_t b = gp % WOB;
@@ -162,22 +179,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) gffw_fused_kernel(const __grid_co
         // kind::f16, fp16 operands (format 0), fp32 accumulate, both operands K-major; M = 128
         const uint32_t idesc1 = (1u << 4) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
         const uint32_t idesc2 = (1u << 4) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-        uint32_t g1 = 0, g2 = 0, gp = 0;             // MMA1 / MMA2 chunks and W_out pairs consumed so far (all tiles)
+        uint32_t g1 = 0, g2 = 0, gp = 0, ws = 0;     // MMA1 / MMA2 chunks, W_out pairs and W_in stages consumed so far
         auto mma1 = [&](int j, bool last) {
             const uint32_t hb = g1 & 1;
             mbar_wait(smem_u32(&hfree[hb]), ((g1 >> 1) & 1) ^ 1);
-            mbar_wait(smem_u32(&win_full), g1 & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t th = tmem_base + TMEM_H0 + hb * 128;
 #pragma unroll
-            for (int half = 0; half < 2; ++half)
+            for (int kb = 0; kb < KB; ++kb, ++ws) {
+                const uint32_t st = ws % NST;
+                mbar_wait(smem_u32(&win_full[st]), (ws / NST) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                for (int kb = 0; kb < KB; ++kb)
+                for (int half = 0; half < 2; ++half)
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         umma_f16(th + half * 64, make_desc(sX + kb * XSLAB + half * (128 * 128) + k * 32),
-                                 make_desc(sWin + kb * 8192 + k * 32), idesc1, (kb | k) ? 1u : 0u);
-            umma_commit(smem_u32(&win_empty));
+                                 make_desc(sWin + st * WIN_STAGE + k * 32), idesc1, (kb | k) ? 1u : 0u);
+                umma_commit(smem_u32(&win_empty[st]));           // frees the stage once these MMAs retire
+            }
             umma_commit(smem_u32(&hfull[hb]));
             if (last) umma_commit(smem_u32(&xempty));
             ++g1;
@@ -191,10 +211,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gffw_fused_kernel(const __grid_co
                 if (j + 1 < nch) mma1(j + 1, j + 2 == nch);
                 if (j == 0) mbar_wait(smem_u32(&yempty), (it & 1) ^ 1);          // the previous tile's epilogue drained Y
                 if ((j & 1) == 0) mbar_wait(smem_u32(&wout_full[gp % WOB]), (gp / WOB) & 1);
-                const uint32_t s = g2 & 3;
-                mbar_wait(smem_u32(&a2_full[s]), (g2 >> 2) & 1);
+                const uint32_t s = g2 & 1;
+                mbar_wait(smem_u32(&a2_full[s]), (g2 >> 1) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a = sA2 + ((g2 >> 1) & 1) * A2_BYTES + (g2 & 1) * 64;
+                const uint32_t a = sA2 + (g2 & 1) * 64;
                 const uint32_t b = sWout + (gp % WOB) * WOUT_BYTES + (j & 1) * 64;
 #pragma unroll
                 for (int k = 0; k < 2; ++k)
@@ -223,7 +243,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gffw_fused_kernel(const __grid_co
 #pragma unroll
             for (int kx = 0; kx < 3; ++kx) {
                 const int rr = (rq * 2 + hr) * HC + col + kx;
-                hoff[hr][kx] = (uint32_t)(rr * 128 + ((((c4 >> 1) ^ (rr & 7))) << 4) + (c4 & 1) * 8);
+                hoff[hr][kx] = (uint32_t)(rr * 128 + ((((c4 >> 1) ^ hs_mask(rr))) << 4) + (c4 & 1) * 8);
             }
         uint32_t aoff[2];                            // byte offsets of the thread's two output pixels in the A tile (half 0)
 #pragma unroll
@@ -259,7 +279,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gffw_fused_kernel(const __grid_co
                         const uint32_t rowa = sHs + e_row * 128;
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            const uint32_t addr = rowa + ((((uint32_t)(e_ch * 4 + e)) ^ ((uint32_t)e_row & 7u)) << 4);
+                            const uint32_t addr = rowa + ((((uint32_t)(e_ch * 4 + e)) ^ (uint32_t)hs_mask(e_row)) << 4);
                             asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pack2(v[8 * e], v[8 * e + 1])),
                                          "r"(pack2(v[8 * e + 2], v[8 * e + 3])), "r"(pack2(v[8 * e + 4], v[8 * e + 5])),
                                          "r"(pack2(v[8 * e + 6], v[8 * e + 7]))
@@ -307,9 +327,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gffw_fused_kernel(const __grid_co
                     }
                 }
                 // -------- gated chunk -> A tile of the second contraction --------
-                const uint32_t s4 = g & 3;
-                mbar_wait(smem_u32(&a2_empty[s4]), ((g >> 2) & 1) ^ 1);          // MMA2 of chunk g-4 has read this slot
-                const uint32_t abuf = sA2 + ((g >> 1) & 1) * A2_BYTES;
+                const uint32_t s4 = g & 1;
+                mbar_wait(smem_u32(&a2_empty[s4]), ((g >> 1) & 1) ^ 1);          // MMA2 of chunk g-2 has read this half
+                const uint32_t abuf = sA2;
 #pragma unroll
                 for (int i = 0; i < 2; ++i)
                     asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(abuf + (aoff[i] ^ ((g & 1) ? 64u : 0u))),
@@ -410,8 +430,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gffw_fused_kernel(const __grid_co
 
 template <int C>
 int launch_gffw(const GffwParams &p, cudaStream_t s) {
-    constexpr int KB = C / 64, WOB = C <= 128 ? 2 : 1;
-    const size_t smem = (size_t)KB * XSLAB + (size_t)KB * 8192 + (size_t)WOB * C * 128 + 2 * A2_BYTES + HS_BYTES + 1024;
+    const size_t smem = Plan<C>::smem;
     static bool configured_[TURTLE_MAX_DEVICES] = {};
     static int nsm_[TURTLE_MAX_DEVICES];
     const int dev_ = turtle_device();
