@@ -52,8 +52,6 @@ if __name__ == "__main__":
     ns_m = dict(np=np, cv2=cv2, torch=torch)
     lift(os.path.join(REF, "basicsr/metrics/psnr_ssim.py"),
          ["_3d_gaussian_calculator", "_generate_3d_gaussian_kernel", "_ssim_3d"], ns_m)
-    lift(os.path.join(REF, "basicsr/utils/img_util.py"), ["tensor2img"],
-         dict(np=np, cv2=cv2, torch=torch, math=math, make_grid=None))
     ns_t = dict(np=np, cv2=cv2, torch=torch, math=math, make_grid=None)
     lift(os.path.join(REF, "basicsr/utils/img_util.py"), ["tensor2img"], ns_t)
     torch.Tensor.cuda = lambda self, *a, **k: self            # _ssim_3d moves everything to the GPU
@@ -62,7 +60,8 @@ if __name__ == "__main__":
     rows = []
     for seed, H, W, noise in CASES:
         out, gt = frame_pair(seed, H, W, noise)
-        a, b = ns_t["tensor2img"](out, rgb2bgr=False), ns_t["tensor2img"](gt, rgb2bgr=False)
+        # (the reference's tensor2img clamps its argument IN PLACE -- img_util.py:73 clamp_ on a view -- so it gets copies)
+        a, b = ns_t["tensor2img"](out.clone(), rgb2bgr=False), ns_t["tensor2img"](gt.clone(), rgb2bgr=False)
         assert np.array_equal(a, mo.tensor2img_u8(out)) and np.array_equal(b, mo.tensor2img_u8(gt))
         ref = dict(
             inf_psnr=ns_inf["calc_PSNR"](a, b), inf_ssim=float(ns_inf["ssim_calculate"](a, b)),

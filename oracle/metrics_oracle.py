@@ -38,14 +38,15 @@ def ssim_inference(a: np.ndarray, b: np.ndarray, sd: float = 1.5, C1: float = 0.
     return float(np.mean(m))
 
 
-def psnr_basicsr(a: np.ndarray, b: np.ndarray) -> float:
+def psnr_basicsr(a: np.ndarray, b: np.ndarray, peak=None) -> float:
     """metrics/psnr_ssim.py:13-68 (calculate_psnr, crop_border 0, no Y channel): float64 MSE,
-    peak 1 if img1.max() <= 1 else 255."""
+    peak 1 if img1.max() <= 1 else 255 (psnr_ssim.py:66) unless ``peak`` fixes it."""
     a, b = a.astype(np.float64), b.astype(np.float64)
     mse = np.mean((a - b) ** 2)
     if mse == 0:
         return float("inf")
-    peak = 1.0 if a.max() <= 1 else 255.0
+    if peak is None:
+        peak = 1.0 if a.max() <= 1 else 255.0
     return float(20.0 * np.log10(peak / np.sqrt(mse)))
 
 
@@ -79,7 +80,9 @@ def ssim_basicsr_3d(a: np.ndarray, b: np.ndarray, max_value: float) -> float:
 def frame_metrics(restored: torch.Tensor, gt: torch.Tensor, flavour: str):
     """-> (psnr, ssim) as the reference computes them for one frame pair ([C,H,W] float tensors).
     'inference': INF:313-327; 'basicsr': VRM:171-200 (tensor2img then calculate_psnr / calculate_ssim);
-    'float': the psnr_ssim.py formulas on the un-quantised [0,1] data."""
+    'float': the psnr_ssim.py formulas on un-quantised data of nominal range [0,1] with max_value FIXED to 1 (the
+    reference switches to 255 as soon as one restored value exceeds 1.0, psnr_ssim.py:66 -- a data-dependent rule that
+    the un-clamped network output would trip; the trainer never calls it on such data, it quantises first = 'basicsr')."""
     if flavour == "inference":
         a, b = tensor2img_u8(restored), tensor2img_u8(gt)
         return psnr_u8(a, b), ssim_inference(a, b)
@@ -88,4 +91,4 @@ def frame_metrics(restored: torch.Tensor, gt: torch.Tensor, flavour: str):
         return psnr_basicsr(a, b), ssim_basicsr_3d(a, b, 255.0)
     a = restored.detach().cpu().numpy().transpose(1, 2, 0)
     b = gt.detach().cpu().numpy().transpose(1, 2, 0)
-    return psnr_basicsr(a, b), ssim_basicsr_3d(a, b, 1.0)
+    return psnr_basicsr(a, b, peak=1.0), ssim_basicsr_3d(a, b, 1.0)

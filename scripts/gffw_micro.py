@@ -68,6 +68,10 @@ for c, H, W in [(64, 736, 1280), (128, 368, 640), (256, 184, 320)]:
              1, 2, s())
         gemm16(g16, hid, w_out, x[i], c, P, c, False, res=x[i])
 
+    if os.environ.get("GFFW_ONCE"):          # one launch per shape (for ncu)
+        fused(0)
+        torch.cuda.synchronize()
+        continue
     tf, tu = timed(fused, nrot), timed(unfused, nrot)
     by = P * c * (2 + 4 + 4 + 2)
     fl = 2 * P * c * 3 * hid

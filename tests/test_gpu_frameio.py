@@ -1,7 +1,8 @@
 """GPU parity of the frame-side kernels (csrc/frameio.cu) against the oracle restatements of the reference's own
 host code: 8-bit conversions (utils/img_util.py:42-102, INFN:262-276), PSNR / SSIM (INF:33-61, metrics/psnr_ssim.py),
 tile gather / overlap-average (INF:172-246).  Integer work (uint8 images, tile copies) must be bit-exact; PSNR within
-1e-6 dB relative, SSIM within 2e-6 (fp32 filter arithmetic, the bar is written here)."""
+1e-6 dB relative; SSIM within 2e-6 on [0,1]-scaled data and 1e-5 on the 0..255-scaled "basicsr" flavour, whose fp32
+variance terms E[x^2] - mu^2 cancel at magnitude 6.5e4 (the reference itself computes them in fp32; bars written here)."""
 import numpy as np
 import pytest
 import torch
@@ -19,7 +20,7 @@ def test_u8_frame_roundtrip_and_quantisation(H, W, C):
     img = torch.randint(0, 256, (H, W, C), dtype=torch.uint8, generator=g)
     f = frameio.u8_to_frame(img.cuda())
     want = img.permute(2, 0, 1).float() / 255
-    assert torch.equal(f.cpu(), want * 1.0) or (f.cpu() - want).abs().max() < 1e-7
+    assert torch.equal(f.cpu(), want)              # IEEE division by 255, bit for bit
     fb = frameio.u8_to_frame(img.cuda(), swap_rb=True)
     if C >= 3:
         assert torch.equal(fb[0], f[2]) and torch.equal(fb[2], f[0]) and torch.equal(fb[1], f[1])
@@ -47,14 +48,15 @@ def test_frame_metrics_match_reference_formulas(flavour):
         out, gt = frame_pair(seed, H, W, noise)
         psnr, ssim = frameio.frame_metrics(out.cuda(), gt.cuda(), flavour)
         want_p, want_s = mo.frame_metrics(out, gt, flavour)
+        tol = 1e-5 if flavour == "basicsr" else 2e-6
         assert abs(psnr - want_p) <= 1e-6 * abs(want_p), (flavour, seed, psnr, want_p)
-        assert abs(ssim - want_s) <= 2e-6, (flavour, seed, ssim, want_s)
+        assert abs(ssim - want_s) <= tol, (flavour, seed, ssim, want_s)
         # and against the values the reference's own functions produced (oracle/make_golden_metrics.py)
         if flavour == "inference":
             assert abs(psnr - row[cols.index("inf_psnr")]) <= 1e-6 * abs(psnr)
             assert abs(ssim - row[cols.index("inf_ssim")]) <= 2e-6
         else:
-            assert abs(ssim - row[cols.index("bsr_ssim" if flavour == "basicsr" else "flt_ssim")]) <= 2e-6
+            assert abs(ssim - row[cols.index("bsr_ssim" if flavour == "basicsr" else "flt_ssim")]) <= tol
     # identical frames: PSNR = +inf, SSIM = 1
     p, s = frameio.frame_metrics(gt.cuda(), gt.cuda(), flavour)
     assert p == float("inf") and abs(s - 1.0) < 1e-6

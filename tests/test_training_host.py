@@ -113,7 +113,10 @@ def _ddp_worker(rank, world, port, q):
     launched_in_backward = sum(buckets.launched)
     buckets.finish()
     mean = flat.grad * buckets.scale
+    # the logging reduce of BM:340-365: rank r contributes r + 1, rank 0 ends up with the mean
+    red = buckets.reduce_loss(torch.tensor(float(rank + 1)))
     if rank == 0:
+        assert abs(red.item() - (world + 1) / 2) < 1e-6
         q.put((mean.clone(), launched_in_backward, len(buckets.ranges), buckets.bytes_reduced))
     dist.barrier()
     dist.destroy_process_group()

@@ -284,6 +284,8 @@ class TurtleNet(nn.Module):
         self.precision = "fp32"        # "fp32": CUDA-core fp32 everywhere; "tf32": tcgen05 TF32 contractions
         self.cuda_graphs = False
         self.half_intermediates = True  # tf32 mode: FFN-side intermediates stored fp16 (same 10-bit mantissa as TF32)
+        self.fuse_gffw = False          # tf32 mode: GatedFeedForward as the single kernel of csrc/gffw_fused.cu (parity-equal
+                                        # to the three-kernel schedule, measured slower on B200: DESIGN.md section 3)
         self._engine = None
 
     # -- public knobs ------------------------------------------------------------------

@@ -26,7 +26,7 @@ namespace {
 // One thread converts 4 consecutive pixels of a row: 12 bytes in, three float4 out (one per channel plane).
 __global__ void __launch_bounds__(256) u8_to_frame_kernel(const uint8_t *__restrict__ src, long long src_pitch,
                                                           float *__restrict__ dst, long long plane, int H, int W, int C,
-                                                          int swap_rb, float scale) {
+                                                          int swap_rb) {
     const int groups = (W + 3) >> 2;
     const long long n = (long long)H * groups;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(256) u8_to_frame_kernel(const uint8_t *__restr
             float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if (k < npx) v[k] = (float)s[k * C + cs] * scale;
+                if (k < npx) v[k] = (float)s[k * C + cs] / 255.0f;      // IEEE division, as numpy's img / 255.
             float *d = dst + (long long)c * plane + (long long)y * W + x0;
             if (npx == 4 && ((((uintptr_t)d) & 15) == 0)) {
                 *reinterpret_cast<float4 *>(d) = make_float4(v[0], v[1], v[2], v[3]);
@@ -298,7 +298,7 @@ inline unsigned grid_for(long long n, int per_block = 256) {
 int turtle_u8_to_frame(const void *src, long long src_pitch, float *dst, int H, int W, int C, int swap_rb, void *stream) {
     if (!src || !dst || H < 1 || W < 1 || C < 1 || C > 4 || src_pitch < (long long)W * C) return TURTLE_EINVAL;
     u8_to_frame_kernel<<<grid_for((long long)H * ((W + 3) / 4)), 256, 0, as_stream(stream)>>>(
-        reinterpret_cast<const uint8_t *>(src), src_pitch, dst, (long long)H * W, H, W, C, swap_rb, 1.0f / 255.0f);
+        reinterpret_cast<const uint8_t *>(src), src_pitch, dst, (long long)H * W, H, W, C, swap_rb);
     TURTLE_CHECK_LAUNCH();
     return TURTLE_OK;
 }

@@ -86,7 +86,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 template <int C> struct Plan {
     static constexpr int KB = C / 64, WOB = C <= 128 ? 2 : 1;
     static constexpr size_t fixed = (size_t)KB * XSLAB + (size_t)WOB * C * 128 + A2_BYTES + HS_BYTES + 1024;
-    static constexpr int fit = (int)((232448 - 2048 - fixed) / WIN_STAGE);
+    static constexpr int fit = (int)((232448 - 8192 - fixed) / WIN_STAGE);     // 227 KB per CTA minus static shared memory
     static constexpr int WST = fit > MAX_WST ? MAX_WST : fit;
     static constexpr size_t smem = fixed + (size_t)WST * WIN_STAGE;
     static_assert(WST >= 6, "W_in ring too shallow");
@@ -435,8 +435,10 @@ int launch_gffw(const GffwParams &p, cudaStream_t s) {
     static int nsm_[TURTLE_MAX_DEVICES];
     const int dev_ = turtle_device();
     if (!configured_[dev_]) {
-        if (cudaFuncSetAttribute(gffw_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(gffw_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();                      // do not leave the error for the next launch check to find
             return TURTLE_ELAUNCH;
+        }
         cudaDeviceGetAttribute(&nsm_[dev_], cudaDevAttrMultiProcessorCount, dev_);
         configured_[dev_] = true;
     }

@@ -748,7 +748,7 @@ class FrameEngine:
         m = self.model
         key = (tuple(inp.shape), inp.device.index, m.precision, bool(getattr(m, "half_intermediates", True)),
                bool(getattr(m, "fuse_layernorm", True)), bool(getattr(m, "sab_front_half", True)),
-               bool(getattr(m, "fuse_gffw", True)), tuple((r.serial, r.pos) for r in rings))
+               bool(getattr(m, "fuse_gffw", False)), tuple((r.serial, r.pos) for r in rings))
         ent = self.graphs.get(key)
         if ent is None:
             if key not in self._graph_seen:
@@ -814,7 +814,7 @@ class FrameEngine:
         self.use_half = bool(getattr(m, "half_intermediates", True))
         self.fuse_ln = bool(getattr(m, "fuse_layernorm", True))
         self.sab_front_half = bool(getattr(m, "sab_front_half", True))
-        self.fuse_gffw = bool(getattr(m, "fuse_gffw", True)) and os.environ.get("TURTLE_FUSE_GFFW", "1") != "0"
+        self.fuse_gffw = (bool(getattr(m, "fuse_gffw", False)) or os.environ.get("TURTLE_FUSE_GFFW", "0") == "1")
         self.gram_ctas = int(os.environ.get("TURTLE_GRAM_CTAS", "296"))      # pixel splits x heads of the Gram kernel
         self._fused = None
         self.trace = {} if getattr(m, "record_trace", False) else None

@@ -430,9 +430,22 @@ class GradBuckets:
             self._launch(b)
         for w in self.works:
             w.wait()
+        self.reset()
+
+    def reset(self):
         self.works.clear()
         self.pending = list(self.members)
         self.launched = [False] * len(self.ranges)
+
+    def reduce_loss(self, loss: Tensor) -> Tensor:
+        """``reduce_loss_dict`` (BM:340-365): one-scalar ``reduce`` to rank 0, divided by the world size there."""
+        if self.world == 1:
+            return loss
+        t = loss.detach().clone()
+        self.dist.reduce(t, dst=0, group=self.group)
+        if self.dist.get_rank(self.group) == 0:
+            t /= self.world
+        return t
 
 
 # ----------------------------------------------------------------------------------------
@@ -513,6 +526,12 @@ class TrainStep:
         # from Python; the step is bound by the host's launch rate) is captured once for the batch shape and replayed;
         # the gradient all-reduce and the optimizer stay outside the graph (the loss scale enters as a device scalar).
         self.cuda_graph = bool(cuda_graph)
+        # overlap_in_graph: capture the bucketed all-reduces INSIDE the step graph (the post-accumulate hooks fire during
+        # the captured backward, NCCL enqueues on its own stream forked from the capturing one, finish() joins it back),
+        # so replayed steps overlap the gradient exchange with the backward pass exactly like eager steps do.  If the
+        # capture of the collectives fails on this software stack, the step falls back to all-reducing after the graph.
+        self.overlap_in_graph = True
+        self._graph_has_allreduce = False
         self._graph = None
         self._eager_steps = 0
         self._scale_t = torch.ones((), device=self.flat.data.device)
@@ -536,15 +555,36 @@ class TrainStep:
     def _replay(self, lq: Tensor, gt: Tensor) -> Tensor:
         if self._graph is None or self._g_lq.shape != lq.shape or self._g_lq.dtype != lq.dtype:
             self._g_lq, self._g_gt = lq.clone(), gt.clone()
-            self.buckets.defer = True
             from . import capi
             n0 = capi.launch_count
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self.flat.grad.zero_()
-                loss = self.loss_of_clip(self._g_lq, self._g_gt)
-                (loss * self._scale_t).backward()
-                self._g_loss = loss.detach()
+
+            def capture(with_allreduce: bool):
+                self.buckets.defer = not with_allreduce
+                self.buckets.reset()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.flat.grad.zero_()
+                    loss = self.loss_of_clip(self._g_lq, self._g_gt)
+                    (loss * self._scale_t).backward()
+                    if with_allreduce:
+                        self.buckets.finish()                    # launches the stragglers and joins NCCL's stream
+                    self._g_loss = loss.detach()
+                return g
+
+            want = self.overlap_in_graph and self.buckets.world > 1
+            try:
+                g = capture(want)
+                self._graph_has_allreduce = want
+            except Exception as e:                               # collectives not capturable here: exchange after the graph
+                if not want:
+                    raise
+                import warnings
+                warnings.warn(f"all-reduce could not be captured in the step graph ({type(e).__name__}: {e}); "
+                              "falling back to the exchange after the graph")
+                torch.cuda.synchronize()
+                g = capture(False)
+                self._graph_has_allreduce = False
+            self.buckets.defer = True                            # replays: the hooks do not run, nothing to launch
             self._graph = g
             self._g_launches = capi.launch_count - n0          # our LayerNorm / depthwise launches inside the graph
             capi.launch_count = n0
@@ -567,7 +607,8 @@ class TrainStep:
             loss = self.loss_of_clip(lq, gt)
             (loss * scale).backward()                            # bucket all-reduces start from the grad hooks
             loss = loss.detach()
-        self.buckets.finish()
+        if not (self._graph is not None and self._graph_has_allreduce and self.buckets.defer):
+            self.buckets.finish()                                # (replayed graphs that hold the collectives already did)
         self.opt.step(grad_scale=self.buckets.scale / scale, check_finite=self.scaler is not None)
         if self.scaler is not None:
             found = bool(self.opt.found_inf.item())
