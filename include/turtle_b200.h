@@ -187,14 +187,14 @@ int turtle_scale_cols(const float *x, int ldx, int x_hs, const float *s, float *
 
 /* k2_dwconv / q2_dwconv: depthwise ws x ws, stride ws, pad 1, then 'b d h w -> b (h w) d' and
  * F.normalize over d (T1:306-308, 559-560, 569-572, 577-578).
- * t [B,H,W,D] pitch ldt (the 1x1 k2/q2 output); w tap-major [ws*ws,D] (= weight.view(D,-1).t());
- * out [B, N=(H/ws)*(W/ws), D] dense,
+ * t [B,H,W,D] pitch ldt (the 1x1 k2/q2 output); w tap-major [ws*ws,D] (= weight.view(D,-1).t()); bias [D] or NULL
+ * (the arch's `bias` option, T1:306-308), added before the normalisation; out [B, N=(H/ws)*(W/ws), D] dense,
  * batch stride out_bstride floats. */
-int turtle_sab_window_reduce(const float *t, int ldt, const float *w, float *out, int64_t out_bstride, int B,
-                             int H, int W, int D, int ws, void *stream);
-/* the same on an fp16 map (ldt in halves; tensor-core mode intermediates); taps, sum and output stay fp32 */
-int turtle_sab_window_reduce_h16(const void *t, int ldt, const float *w, float *out, int64_t out_bstride, int B, int H,
-                                int W, int D, int ws, void *stream);
+int turtle_sab_window_reduce(const float *t, int ldt, const float *w, const float *bias, float *out, int64_t out_bstride,
+                             int B, int H, int W, int D, int ws, void *stream);
+/* the same on an fp16 map (ldt in halves; tensor-core mode intermediates); taps, bias, sum and output stay fp32 */
+int turtle_sab_window_reduce_h16(const void *t, int ldt, const float *w, const float *bias, float *out,
+                                 int64_t out_bstride, int B, int H, int W, int D, int ws, void *stream);
 
 /* 'b d (p1 h)(p2 w) -> b (h w) (p1 p2 d)' + F.normalize, for the T0 q/k path (T0:487-498). */
 int turtle_sab_patch_normalize(float *rows, int64_t n_rows, int D, void *stream);

@@ -107,10 +107,12 @@ def cache_digest(caches):
     return np.asarray(rows, dtype=np.float64)
 
 
-def make_case(variant, gates, tiny, frames, H, W, seed):
+def make_case(variant, gates, tiny, frames, H, W, seed, overrides=None, tag=""):
     opt = load_opt(variant)
     if tiny:
         opt = tiny_opt(opt)
+    if overrides:
+        opt.update(overrides)
     mod = load_ref_module(variant)
     torch.manual_seed(10)                         # yml manual_seed: 10
     ref = mod.make_model(opt).eval()
@@ -176,7 +178,7 @@ def make_case(variant, gates, tiny, frames, H, W, seed):
     if tiny:
         for k, v in sd.items():
             data["w::" + k] = v.numpy()
-    name = f"{'tiny' if tiny else 'full'}_{variant}_{gates}.npz"
+    name = f"{'tiny' if tiny else 'full'}_{variant}_{gates}{tag}.npz"
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, name), **data)
     print("   wrote", name, os.path.getsize(os.path.join(OUT, name)) // 1024, "KiB")
@@ -189,3 +191,9 @@ if __name__ == "__main__":
     make_case("t1", "live", tiny=True, frames=5, H=64, W=96, seed=9)
     make_case("super", "live", tiny=True, frames=3, H=128, W=128, seed=11)
     make_case("t0", "live", tiny=True, frames=3, H=64, W=64, seed=12)
+    # the option switches no shipped yml uses: BiasFree LayerNorm (T1:67-81), both frames as input (T1:1059-1061),
+    # conv biases (opt['bias'])
+    make_case("t1", "live", tiny=True, frames=4, H=64, W=64, seed=13, tag="_biasfree_bothinputs",
+              overrides=dict(LayerNorm_type="BiasFree", use_both_input=True))
+    make_case("t1", "live", tiny=True, frames=4, H=64, W=64, seed=14, tag="_convbias", overrides=dict(bias=True))
+    make_case("t0", "live", tiny=True, frames=3, H=64, W=64, seed=15, tag="_convbias", overrides=dict(bias=True))

@@ -233,17 +233,20 @@ class Oracle:
         b, c, h, w = x.shape
         t0 = self.spec.variant == "t0"
         x_qk = x + sincos_posenc_2d(c, h, w) if t0 else x
-        qk = dwconv3x3(conv1x1(x_qk, self.sd[pre + "qk.weight"]), self.sd[pre + "qk_dwconv.weight"])
+        # (every conv of the block takes the arch's ``bias`` option, T1:298-310; the shipped ymls leave it False)
+        qk = dwconv3x3(conv1x1(x_qk, self.sd[pre + "qk.weight"], self.p(pre + "qk.bias")),
+                       self.sd[pre + "qk_dwconv.weight"], self.p(pre + "qk_dwconv.bias"))
         q, k = qk.chunk(2, dim=1)
-        v = dwconv3x3(conv1x1(x, self.sd[pre + "v.weight"]), self.sd[pre + "v_dwconv.weight"])
+        v = dwconv3x3(conv1x1(x, self.sd[pre + "v.weight"], self.p(pre + "v.bias")),
+                      self.sd[pre + "v_dwconv.weight"], self.p(pre + "v_dwconv.bias"))
         Hg, Wg = h // ws, w // ws
         if t0:
             q, k = to_dilated_patches(q, ws), to_dilated_patches(k, ws)
         else:
-            k = F.conv2d(conv1x1(k, self.sd[pre + "k2.weight"]), self.sd[pre + "k2_dwconv.weight"],
-                         stride=ws, padding=1, groups=2 * c)
-            q = F.conv2d(conv1x1(q, self.sd[pre + "q2.weight"]), self.sd[pre + "q2_dwconv.weight"],
-                         stride=ws, padding=1, groups=2 * c)
+            k = F.conv2d(conv1x1(k, self.sd[pre + "k2.weight"], self.p(pre + "k2.bias")), self.sd[pre + "k2_dwconv.weight"],
+                         self.p(pre + "k2_dwconv.bias"), stride=ws, padding=1, groups=2 * c)
+            q = F.conv2d(conv1x1(q, self.sd[pre + "q2.weight"], self.p(pre + "q2.bias")), self.sd[pre + "q2_dwconv.weight"],
+                         self.p(pre + "q2_dwconv.bias"), stride=ws, padding=1, groups=2 * c)
             assert q.shape[-2:] == (Hg, Wg)
             q = q.flatten(2).transpose(1, 2)          # b N 2c
             k = k.flatten(2).transpose(1, 2)
@@ -268,7 +271,8 @@ class Oracle:
                 {"topk": top_idx.clone(), "scores": S.clone(), "weights": Wt.clone()})
         O = v if t0 else Wt @ v                        # T0:521-523 discards the aggregation
         O = from_dilated_patches(O[:, :, 0], ws, c, h, w)                    # b F c h w
-        O = conv1x1(O.reshape(b * Fr, c, h, w), self.sd[pre + "project_out.weight"]).reshape(b, Fr, c, h, w)
+        O = conv1x1(O.reshape(b * Fr, c, h, w), self.sd[pre + "project_out.weight"],
+                    self.p(pre + "project_out.bias")).reshape(b, Fr, c, h, w)
         return O, k[:, -keep:], v[:, -keep:]
 
     def causal_history(self, pre: str, x: Tensor, heads: int, scale_patch: int, keep: int, k_hist, v_hist):
@@ -276,8 +280,8 @@ class Oracle:
         b, c, h, w = x.shape
         xs, k_new, v_new = self.state_align(pre + "spatial_aligner.", x, 2 * scale_patch, keep, k_hist, v_hist)
         Fr = xs.shape[1]
-        kv = dwconv3x3(conv1x1(xs.reshape(b * Fr, c, h, w), self.sd[pre + "kv.weight"]),
-                       self.sd[pre + "kv_dwconv.weight"])
+        kv = dwconv3x3(conv1x1(xs.reshape(b * Fr, c, h, w), self.sd[pre + "kv.weight"], self.p(pre + "kv.bias")),
+                       self.sd[pre + "kv_dwconv.weight"], self.p(pre + "kv_dwconv.bias"))
         k, v = kv.chunk(2, dim=1)
 
         def rows(t):   # '(b f) (head c) h w -> b head (f c) (h w)'

@@ -180,16 +180,18 @@ def test_channel_attention_chain(heads, ch, S, mode):
     assert (xd.cpu() - want).abs().max() < (5e-5 if mode == capi.FP32 else 1e-3)
 
 
-@pytest.mark.parametrize("ws,D", [(4, 64), (8, 32), (16, 16)])
-def test_sab_window_reduce(ws, D):
+@pytest.mark.parametrize("bias", [False, True])
+@pytest.mark.parametrize("ws,D", [(4, 64), (8, 32), (16, 16), (4, 20)])
+def test_sab_window_reduce(ws, D, bias):
     B, H, W = 2, 32, 48
     t, w = rnd(B, D, H, W), rnd(D, 1, ws, ws, seed=1)
-    want = orc.l2norm_rows(F.conv2d(t, w, stride=ws, padding=1, groups=D).flatten(2).transpose(1, 2))
+    b = rnd(D, seed=2) if bias else None
+    want = orc.l2norm_rows(F.conv2d(t, w, b, stride=ws, padding=1, groups=D).flatten(2).transpose(1, 2))
     N = (H // ws) * (W // ws)
     out = torch.empty(B, N, D, device="cuda")
     wk = w.reshape(D, -1).t().contiguous().cuda()
-    call("turtle_sab_window_reduce", dp(nhwc(t)), D, wk.data_ptr(), out.data_ptr(), N * D, B, H, W, D, ws,
-         stream())
+    call("turtle_sab_window_reduce", dp(nhwc(t)), D, wk.data_ptr(), dp(b) if bias else None, out.data_ptr(), N * D, B, H, W,
+         D, ws, stream())
     assert (out.cpu() - want).abs().max() < TOL
 
 

@@ -169,18 +169,22 @@ def test_gemm_fused_layernorm(Cin, C_, P, a16):
     assert ok, worst
 
 
+@pytest.mark.parametrize("bias", [False, True])
 @pytest.mark.parametrize("ws,D", [(4, 64), (8, 128), (16, 32)])
-def test_sab_window_reduce_fp16_map(ws, D):
+def test_sab_window_reduce_fp16_map(ws, D, bias):
     from oracle import turtle_oracle as orc
     B, H, W = 2, 32, 48
     t = rnd(B, H, W, D).half().cuda()
     w = rnd(D, 1, ws, ws, seed=1)
     td = t.cpu().float().permute(0, 3, 1, 2)
-    want = orc.l2norm_rows(F.conv2d(td, w, stride=ws, padding=1, groups=D).flatten(2).transpose(1, 2))
+    b = rnd(D, seed=2).cuda() if bias else None
+    want = orc.l2norm_rows(F.conv2d(td, w, None if b is None else b.cpu(), stride=ws, padding=1,
+                                    groups=D).flatten(2).transpose(1, 2))
     N = (H // ws) * (W // ws)
     out = torch.full((B, N, D), float("nan"), device="cuda")
     wk = w.reshape(D, -1).t().contiguous().cuda()
-    call("turtle_sab_window_reduce_h16", t.data_ptr(), D, wk.data_ptr(), out.data_ptr(), N * D, B, H, W, D, ws, stream())
+    call("turtle_sab_window_reduce_h16", t.data_ptr(), D, wk.data_ptr(), b.data_ptr() if bias else None, out.data_ptr(),
+         N * D, B, H, W, D, ws, stream())
     assert (out.cpu() - want).abs().max() < 2e-5
 
 

@@ -7,7 +7,8 @@ from helpers import load_case
 from oracle.turtle_oracle import (ArchSpec, Oracle, clipped_softmax_rows, from_dilated_patches,
                                   local_l1_mask, to_dilated_patches)
 
-CASES = ["tiny_t1_live.npz", "tiny_super_live.npz", "tiny_t0_live.npz", "full_t1_init.npz"]
+CASES = ["tiny_t1_live.npz", "tiny_super_live.npz", "tiny_t0_live.npz", "full_t1_init.npz",
+         "tiny_t1_live_biasfree_bothinputs.npz", "tiny_t1_live_convbias.npz", "tiny_t0_live_convbias.npz"]
 
 
 @pytest.mark.parametrize("name", CASES)

@@ -50,8 +50,8 @@ _SIGS = {
     "turtle_chan_softmax": ([_fp, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _fp, _fp, _fp], C.c_int),
     "turtle_chan_fold": ([_fp, _fp, _i32, _i32, _i32, _fp, _i32, _fp], C.c_int),
     "turtle_scale_cols": ([_fp, _i32, _i32, _fp, _fp, _i32, _i32, _i64, _i32, _i32, _fp], C.c_int),
-    "turtle_sab_window_reduce": ([_fp, _i32, _fp, _fp, _i64, _i32, _i32, _i32, _i32, _i32, _fp], C.c_int),
-    "turtle_sab_window_reduce_h16": ([_fp, _i32, _fp, _fp, _i64, _i32, _i32, _i32, _i32, _i32, _fp], C.c_int),
+    "turtle_sab_window_reduce": ([_fp, _i32, _fp, _fp, _fp, _i64, _i32, _i32, _i32, _i32, _i32, _fp], C.c_int),
+    "turtle_sab_window_reduce_h16": ([_fp, _i32, _fp, _fp, _fp, _i64, _i32, _i32, _i32, _i32, _i32, _fp], C.c_int),
     "turtle_sab_patch_normalize": ([_fp, _i64, _i32, _fp], C.c_int),
     "turtle_sab_select": ([_fp, _fp, _i64, _i32, _i32, _i32, _i32, _fp, _i32, _fp, _fp, _i32, _fp], C.c_int),
     "turtle_sab_select_tc_workspace": ([_i32, _i32, _i32], C.c_longlong),

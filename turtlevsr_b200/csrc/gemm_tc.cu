@@ -328,6 +328,7 @@ struct alignas(64) Tc2Params {
     int Cout, NG, ngroups;
     long long total_units;
     int tma_epi, epi_boxes, dbg_skip;
+    int w_res;                 // 1: the whole weight matrix (one n-group) stays in shared memory for the CTA's lifetime
     const float *bias, *scale, *res;
     int act, ldres;
     float *out;
@@ -346,7 +347,7 @@ constexpr int EPI_BYTES = EPI_WARPS * 2 * EPI_BUF;      // 64 KB with two boxes 
 template <bool A16, bool O16, bool PAIR>
 __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant__ Tc2Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2], rfull_bar[EPI_WARPS][4];
+    __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2], rfull_bar[EPI_WARPS][4], wres_bar;
     __shared__ uint32_t tmem_base_sh;
     __shared__ float2 lnstat[2][4][2][32];      // fused LN: (mean, M2) of each row half, [tile parity][quarter][chalf][lane]
     pdl_trigger();
@@ -361,8 +362,14 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t b_bytes = (uint32_t)(PAIR ? p.NG / 2 : p.NG) * TK * 4;   // weight rows staged by THIS CTA
-    const uint32_t stage_bytes = A_STAGE_BYTES + b_bytes;
-    const uint32_t epi0 = smem0 + (uint32_t)p.stages * stage_bytes;     // per-warp staging boxes (1024 B aligned)
+    // resident weights (w_res, single n-group, no pairs): all k-blocks of W sit in front of the ring, loaded once; the
+    // ring then carries A tiles only.  A persistent CTA walks 3..50 pixel tiles with the same weights, and with short K
+    // the per-tile weight reload was 30-50 % of the TMA unit's row-segment work.
+    const bool wres = !PAIR && p.w_res;
+    const uint32_t wres0 = smem0;
+    const uint32_t ring0 = smem0 + (wres ? (uint32_t)p.nkb * b_bytes : 0u);
+    const uint32_t stage_bytes = A_STAGE_BYTES + (wres ? 0u : b_bytes);
+    const uint32_t epi0 = ring0 + (uint32_t)p.stages * stage_bytes;     // per-warp staging boxes (1024 B aligned)
     const uint32_t rank = PAIR ? cluster_rank() : 0u;
     const long long u0 = PAIR ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
     const long long ustride = PAIR ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
@@ -380,6 +387,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
         for (int w = 0; w < EPI_WARPS; ++w) {
             for (int b = 0; b < 4; ++b) mbar_init(smem_u32(&rfull_bar[w][b]), 1);
         }
+        mbar_init(smem_u32(&wres_bar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -405,6 +413,12 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
         // ------------------------------ TMA producer ------------------------------
         int stage = 0;
         uint32_t phase = 0;
+        if (wres && u0 < p.total_units) {
+            constexpr int KE_ = A16 ? 64 : 32;
+            const uint32_t wb = smem_u32(&wres_bar);
+            mbar_expect_tx(wb, (uint32_t)p.nkb * b_bytes);
+            for (int kb = 0; kb < p.nkb; ++kb) tma_load_2d(wres0 + kb * b_bytes, &p.mapW, kb * KE_, 0, wb);
+        }
         for (long long u = u0; u < p.total_units; u += ustride) {
             const int ng = (int)(u % p.ngroups);
             const long long tile = (u / p.ngroups) * TPU + rank;
@@ -418,7 +432,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
             for (int kb = 0; kb < p.nkb; ++kb) {
                 mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
                 const uint32_t fb = smem_u32(&full_bar[stage]);
-                const uint32_t sa = smem0 + stage * stage_bytes;
+                const uint32_t sa = ring0 + stage * stage_bytes;
                 constexpr int KE = A16 ? 64 : 32;       // K elements per 128-byte k-block
                 const int seg = kb / p.kb_per_seg, r = kb - seg * p.kb_per_seg;
                 if (PAIR) {
@@ -439,7 +453,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
                         const int sub = r / p.kb_per_sub;
                         tma_load_3d(sa, &p.mapA[seg], (r - sub * p.kb_per_sub) * KE, sub, m0, fb);
                     }
-                    tma_load_2d(sa + A_STAGE_BYTES, &p.mapW, kb * KE, ng * NG, fb);
+                    if (!wres) tma_load_2d(sa + A_STAGE_BYTES, &p.mapW, kb * KE, ng * NG, fb);
                 }
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
@@ -453,6 +467,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
+        if (wres && u0 < p.total_units) mbar_wait(smem_u32(&wres_bar), 0);       // the resident weights have landed
         for (long long u = u0; u < p.total_units; u += ustride, ++it) {
             const int acc = it & 1;
             mbar_wait(smem_u32(&tempty_bar[acc]), ((it >> 1) & 1) ^ 1);     // epilogue drained this accumulator
@@ -461,8 +476,8 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
             for (int kb = 0; kb < p.nkb; ++kb) {
                 mbar_wait(smem_u32(&full_bar[stage]), phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = smem0 + stage * stage_bytes;
-                const uint32_t sb = sa + A_STAGE_BYTES;
+                const uint32_t sa = ring0 + stage * stage_bytes;
+                const uint32_t sb = wres ? wres0 + kb * b_bytes : sa + A_STAGE_BYTES;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {       // 4 x 32 B of K per 128 B swizzle row
                     if (PAIR) umma_pair(A16, tacc, make_desc(sa + k * 32), make_desc(sb + k * 32), idesc, (kb | k) ? 1u : 0u);
@@ -950,8 +965,18 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
         if (!turtle_get_tmap2(&p.mapW, a->Wt, 2, dims, str, box, 1, a16 ? 1 : 0)) return TURTLE_ENOTSUP;
     }
     p.total_units = (pair ? (tiles + 1) / 2 : tiles) * p.ngroups;
-    const size_t stage_bytes = A_STAGE_BYTES + (size_t)(pair ? NG / 2 : NG) * TK * 4;
     const size_t max_smem = 232448 - 6144;   // 227 KB opt-in limit minus the kernel's static smem (barriers, LN statistics)
+    // resident weights: one n-group, no pairs, every CTA walks >= 2 tiles, and the whole [NG x K] matrix fits next to
+    // the minimum ring (2 A stages) and the minimum staging boxes (2 per epilogue warp)
+    static const bool no_wres = getenv("TURTLE_GEMM_WRES") && atoi(getenv("TURTLE_GEMM_WRES")) == 0;
+    const size_t w_total = (size_t)p.nkb * NG * TK * 4;
+    int nsm_now = 148;
+    cudaDeviceGetAttribute(&nsm_now, cudaDevAttrMultiProcessorCount, turtle_device());
+    const bool wres = !no_wres && !pair && p.ngroups == 1 && tiles >= 2LL * nsm_now &&
+                      w_total + 2 * A_STAGE_BYTES + (size_t)EPI_WARPS * 2 * EPI_BUF + 1024 <= max_smem;
+    p.w_res = wres ? 1 : 0;
+    const size_t ring_budget = max_smem - (wres ? w_total : 0);     // what the A(+B) ring and the staging boxes share
+    const size_t stage_bytes = wres ? (size_t)A_STAGE_BYTES : A_STAGE_BYTES + (size_t)(pair ? NG / 2 : NG) * TK * 4;
     // staging boxes per epilogue warp: the fp32-output paths that read a residual keep NB-1 residual boxes in flight
     // per warp, so take 4 (or 3) boxes where the operand ring still holds min(nkb, 3) stages
     static const int box_cap = getenv("TURTLE_GEMM_EPIBOX") ? atoi(getenv("TURTLE_GEMM_EPIBOX")) : 4;
@@ -964,7 +989,8 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
     int boxes = 2;
     if (a->res && !o16)
         for (int cand = box_cap < 4 ? box_cap : 4; cand > 2; --cand)
-            if ((long long)((max_smem - 1024 - (size_t)EPI_WARPS * cand * EPI_BUF) / stage_bytes) >= (p.nkb < min_st ? p.nkb : min_st)) {
+            if (ring_budget > 1024 + (size_t)EPI_WARPS * cand * EPI_BUF &&
+                (long long)((ring_budget - 1024 - (size_t)EPI_WARPS * cand * EPI_BUF) / stage_bytes) >= (p.nkb < min_st ? p.nkb : min_st)) {
                 boxes = cand;
                 break;
             }
@@ -976,7 +1002,7 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
     p.dbg_skip = 0;
 #endif
     const size_t epi_bytes = (size_t)EPI_WARPS * boxes * EPI_BUF;
-    int stages = (int)((max_smem - 1024 - epi_bytes) / stage_bytes);
+    int stages = (int)((ring_budget - 1024 - epi_bytes) / stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) return TURTLE_ENOTSUP;
     p.stages = stages;
@@ -1007,7 +1033,7 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
         if (!p.tma_epi || o16 || !a->res || p.ngroups != 1 || (NG != 64 && NG != 128 && NG != 256)) return TURTLE_ENOTSUP;
         p.ln = 1; p.ln_w = a->ln_w; p.ln_b = a->ln_b;
     }
-    const size_t smem = stages * stage_bytes + epi_bytes + 1024;
+    const size_t smem = (wres ? w_total : 0) + stages * stage_bytes + epi_bytes + 1024;
     if (o16 && !p.tma_epi) return TURTLE_ENOTSUP;
     static bool configured_[TURTLE_MAX_DEVICES] = {};      // cudaFuncSetAttribute is a per-device property
     const int dev_ = turtle_device();

@@ -12,6 +12,7 @@ namespace {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) window_reduce_kernel(const float *__restrict__ t, int ldt,
                                                             const float *__restrict__ wk /* [ws*ws][D] */,
+                                                            const float *__restrict__ bias /* [D] or null */,
                                                             float *__restrict__ out, int64_t out_bstride, int H,
                                                             int W, int D, int ws) {
     __shared__ float red[8];
@@ -35,6 +36,11 @@ __global__ void __launch_bounds__(256) window_reduce_kernel(const float *__restr
                 if (d < D) acc[r] = fmaf(__ldg(tp + d), __ldg(wp + d), acc[r]);
             }
         }
+    }
+    if (bias) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+            if (tid + 256 * r < D) acc[r] += __ldg(bias + tid + 256 * r);
     }
     float ss = acc[0] * acc[0] + acc[1] * acc[1];
     ss = warp_sum(ss);
@@ -61,6 +67,7 @@ __global__ void __launch_bounds__(256) window_reduce_kernel(const float *__restr
 template <bool H16>
 __global__ void __launch_bounds__(256) window_reduce_vec_kernel(const float *__restrict__ t, int ldt,
                                                                 const float *__restrict__ wk /* [ws*ws][D] */,
+                                                                const float *__restrict__ bias /* [D] or null */,
                                                                 float *__restrict__ out, int64_t out_bstride, int H,
                                                                 int W, int D, int ws) {
     pdl_trigger();
@@ -106,6 +113,10 @@ __global__ void __launch_bounds__(256) window_reduce_vec_kernel(const float *__r
         for (int g = 1; g < G; ++g) {          // fixed order: deterministic
             const float4 o = part[g * L + tid];
             acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+        }
+        if (bias) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias) + tid);
+            acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
         }
         ss = acc.x * acc.x + acc.y * acc.y + acc.z * acc.z + acc.w * acc.w;
     }
@@ -516,29 +527,29 @@ __global__ void __launch_bounds__(256) sab_aggregate_quad_kernel(const int32_t *
 
 }  // namespace
 
-extern "C" int turtle_sab_window_reduce(const float *t, int ldt, const float *w, float *out, int64_t out_bstride,
-                                        int B, int H, int W, int D, int ws, void *stream) {
+extern "C" int turtle_sab_window_reduce(const float *t, int ldt, const float *w, const float *bias, float *out,
+                                        int64_t out_bstride, int B, int H, int W, int D, int ws, void *stream) {
     if (!t || !w || !out || D < 1 || D > 512 || ws < 1 || H % ws || W % ws) return TURTLE_EINVAL;
     dim3 grid((H / ws) * (W / ws), B);
     const int L = D >> 2;
     if (!(D & 3) && L >= 1 && L <= 128 && !(L & (L - 1)) && !(ldt & 3) && !(out_bstride & 3) &&
-        !(((uintptr_t)t | (uintptr_t)w | (uintptr_t)out) & 15))
-        launch_pdl(window_reduce_vec_kernel<false>, dim3(grid), dim3(256), 0, as_stream(stream), t, ldt, w, out, out_bstride, H, W, D, ws);
+        !(((uintptr_t)t | (uintptr_t)w | (uintptr_t)out | (uintptr_t)bias) & 15))
+        launch_pdl(window_reduce_vec_kernel<false>, dim3(grid), dim3(256), 0, as_stream(stream), t, ldt, w, bias, out, out_bstride, H, W, D, ws);
     else
-        window_reduce_kernel<<<grid, 256, 0, as_stream(stream)>>>(t, ldt, w, out, out_bstride, H, W, D, ws);
+        window_reduce_kernel<<<grid, 256, 0, as_stream(stream)>>>(t, ldt, w, bias, out, out_bstride, H, W, D, ws);
     TURTLE_CHECK_LAUNCH();
     return TURTLE_OK;
 }
 
-extern "C" int turtle_sab_window_reduce_h16(const void *t, int ldt, const float *w, float *out, int64_t out_bstride,
-                                            int B, int H, int W, int D, int ws, void *stream) {
+extern "C" int turtle_sab_window_reduce_h16(const void *t, int ldt, const float *w, const float *bias, float *out,
+                                            int64_t out_bstride, int B, int H, int W, int D, int ws, void *stream) {
     if (!t || !w || !out || D < 1 || D > 512 || ws < 1 || H % ws || W % ws) return TURTLE_EINVAL;
     const int L = D >> 2;
     if ((D & 3) || L > 128 || (L & (L - 1)) || (ldt & 3) || (out_bstride & 3) || ((uintptr_t)t & 7) ||
-        (((uintptr_t)w | (uintptr_t)out) & 15))
+        (((uintptr_t)w | (uintptr_t)out | (uintptr_t)bias) & 15))
         return TURTLE_ENOTSUP;
     dim3 grid((H / ws) * (W / ws), B);
-    launch_pdl(window_reduce_vec_kernel<true>, dim3(grid), dim3(256), 0, as_stream(stream), reinterpret_cast<const float *>(t), ldt, w, out,
+    launch_pdl(window_reduce_vec_kernel<true>, dim3(grid), dim3(256), 0, as_stream(stream), reinterpret_cast<const float *>(t), ldt, w, bias, out,
                                                                        out_bstride, H, W, D, ws);
     TURTLE_CHECK_LAUNCH();
     return TURTLE_OK;

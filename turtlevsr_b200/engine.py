@@ -315,11 +315,12 @@ class FrameEngine:
              _ptr(y), C_, P, C_, self.rnd, self.stream)
         return y
 
-    def dwconv(self, x, ldx, wname, bname, y, ldy, NB, H, W, Cc, fuse=0, layout=0, ws=1, wkind="dw", rnd=None):
+    def dwconv(self, x, ldx, wname, bname, y, ldy, NB, H, W, Cc, fuse=0, layout=0, ws=1, wkind="dw", rnd=None, boff=0):
+        """bname: bias parameter name or None (absent parameters are skipped); boff: first channel of it to use."""
         rnd = (self.rnd if layout == 0 else 0) if rnd is None else rnd      # ring / patch rows stay unrounded
         self._meta = (4 * NB * H * W * (Cc + (Cc // 2 if fuse == 2 else Cc)), 2 * 9 * NB * H * W * Cc)
-        self._call("turtle_dwconv3x3", x, ldx, _ptr(self._w(wname, wkind)), _ptr(self._w(bname)) if bname else None, y, ldy,
-             NB, H, W, Cc, fuse, layout, ws, rnd, self.stream)
+        self._call("turtle_dwconv3x3", x, ldx, _ptr(self._w(wname, wkind)), _ptr(self._w(bname), boff) if bname else None, y,
+                   ldy, NB, H, W, Cc, fuse, layout, ws, rnd, self.stream)
 
     # ------------------------------------------------------------------------------------
     # feed-forwards (x updated in place)
@@ -533,41 +534,45 @@ class FrameEngine:
         s16 = (not t0) and self.sab_front_half and self.half_path(c, 2 * c)
         sdt = torch.float16 if s16 else torch.float32
         qk = self.ws.get("wide16" if s16 else "wide", P, 2 * c, dtype=sdt)
-        self.conv1x1(_ptr(src), c, c, sa + "qk.weight", _ptr(qk), 2 * c, P, 2 * c, o16=s16)
+        self.conv1x1(_ptr(src), c, c, sa + "qk.weight", _ptr(qk), 2 * c, P, 2 * c, bias=self._w(sa + "qk.bias"), o16=s16)
         qkd = self.ws.get("dw16" if s16 else "dw", P, 2 * c, dtype=sdt)
         vt = self.ws.get("sab_v", P, c)
-        self.conv1x1(_ptr(xn), c, c, sa + "v.weight", _ptr(vt), c, P, c)
+        self.conv1x1(_ptr(xn), c, c, sa + "v.weight", _ptr(vt), c, P, c, bias=self._w(sa + "v.bias"))
         qn = self.ws.get("sab_qn", B, N, Dk)
         if not t0 and s16:
             self._meta = (2 * P * 4 * c, 2 * 9 * P * 2 * c)
-            self._call("turtle_dwconv3x3", _ptr(qk), 2 * c, _ptr(self._w(sa + "qk_dwconv.weight", "dw16")), None,
-                       _ptr(qkd), 2 * c, B, H, W, 2 * c, 0, 0, 1, 2, self.stream)
+            self._call("turtle_dwconv3x3", _ptr(qk), 2 * c, _ptr(self._w(sa + "qk_dwconv.weight", "dw16")),
+                       _ptr(self._w(sa + "qk_dwconv.bias")), _ptr(qkd), 2 * c, B, H, W, 2 * c, 0, 0, 1, 2, self.stream)
             red = self.ws.get("wide16", P, 2 * c, dtype=torch.float16)            # qk no longer needed
-            self.conv1x1(_ptr(qkd, c), 2 * c, c, sa + "k2.weight", _ptr(red), 2 * c, P, 2 * c, a16=True, o16=True)
+            self.conv1x1(_ptr(qkd, c), 2 * c, c, sa + "k2.weight", _ptr(red), 2 * c, P, 2 * c, bias=self._w(sa + "k2.bias"),
+                         a16=True, o16=True)
             self._call("turtle_sab_window_reduce_h16", _ptr(red), 2 * c, _ptr(self._w(sa + "k2_dwconv.weight", "dw")),
-                       _ptr(ring.kbuf[:, slot]), ring.kbuf.stride(0), B, H, W, 2 * c, ws_, self.stream)
-            self.conv1x1(_ptr(qkd), 2 * c, c, sa + "q2.weight", _ptr(red), 2 * c, P, 2 * c, a16=True, o16=True)
+                       _ptr(self._w(sa + "k2_dwconv.bias")), _ptr(ring.kbuf[:, slot]), ring.kbuf.stride(0), B, H, W, 2 * c,
+                       ws_, self.stream)
+            self.conv1x1(_ptr(qkd), 2 * c, c, sa + "q2.weight", _ptr(red), 2 * c, P, 2 * c, bias=self._w(sa + "q2.bias"),
+                         a16=True, o16=True)
             self._call("turtle_sab_window_reduce_h16", _ptr(red), 2 * c, _ptr(self._w(sa + "q2_dwconv.weight", "dw")),
-                       _ptr(qn), N * Dk, B, H, W, 2 * c, ws_, self.stream)
+                       _ptr(self._w(sa + "q2_dwconv.bias")), _ptr(qn), N * Dk, B, H, W, 2 * c, ws_, self.stream)
         elif not t0:
-            self.dwconv(_ptr(qk), 2 * c, sa + "qk_dwconv.weight", None, _ptr(qkd), 2 * c, B, H, W, 2 * c)
+            self.dwconv(_ptr(qk), 2 * c, sa + "qk_dwconv.weight", sa + "qk_dwconv.bias", _ptr(qkd), 2 * c, B, H, W, 2 * c)
             red = self.ws.get("wide", P, 2 * c)            # qk no longer needed
             # k: 1x1 c->2c on the k half, then window reduce + normalise straight into the ring slot
-            self.conv1x1(_ptr(qkd, c), 2 * c, c, sa + "k2.weight", _ptr(red), 2 * c, P, 2 * c)
+            self.conv1x1(_ptr(qkd, c), 2 * c, c, sa + "k2.weight", _ptr(red), 2 * c, P, 2 * c, bias=self._w(sa + "k2.bias"))
             self._call("turtle_sab_window_reduce", _ptr(red), 2 * c, _ptr(self._w(sa + "k2_dwconv.weight", "dw")),
-                 _ptr(ring.kbuf[:, slot]), ring.kbuf.stride(0), B, H, W, 2 * c, ws_, self.stream)
-            self.conv1x1(_ptr(qkd), 2 * c, c, sa + "q2.weight", _ptr(red), 2 * c, P, 2 * c)
+                       _ptr(self._w(sa + "k2_dwconv.bias")), _ptr(ring.kbuf[:, slot]), ring.kbuf.stride(0), B, H, W, 2 * c,
+                       ws_, self.stream)
+            self.conv1x1(_ptr(qkd), 2 * c, c, sa + "q2.weight", _ptr(red), 2 * c, P, 2 * c, bias=self._w(sa + "q2.bias"))
             self._call("turtle_sab_window_reduce", _ptr(red), 2 * c, _ptr(self._w(sa + "q2_dwconv.weight", "dw")),
-                 _ptr(qn), N * Dk, B, H, W, 2 * c, ws_, self.stream)
+                       _ptr(self._w(sa + "q2_dwconv.bias")), _ptr(qn), N * Dk, B, H, W, 2 * c, ws_, self.stream)
         for b in range(B):
             # v: depthwise 3x3 written directly as dilated patch rows into the ring slot
-            self.dwconv(_ptr(vt, b * Pimg * c), c, sa + "v_dwconv.weight", None, _ptr(ring.vbuf[b, slot]), c, 1, H, W, c,
-                        layout=1, ws=ws_)
+            self.dwconv(_ptr(vt, b * Pimg * c), c, sa + "v_dwconv.weight", sa + "v_dwconv.bias", _ptr(ring.vbuf[b, slot]), c,
+                        1, H, W, c, layout=1, ws=ws_)
             if t0:
-                self.dwconv(_ptr(qk, b * Pimg * 2 * c), 2 * c, sa + "qk_dwconv.weight", None, _ptr(qn[b]), c, 1, H, W,
-                            c, layout=1, ws=ws_, wkind="dw_lo")
-                self.dwconv(_ptr(qk, b * Pimg * 2 * c + c), 2 * c, sa + "qk_dwconv.weight", None,
-                            _ptr(ring.kbuf[b, slot]), c, 1, H, W, c, layout=1, ws=ws_, wkind="dw_hi")
+                self.dwconv(_ptr(qk, b * Pimg * 2 * c), 2 * c, sa + "qk_dwconv.weight", sa + "qk_dwconv.bias", _ptr(qn[b]),
+                            c, 1, H, W, c, layout=1, ws=ws_, wkind="dw_lo")
+                self.dwconv(_ptr(qk, b * Pimg * 2 * c + c), 2 * c, sa + "qk_dwconv.weight", sa + "qk_dwconv.bias",
+                            _ptr(ring.kbuf[b, slot]), c, 1, H, W, c, layout=1, ws=ws_, wkind="dw_hi", boff=c)
                 self._call("turtle_sab_patch_normalize", _ptr(qn[b]), N, Dk, self.stream)
                 self._call("turtle_sab_patch_normalize", _ptr(ring.kbuf[b, slot]), N, Dk, self.stream)
 
@@ -598,21 +603,23 @@ class FrameEngine:
         if self.trace is not None:
             self.trace.setdefault(sa, []).append(dict(idx=idx.clone(), wgt=wgt.clone(), qn=qn.clone()))
         xs = self.ws.get("sab_xs16" if r16 else "sab_xs", B, F_, Pimg, c, dtype=dt16)
-        self.conv1x1(_ptr(agg), c, c, sa + "project_out.weight", _ptr(xs), c, B * F_ * Pimg, c, round_out=True,
-                     a16=r16, o16=r16)
+        self.conv1x1(_ptr(agg), c, c, sa + "project_out.weight", _ptr(xs), c, B * F_ * Pimg, c,
+                     bias=self._w(sa + "project_out.bias"), round_out=True, a16=r16, o16=r16)
         ring.commit()
         k_out, v_out = ring.views()
 
         # --- router over the aligned history (T1:649-660) ---------------------------------------
         kv = self.ws.get("chm_kv16" if r16 else "chm_kv", B * F_ * Pimg, 2 * c, dtype=dt16)
-        self.conv1x1(_ptr(xs), c, c, pre + "kv.weight", _ptr(kv), 2 * c, B * F_ * Pimg, 2 * c, a16=r16, o16=r16)
+        self.conv1x1(_ptr(xs), c, c, pre + "kv.weight", _ptr(kv), 2 * c, B * F_ * Pimg, 2 * c, bias=self._w(pre + "kv.bias"),
+                     a16=r16, o16=r16)
         kvd = self.ws.get("chm_kvd16" if r16 else "chm_kvd", B, F_, Pimg, 2 * c, dtype=dt16)
         if r16:
             self._meta = (2 * B * F_ * Pimg * 4 * c, 2 * 9 * B * F_ * Pimg * 2 * c)
-            self._call("turtle_dwconv3x3", _ptr(kv), 2 * c, _ptr(self._w(pre + "kv_dwconv.weight", "dw16")), None,
-                       _ptr(kvd), 2 * c, B * F_, H, W, 2 * c, 0, 0, 1, 2, self.stream)
+            self._call("turtle_dwconv3x3", _ptr(kv), 2 * c, _ptr(self._w(pre + "kv_dwconv.weight", "dw16")),
+                       _ptr(self._w(pre + "kv_dwconv.bias")), _ptr(kvd), 2 * c, B * F_, H, W, 2 * c, 0, 0, 1, 2, self.stream)
         else:
-            self.dwconv(_ptr(kv), 2 * c, pre + "kv_dwconv.weight", None, _ptr(kvd), 2 * c, B * F_, H, W, 2 * c)
+            self.dwconv(_ptr(kv), 2 * c, pre + "kv_dwconv.weight", pre + "kv_dwconv.bias", _ptr(kvd), 2 * c, B * F_, H, W,
+                        2 * c)
         ch = c // heads
         hist = []
         for b in range(B):
