@@ -968,7 +968,10 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
     const size_t max_smem = 232448 - 6144;   // 227 KB opt-in limit minus the kernel's static smem (barriers, LN statistics)
     // resident weights: one n-group, no pairs, every CTA walks >= 2 tiles, and the whole [NG x K] matrix fits next to
     // the minimum ring (2 A stages) and the minimum staging boxes (2 per epilogue warp)
-    static const bool no_wres = getenv("TURTLE_GEMM_WRES") && atoi(getenv("TURTLE_GEMM_WRES")) == 0;
+    // OFF by default: measured neutral on B200 (scripts/gemm_micro.py, every hot shape within +-1 us; 128->256 @235520
+    // 35.2 -> 36.7 us) -- the per-tile weight reload comes out of L2 and is not what bounds the short-K GEMMs.
+    // TURTLE_GEMM_WRES=1 turns it on for A/B runs.
+    static const bool no_wres = !(getenv("TURTLE_GEMM_WRES") && atoi(getenv("TURTLE_GEMM_WRES")) == 1);
     const size_t w_total = (size_t)p.nkb * NG * TK * 4;
     int nsm_now = 148;
     cudaDeviceGetAttribute(&nsm_now, cudaDevAttrMultiProcessorCount, turtle_device());

@@ -87,9 +87,11 @@ class FrameEngine:
         if self.profile is None:
             ops.launch(name, *args)
             return
+        # per-launch timing pass: straight through ctypes -- the dispatcher's extra host time per launch would sit between
+        # the two events whenever the GPU drains the queue faster than the host fills it (kernels of a few tens of us)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        ops.launch(name, *args)
+        capi.call(name, *args)
         e1.record()
         if self.profile_shapes and name in ("turtle_dwconv3x3", "turtle_layernorm"):
             if name == "turtle_dwconv3x3":      # (x, ldx, w, b, y, ldy, NB, H, W, C, fuse, layout, ws, rnd, stream)
@@ -242,8 +244,12 @@ class FrameEngine:
         self._call_gemm(name, a)
 
     def _gemm_launch(self, a):
+        if self.profile is not None:                  # timing pass: no dispatcher between the events (see _call)
+            launch = lambda: capi.call("turtle_gemm", C.byref(a), self.stream)
+        else:
+            launch = lambda: ops.launch_gemm(a, a._ptrs, self.stream)
         try:
-            ops.launch_gemm(a, a._ptrs, self.stream)
+            launch()
         except capi.TurtleKernelError as e:
             # the fused LayerNorm epilogue exists on the tensor-core kernel only: a shape that kernel does not cover
             # (sub-32 head widths of reduced configs) runs without it and the norm stays a launch of its own
@@ -251,7 +257,7 @@ class FrameEngine:
                 raise
             a.ln_out = None
             self._fused = None
-            ops.launch_gemm(a, a._ptrs, self.stream)
+            launch()
 
     def _call_gemm(self, tag, a):
         if self.dry_run:
