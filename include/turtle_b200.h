@@ -280,6 +280,12 @@ int turtle_dwconv3x3_nchw_wgrad(const void *x, const void *dy, int dtype, float 
 int turtle_gffw_fused(const void *xn16, const void *w_in16, const void *taps16, const void *w_out16, float *x,
                       void *ln_out16, const float *ln_w, const float *ln_b, int B, int H, int W, int C, int hid,
                       void *stream);
+/* The second half of GatedFeedForward on its own:  x += W_out . ( gelu(u1) * u2 ),  [u1 | u2] = dw3x3(t16), where
+ * t16 fp16 [B,H,W,2*hid] dense is the hidden map the project_in GEMM wrote (turtle_gemm, fp16 output).  Depthwise + gate
+ * feed the project_out tcgen05 contraction through shared memory (halo boxes by TMA, two CTAs per SM), so the gated map
+ * never reaches HBM and project_out is not a separate pass.  Other arguments and limits as turtle_gffw_fused. */
+int turtle_gffw_tail(const void *t16, const void *taps16, const void *w_out16, float *x, void *ln_out16, const float *ln_w,
+                     const float *ln_b, int B, int H, int W, int C, int hid, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Frame side of the per-clip loop: decode/normalise, quantise/encode, metrics, tiling.

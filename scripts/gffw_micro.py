@@ -68,10 +68,21 @@ for c, H, W in [(64, 736, 1280), (128, 368, 640), (256, 184, 320)]:
              1, 2, s())
         gemm16(g16, hid, w_out, x[i], c, P, c, False, res=x[i])
 
+    def tail(i):                # project_in GEMM + (depthwise + gate + project_out) kernel
+        gemm16(xn[i], c, w_in, t16, 2 * hid, P, 2 * hid, True)
+        call("turtle_gffw_tail", t16.data_ptr(), taps_f.data_ptr(), w_out.data_ptr(), x[i].data_ptr(), ln[i].data_ptr(),
+             ln_w.data_ptr(), ln_b.data_ptr(), 1, H, W, c, hid, s())
+
+    def tail_only(i):
+        call("turtle_gffw_tail", t16.data_ptr(), taps_f.data_ptr(), w_out.data_ptr(), x[i].data_ptr(), ln[i].data_ptr(),
+             ln_w.data_ptr(), ln_b.data_ptr(), 1, H, W, c, hid, s())
+
     if os.environ.get("GFFW_ONCE"):          # one launch per shape (for ncu)
-        fused(0)
+        (tail_only if os.environ["GFFW_ONCE"] == "tail" else fused)(0)
         torch.cuda.synchronize()
         continue
+    tt, tto = timed(tail, nrot), timed(tail_only, nrot)
+    print(f"GFFW c={c} {H}x{W}: project_in GEMM + gffw_tail {tt:8.1f} us (tail kernel alone {tto:8.1f} us)", flush=True)
     tf, tu = timed(fused, nrot), timed(unfused, nrot)
     by = P * c * (2 + 4 + 4 + 2)
     fl = 2 * P * c * 3 * hid

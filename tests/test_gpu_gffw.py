@@ -90,6 +90,19 @@ def test_fused_gffw_matches_reference_and_unfused_path(c, hid, B, H, W, ln):
         d = (x - x2).abs().max().item()
         print(f"   fused vs unfused schedule: max|d| {d:.3e}")
         assert d <= 3e-3 * max(1.0, scale)
+        # the second half on its own (turtle_gffw_tail): depthwise + gate feeding project_out, from the same hidden map
+        if hid * 2 <= 5 * c:
+            x3 = x0.clone()
+            ln3 = torch.full((P, c), float("nan"), device="cuda", dtype=torch.float16) if ln else None
+            call("turtle_gffw_tail", t16.data_ptr(), pack_taps(wdw16.float(), hid).cuda().data_ptr(), w_out16.data_ptr(),
+                 x3.data_ptr(), ln3.data_ptr() if ln else None, ln_w.data_ptr() if ln else None,
+                 ln_b.data_ptr() if ln else None, B, H, W, c, hid, stream())
+            torch.cuda.synchronize()
+            d3 = (x3 - x2).abs().max().item()
+            print(f"   gffw_tail vs unfused schedule: max|d| {d3:.3e}")
+            assert d3 <= 3e-3 * max(1.0, scale)
+            if ln:
+                assert (ln3.float() - ln_out.float()).abs().max().item() <= 8e-3 * max(1.0, ln_out.float().abs().max().item())
 
 
 def test_fused_gffw_rejects_unsupported_shapes():

@@ -286,6 +286,8 @@ class TurtleNet(nn.Module):
         self.half_intermediates = True  # tf32 mode: FFN-side intermediates stored fp16 (same 10-bit mantissa as TF32)
         self.fuse_gffw = False          # tf32 mode: GatedFeedForward as the single kernel of csrc/gffw_fused.cu (parity-equal
                                         # to the three-kernel schedule, measured slower on B200: DESIGN.md section 3)
+        self.gffw_tail = False          # tf32 mode: depthwise + gate + project_out of GatedFeedForward as one kernel
+                                        # (turtle_gffw_tail; parity-equal, measured slower: DESIGN.md section 3)
         self._engine = None
 
     # -- public knobs ------------------------------------------------------------------

@@ -66,6 +66,7 @@ _SIGS = {
     "turtle_dwconv3x3_nchw_wgrad_workspace": ([_i32, _i32, _i32, _i32], C.c_longlong),
     "turtle_dwconv3x3_nchw_wgrad": ([_fp, _fp, _i32, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _fp], C.c_int),
     "turtle_gffw_fused": ([_fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _i32, _fp], C.c_int),
+    "turtle_gffw_tail": ([_fp, _fp, _fp, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _i32, _fp], C.c_int),
     "turtle_u8_to_frame": ([_fp, C.c_longlong, _fp, _i32, _i32, _i32, _i32, _fp], C.c_int),
     "turtle_frame_to_u8": ([_fp, _fp, C.c_longlong, _i32, _i32, _i32, _i32, _i32, _fp], C.c_int),
     "turtle_frame_metrics_workspace": ([_i32, _i32], C.c_longlong),

@@ -447,6 +447,323 @@ int launch_gffw(const GffwParams &p, cudaStream_t s) {
     return cudaGetLastError() == cudaSuccess ? TURTLE_OK : TURTLE_ELAUNCH;
 }
 
+
+// =================================================================================================================
+// The cheaper half of the fusion: depthwise 3x3 + gate as the A-PRODUCER of the project_out contraction.
+//
+//     x += W_out . ( gelu(u1) * u2 ),   [u1 | u2] = dw3x3(t),   t = the fp16 hidden map written by the project_in GEMM
+//
+// What it removes from the three-kernel schedule is the gated map's round trip (10 of the 42 bytes per channel-pixel)
+// and the project_out GEMM as a separate pass; what it keeps -- deliberately -- is the stand-alone depthwise kernel's
+// shape: halo boxes of the hidden map arrive by TMA (hardware zero padding) in a small mbarrier ring, eight compute warps
+// free-run over them with the 4-rows-per-thread sliding window of dwconv16.cu (no block barriers), and TWO CTAs fit per
+// SM (<= 110 KB of shared memory, <= 256 TMEM columns each), so the issue-bound depthwise arithmetic keeps most of the
+// occupancy it has on its own while the tensor pipe accumulates project_out over the chunks behind it.
+// =================================================================================================================
+constexpr int T_CW = 8;                         // compute warps
+constexpr int T_THREADS = 128 + T_CW * 32;
+constexpr int T_CK = 32;                        // channels per halo box
+constexpr int T_BOXB = HR * HC * T_CK * 2;      // 11520 B: one 10x18x32 fp16 halo box
+constexpr int T_STAGE = 2 * T_BOXB;             // u1 box + u2 box
+
+struct alignas(64) GffwTailParams {
+    CUtensorMap mapT, mapWout;
+    const __half *taps;        // [chunk][2][9][32]
+    float *x;
+    __half *ln_out;
+    const float *ln_w, *ln_b;
+    int B, H, W, hid, nch;
+    int tiles_x, tiles_y, total_tiles;
+};
+
+template <int C> struct TailPlan {
+    static constexpr int WOB = C <= 128 ? 2 : 1;
+    static constexpr int NSTG = C == 64 ? 3 : 2;
+    static constexpr bool TAPS_SMEM = C <= 128;              // all depthwise taps of the layer staged once per CTA
+    static constexpr int TAPS_MAX = TAPS_SMEM ? (C * 5 / 2) * 36 : 0;          // hid <= 2.5 C: [hid/32][2][9][32] fp16
+    static constexpr size_t smem = (size_t)NSTG * T_STAGE + A2_BYTES + (size_t)WOB * C * 128 + TAPS_MAX + 1024 + 1024;
+    static constexpr int TCOLS = C < 32 ? 32 : C;
+};
+
+template <int C>
+__global__ void __launch_bounds__(T_THREADS, 2) gffw_tail_kernel(const __grid_constant__ GffwTailParams p) {
+    constexpr int WOB = TailPlan<C>::WOB, NSTG = TailPlan<C>::NSTG, TCOLS = TailPlan<C>::TCOLS;
+    constexpr int WOUT_BYTES = C * 128;
+    constexpr int CH = C / 2;                        // output columns per epilogue warp
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t hfull[3], hempty[3], wout_full[2], wout_empty[2], a2_full[2], a2_empty[2], yfull, yempty;
+    __shared__ uint32_t tmem_base_sh;
+    __shared__ float2 lnstat[4][2][32];
+
+    const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t sA2 = smem0;
+    const uint32_t sWout = sA2 + A2_BYTES;
+    const uint32_t sH = sWout + WOB * WOUT_BYTES;            // halo ring (128 B aligned is enough: no swizzle)
+    const uint8_t *gH = smem_raw + (sH - smem_u32(smem_raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr bool TAPS_SMEM = TailPlan<C>::TAPS_SMEM;
+    const __half *taps = p.taps;
+    if (TAPS_SMEM) {                                        // constants: staged before anything else is waited for
+        uint8_t *st = smem_raw + (sH - smem_u32(smem_raw)) + NSTG * T_STAGE;
+        const int n16 = p.hid * 36 / 16;
+        for (int i = threadIdx.x; i < n16; i += T_THREADS)
+            reinterpret_cast<uint4 *>(st)[i] = __ldg(reinterpret_cast<const uint4 *>(p.taps) + i);
+        taps = reinterpret_cast<const __half *>(st);
+    }
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < NSTG; ++i) {
+            mbar_init(smem_u32(&hfull[i]), 1);
+            mbar_init(smem_u32(&hempty[i]), T_CW);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&wout_full[i]), 1);
+            mbar_init(smem_u32(&wout_empty[i]), 1);
+            mbar_init(smem_u32(&a2_full[i]), T_CW);
+            mbar_init(smem_u32(&a2_empty[i]), 1);
+        }
+        mbar_init(smem_u32(&yfull), 1);
+        mbar_init(smem_u32(&yempty), T_CW);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x == 32) {
+        tma_prefetch_map(&p.mapT);
+        tma_prefetch_map(&p.mapWout);
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_sh)), "n"(TCOLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_sh;
+    const int nch = p.nch;
+
+    if (warp == 0 && lane == 0) {
+        // =========================== TMA producer: halo boxes of the hidden map, W_out slabs ===========================
+        uint32_t g = 0, gp = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, tb = tile / (p.tiles_x * p.tiles_y);
+            for (int j = 0; j < nch; ++j, ++g) {
+                const uint32_t st = g % NSTG, fb = smem_u32(&hfull[st]);
+                mbar_wait(smem_u32(&hempty[st]), ((g / NSTG) & 1) ^ 1);
+                mbar_expect_tx(fb, T_STAGE);
+                tma_load_4d(sH + st * T_STAGE, &p.mapT, j * 32, tx * TW - 1, ty * TH - 1, tb, fb);
+                tma_load_4d(sH + st * T_STAGE + T_BOXB, &p.mapT, p.hid + j * 32, tx * TW - 1, ty * TH - 1, tb, fb);
+                if ((j & 1) == 0) {
+                    const uint32_t b = gp % WOB;
+                    mbar_wait(smem_u32(&wout_empty[b]), ((gp / WOB) & 1) ^ 1);
+                    mbar_expect_tx(smem_u32(&wout_full[b]), WOUT_BYTES);
+                    tma_load_2d(sWout + b * WOUT_BYTES, &p.mapWout, (j >> 1) * 64, 0, smem_u32(&wout_full[b]));
+                    ++gp;
+                }
+            }
+        }
+    } else if (warp == 1 && lane == 0) {
+        // =========================== MMA issuer: Y += A_chunk . W_out_chunk^T ===========================
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(C >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        uint32_t g = 0, gp = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            for (int j = 0; j < nch; ++j, ++g) {
+                if (j == 0) mbar_wait(smem_u32(&yempty), (it & 1) ^ 1);
+                if ((j & 1) == 0) mbar_wait(smem_u32(&wout_full[gp % WOB]), (gp / WOB) & 1);
+                const uint32_t s = g & 1;
+                mbar_wait(smem_u32(&a2_full[s]), (g >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a = sA2 + s * 64;
+                const uint32_t b = sWout + (gp % WOB) * WOUT_BYTES + (j & 1) * 64;
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    umma_f16(tmem_base, make_desc(a + k * 32), make_desc(b + k * 32), idesc, (j | k) ? 1u : 0u);
+                umma_commit(smem_u32(&a2_empty[s]));
+                if ((j & 1) || j + 1 == nch) {
+                    umma_commit(smem_u32(&wout_empty[gp % WOB]));
+                    ++gp;
+                }
+            }
+            umma_commit(smem_u32(&yfull));
+        }
+    } else if (warp >= 4) {
+        // =========================== compute warps: depthwise + gate -> A tile; tile epilogue ===========================
+        const int cw = warp - 4, ct = threadIdx.x - 128;
+        const int q = cw & 3, colh = cw >> 2;
+        const int c4 = ct & 7, col = (ct >> 3) & 15, half = ct >> 7;
+        const uint32_t toff = (uint32_t)(((half * 4) * HC + col) * T_CK + c4 * 4) * 2;       // window origin inside a box
+        uint32_t aoff[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = (half * 4 + i) * TW + col;
+            aoff[i] = (uint32_t)(m * 128 + ((((c4 >> 1) ^ (m & 7))) << 4) + (c4 & 1) * 8);
+        }
+        const int m_epi = q * 32 + lane;
+        uint32_t g = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+            const int tx = tile % p.tiles_x, ty = (tile / p.tiles_x) % p.tiles_y, tb = tile / (p.tiles_x * p.tiles_y);
+            for (int j = 0; j < nch; ++j, ++g) {
+                const uint2 *tp = reinterpret_cast<const uint2 *>(taps + (size_t)j * (2 * 9 * 32)) + c4;
+                uint2 wv0[9];
+                if (!TAPS_SMEM) {                     // global taps: the u1 set is requested before the halo is waited for
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) wv0[t] = __ldg(tp + t * 8);
+                }
+                const uint32_t st = g % NSTG;
+                mbar_wait(smem_u32(&hfull[st]), (g / NSTG) & 1);
+                const uint8_t *sbase = gH + st * T_STAGE + toff;
+                float4 out[4];
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    uint2 wv[9];
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) wv[t] = TAPS_SMEM ? tp[(s * 9 + t) * 8] : (s == 0 ? wv0[t] : __ldg(tp + (9 + t) * 8));
+                    const uint8_t *sb = sbase + s * T_BOXB;
+                    uint2 r[3][3];
+#pragma unroll
+                    for (int dx = 0; dx < 3; ++dx) {
+                        r[0][dx] = *reinterpret_cast<const uint2 *>(sb + (0 * HC + dx) * T_CK * 2);
+                        r[1][dx] = *reinterpret_cast<const uint2 *>(sb + (1 * HC + dx) * T_CK * 2);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx)
+                            r[2][dx] = *reinterpret_cast<const uint2 *>(sb + ((i + 2) * HC + dx) * T_CK * 2);
+                        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) fma4h(a, r[ky][kx], wv[ky * 3 + kx]);
+                        if (s == 0) {
+                            const float2 g0 = gelu_fast2(make_float2(a.x, a.y)), g1 = gelu_fast2(make_float2(a.z, a.w));
+                            out[i] = make_float4(g0.x, g0.y, g1.x, g1.y);
+                        } else {
+                            const float2 m0 = f2_mul(make_float2(out[i].x, out[i].y), make_float2(a.x, a.y));
+                            const float2 m1 = f2_mul(make_float2(out[i].z, out[i].w), make_float2(a.z, a.w));
+                            out[i] = make_float4(m0.x, m0.y, m1.x, m1.y);
+                        }
+#pragma unroll
+                        for (int dx = 0; dx < 3; ++dx) {
+                            r[0][dx] = r[1][dx];
+                            r[1][dx] = r[2][dx];
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&hempty[st]));               // this warp is done with the halo stage
+                const uint32_t s2 = g & 1;
+                mbar_wait(smem_u32(&a2_empty[s2]), ((g >> 1) & 1) ^ 1);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    asm volatile("st.shared.v2.b32 [%0], {%1,%2};" ::"r"(sA2 + (aoff[i] ^ (s2 ? 64u : 0u))),
+                                 "r"(pack2(out[i].x, out[i].y)), "r"(pack2(out[i].z, out[i].w))
+                                 : "memory");
+                bulk_fence();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&a2_full[s2]));
+            }
+            // -------- tile epilogue: Y + residual -> x (in place) [+ LayerNorm -> fp16] --------
+            mbar_wait(smem_u32(&yfull), it & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int py = ty * TH + (m_epi >> 4), px = tx * TW + (m_epi & 15);
+            const bool live = py < p.H && px < p.W;
+            const long long pix = ((long long)tb * p.H + py) * p.W + px;
+            float *xr = p.x + pix * C + colh * CH;
+            const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + colh * CH;
+            float mean = 0.f, M2 = 0.f;
+#pragma unroll
+            for (int c0 = 0; c0 < CH; c0 += 16) {
+                float v[16];
+                tmem_ld16(trow + c0, v);
+                float cs = 0.f;
+                if (live) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float4 r4 = *reinterpret_cast<const float4 *>(xr + c0 + 4 * e);
+                        v[4 * e] += r4.x; v[4 * e + 1] += r4.y; v[4 * e + 2] += r4.z; v[4 * e + 3] += r4.w;
+                        *reinterpret_cast<float4 *>(xr + c0 + 4 * e) = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                        cs += (v[4 * e] + v[4 * e + 1]) + (v[4 * e + 2] + v[4 * e + 3]);
+                    }
+                }
+                if (p.ln_out) {
+                    uint32_t rr[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) rr[e] = __float_as_uint(v[e]);
+                    asm volatile(
+                        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(trow + c0),
+                        "r"(rr[0]), "r"(rr[1]), "r"(rr[2]), "r"(rr[3]), "r"(rr[4]), "r"(rr[5]), "r"(rr[6]), "r"(rr[7]), "r"(rr[8]),
+                        "r"(rr[9]), "r"(rr[10]), "r"(rr[11]), "r"(rr[12]), "r"(rr[13]), "r"(rr[14]), "r"(rr[15])
+                        : "memory");
+                    const float cm = cs * (1.0f / 16.0f);
+                    float cM2 = 0.f;
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) cM2 = fmaf(v[e] - cm, v[e] - cm, cM2);
+                    const float cnt = (float)c0, tot = cnt + 16.0f, delta = cm - mean;
+                    mean = fmaf(delta, 16.0f / tot, mean);
+                    M2 += cM2 + delta * delta * (cnt * 16.0f / tot);
+                }
+            }
+            if (p.ln_out) {
+                tmem_wait_st();
+                lnstat[q][colh][lane] = make_float2(mean, M2);
+                named_bar(2 + q, 64);                // the two warps that share these 32 rows
+                const float2 s0 = lnstat[q][0][lane], s1 = lnstat[q][1][lane];
+                const float mu = 0.5f * (s0.x + s1.x);
+                const float var = (s0.y + s1.y + (float)CH * ((s0.x - mu) * (s0.x - mu) + (s1.x - mu) * (s1.x - mu))) * (1.0f / (float)C);
+                const float rstd = rsqrtf(var + 1e-5f);
+                __half *lr = p.ln_out + pix * C + colh * CH;
+#pragma unroll
+                for (int c0 = 0; c0 < CH; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(trow + c0, v);
+                    if (live) {
+                        uint32_t h[8];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float4 w4 = __ldg(reinterpret_cast<const float4 *>(p.ln_w + colh * CH + c0 + 4 * e));
+                            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.ln_b + colh * CH + c0 + 4 * e));
+                            h[2 * e] = pack2(fmaf((v[4 * e] - mu) * rstd, w4.x, b4.x), fmaf((v[4 * e + 1] - mu) * rstd, w4.y, b4.y));
+                            h[2 * e + 1] = pack2(fmaf((v[4 * e + 2] - mu) * rstd, w4.z, b4.z), fmaf((v[4 * e + 3] - mu) * rstd, w4.w, b4.w));
+                        }
+                        *reinterpret_cast<uint4 *>(lr + c0) = make_uint4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<uint4 *>(lr + c0 + 8) = make_uint4(h[4], h[5], h[6], h[7]);
+                    }
+                }
+                named_bar(2 + q, 64);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&yempty));
+        }
+    }
+    __syncwarp();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TCOLS) : "memory");
+}
+
+template <int C>
+int launch_gffw_tail(const GffwTailParams &p, cudaStream_t s) {
+    const size_t smem = TailPlan<C>::smem;
+    static bool configured_[TURTLE_MAX_DEVICES] = {};
+    static int nsm_[TURTLE_MAX_DEVICES];
+    const int dev_ = turtle_device();
+    if (!configured_[dev_]) {
+        if (cudaFuncSetAttribute(gffw_tail_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+            cudaGetLastError();
+            return TURTLE_ELAUNCH;
+        }
+        cudaDeviceGetAttribute(&nsm_[dev_], cudaDevAttrMultiProcessorCount, dev_);
+        configured_[dev_] = true;
+    }
+    int grid = 2 * nsm_[dev_];
+    if (grid > p.total_tiles) grid = p.total_tiles;
+    gffw_tail_kernel<C><<<grid, T_THREADS, smem, s>>>(p);
+    return cudaGetLastError() == cudaSuccess ? TURTLE_OK : TURTLE_ELAUNCH;
+}
+
 }  // namespace
 
 extern "C" int turtle_gffw_fused(const void *xn16, const void *w_in16, const void *taps16, const void *w_out16, float *x,
@@ -489,4 +806,39 @@ extern "C" int turtle_gffw_fused(const void *xn16, const void *w_in16, const voi
     p.total_tiles = (int)tiles;
     cudaStream_t s = as_stream(stream);
     return C == 64 ? launch_gffw<64>(p, s) : C == 128 ? launch_gffw<128>(p, s) : launch_gffw<256>(p, s);
+}
+
+extern "C" int turtle_gffw_tail(const void *t16, const void *taps16, const void *w_out16, float *x, void *ln_out16,
+                                const float *ln_w, const float *ln_b, int B, int H, int W, int C, int hid, void *stream) {
+    if (!t16 || !taps16 || !w_out16 || !x || B < 1 || H < 1 || W < 1) return TURTLE_EINVAL;
+    if (ln_out16 && (!ln_w || !ln_b)) return TURTLE_EINVAL;
+    if ((C != 64 && C != 128 && C != 256) || hid < 32 || hid % 32) return TURTLE_ENOTSUP;
+    if ((((uintptr_t)t16 | (uintptr_t)w_out16 | (uintptr_t)x | (uintptr_t)taps16 | (uintptr_t)ln_out16) & 15)) return TURTLE_ENOTSUP;
+    if (C <= 128 && hid * 36 > (C * 5 / 2) * 36) return TURTLE_ENOTSUP;          // the staged taps are sized for hid <= 2.5 C
+    GffwTailParams p{};
+    {
+        uint64_t dims[4] = {(uint64_t)(2 * hid), (uint64_t)W, (uint64_t)H, (uint64_t)B};
+        uint64_t str[3] = {(uint64_t)hid * 4, (uint64_t)hid * 4 * W, (uint64_t)hid * 4 * W * H};
+        uint32_t box[4] = {T_CK, HC, HR, 1};
+        if (!turtle_get_tmap2(&p.mapT, t16, 4, dims, str, box, 0, 1)) return TURTLE_ENOTSUP;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)hid, (uint64_t)C};
+        uint64_t str[1] = {(uint64_t)hid * 2};
+        uint32_t box[2] = {64, (uint32_t)C};
+        if (!turtle_get_tmap2(&p.mapWout, w_out16, 2, dims, str, box, 1, 1)) return TURTLE_ENOTSUP;
+    }
+    p.taps = reinterpret_cast<const __half *>(taps16);
+    p.x = x;
+    p.ln_out = reinterpret_cast<__half *>(ln_out16);
+    p.ln_w = ln_w;
+    p.ln_b = ln_b;
+    p.B = B; p.H = H; p.W = W; p.hid = hid; p.nch = hid / 32;
+    p.tiles_x = (W + TW - 1) / TW;
+    p.tiles_y = (H + TH - 1) / TH;
+    const long long tiles = (long long)p.tiles_x * p.tiles_y * B;
+    if (tiles >= (1LL << 30)) return TURTLE_ENOTSUP;
+    p.total_tiles = (int)tiles;
+    cudaStream_t s = as_stream(stream);
+    return C == 64 ? launch_gffw_tail<64>(p, s) : C == 128 ? launch_gffw_tail<128>(p, s) : launch_gffw_tail<256>(p, s);
 }

@@ -349,6 +349,16 @@ class FrameEngine:
             t = self.ws.get("wide16", P, hid2, dtype=torch.float16)
             self.conv1x1(_ptr(xn), c, c, pre + "project_in.weight", _ptr(t), hid2, P, hid2,
                          bias=self._w(pre + "project_in.bias"), a16=True, o16=True)
+            if (self.gffw_tail and c in (64, 128, 256) and hid % 32 == 0 and hid * 2 <= 5 * c
+                    and (pre + "dwconv.bias") not in self._sd and (pre + "project_out.bias") not in self._sd):
+                # depthwise + gate as the A-producer of project_out: the gated map never reaches HBM (csrc/gffw_fused.cu)
+                lt = self.ln_target(P, c, ln) if ln else None
+                self._meta = (P * (2 * hid2 + c * (4 + 4 + (2 if ln else 0))) + 2 * hid * c, 2 * P * c * hid + 2 * 9 * P * hid2)
+                self._call("turtle_gffw_tail", _ptr(t), _ptr(self._w(pre + "dwconv.weight", "dwgffw")),
+                           _ptr(self._w(pre + "project_out.weight", "gemm16")), _ptr(x), lt[0] if lt else None,
+                           _ptr(self._w(ln + "body.weight")) if lt else None, _ptr(self._w(ln + "body.bias")) if lt else None,
+                           B, H, W, c, hid, self.stream)
+                return
             g = self.ws.get("dw16", P, hid, dtype=torch.float16)
             self._meta = (2 * P * (hid2 + hid), 2 * 9 * P * hid2)
             self._call("turtle_dwconv3x3", _ptr(t), hid2, _ptr(self._w(pre + "dwconv.weight", "dw16")),
@@ -761,7 +771,8 @@ class FrameEngine:
         m = self.model
         key = (tuple(inp.shape), inp.device.index, m.precision, bool(getattr(m, "half_intermediates", True)),
                bool(getattr(m, "fuse_layernorm", True)), bool(getattr(m, "sab_front_half", True)),
-               bool(getattr(m, "fuse_gffw", False)), tuple((r.serial, r.pos) for r in rings))
+               bool(getattr(m, "fuse_gffw", False)), bool(getattr(m, "gffw_tail", False)),
+               tuple((r.serial, r.pos) for r in rings))
         ent = self.graphs.get(key)
         if ent is None:
             if key not in self._graph_seen:
@@ -828,6 +839,7 @@ class FrameEngine:
         self.fuse_ln = bool(getattr(m, "fuse_layernorm", True))
         self.sab_front_half = bool(getattr(m, "sab_front_half", True))
         self.fuse_gffw = (bool(getattr(m, "fuse_gffw", False)) or os.environ.get("TURTLE_FUSE_GFFW", "0") == "1")
+        self.gffw_tail = (bool(getattr(m, "gffw_tail", False)) or os.environ.get("TURTLE_GFFW_TAIL", "0") == "1")
         self.gram_ctas = int(os.environ.get("TURTLE_GRAM_CTAS", "296"))      # pixel splits x heads of the Gram kernel
         self._fused = None
         self.trace = {} if getattr(m, "record_trace", False) else None
