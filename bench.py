@@ -331,6 +331,75 @@ def train_arm(args, rank, world, local_rank, dev, dist, barrier):
     return 0
 
 
+def tiled_arm(args, rank, world, local_rank, dev, dist, barrier):
+    """the reference's tiled inference (INF:172-246, the defaults of its app: tile 320, overlap 128 =
+    24 tiles per 1280x720 frame) with the per-tile histories resident in HBM, all tiles of a frame restored by ONE batched
+    forward between the fused gather / blend kernels.  A step = one 1280x720 frame; the frame pair is uploaded from pinned
+    host memory and the blended frame is read back inside every timed step."""
+    import turtlevsr_b200.tiling as tl
+    from turtlevsr_b200 import capi
+    net, _ = build_model(args.precision, dev)
+    net.enable_cuda_graphs(not args.no_graphs, max_graphs=64)
+    K, Wm = args.steps, max(args.warmup, 3)
+    g = torch.Generator().manual_seed(3000 + rank)
+    pool = 6
+    host = torch.rand(pool, 1, 3, H720, W720, generator=g).pin_memory()
+    out_host = torch.empty(1, 3, H720, W720).pin_memory()
+    dk = dv = None
+    prev = host[0].to(dev, non_blocking=True)
+
+    def one(j):
+        nonlocal dk, dv, prev
+        cur = host[j % pool].to(dev, non_blocking=True)
+        out, dk, dv = tl.run_inference_patched(prev, cur, net, dev, 320, 128, prev_patch_dict_k=dk, prev_patch_dict_v=dv,
+                                               model_type="t1", batch_tiles=True)
+        out_host.copy_(out[..., :H720, :W720], non_blocking=True)
+        prev = cur
+        return out
+
+    with torch.no_grad():
+        from turtlevsr_b200.history import RING_PERIOD
+        primed = (3 * RING_PERIOD + 4) if not args.no_graphs else 0
+        for j in range(primed + Wm):
+            one(j)
+        barrier()
+        n0 = capi.launch_count
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local_rank) as clk:
+            e0.record()
+            for j in range(K):
+                one(primed + Wm + j)
+            e1.record()
+            barrier()
+    ms = e0.elapsed_time(e1)
+    launches = capi.launch_count - n0
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    if rank == 0:
+        ntiles = len([k for k in dk if k != tl.BATCH_KEY])
+        fps = world * K / (ms * 1e-3)
+        line = {"metric": "tiled frames/sec at 1280x720 (tile 320, overlap 128)", "value": fps, "unit": "frames/s",
+                "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD + f", tiled: {ntiles} tiles of 320x320 (overlap 128) per frame, one history "
+                                                  "per tile resident in HBM, all tiles as one batch",
+                           "parallelism": f"clip-sharded x{world}", "precision_mode": args.precision,
+                           "launch": "CUDA-graph replay" if not args.no_graphs else "eager launches",
+                           "l2": "per-frame working set >> 126 MB L2"},
+                "clocks": clk.summary(),
+                "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 3 * H720 * W720 * 4,
+                        "d2h_bytes_per_step": 3 * H720 * W720 * 4},
+                "gpu_launches": launches,
+                "pixels_restored_per_frame": ntiles * 320 * 320}
+        emit(line)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -342,8 +411,9 @@ def main():
     ap.add_argument("--width", type=int, default=W720)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="issue every frame launch by launch (no CUDA-graph replay)")
-    ap.add_argument("--workload", default="infer", choices=["infer", "train"],
-                    help="infer = the BASELINE metric (default); train = cfg 5's DDP training step (secondary line)")
+    ap.add_argument("--workload", default="infer", choices=["infer", "train", "tiled"],
+                    help="infer = the BASELINE metric (default); train = cfg 5's DDP training step; tiled = the reference's "
+                         "tiled inference with device-resident per-tile histories (secondary lines)")
     args = ap.parse_args()
 
     _claim_stdout()
@@ -386,6 +456,8 @@ def main():
     from turtlevsr_b200 import capi
     if args.workload == "train":
         return train_arm(args, rank, world, local_rank, dev, dist, barrier)
+    if args.workload == "tiled":
+        return tiled_arm(args, rank, world, local_rank, dev, dist, barrier)
     net, opt = build_model(args.precision, dev)
     use_graphs = not args.no_graphs
     net.enable_cuda_graphs(use_graphs)
