@@ -176,6 +176,23 @@ int turtle_chan_softmax(const float *gpart, const float *sqq, const float *sqk, 
 int turtle_chan_fold(const float *Pm, const float *Wo, int nseg, int heads, int ch, float *M, int round_tf32,
                      void *stream);
 
+/* Batched forms of the three steps above: B batch elements per launch (the tiles of tiled inference, training
+ * batches), element b of every operand at a fixed stride from element 0, so the launch count of a channel-attention
+ * block no longer scales with B.
+ *   gram_b:    q_bs / k_bs = element strides of the q / k maps between batch elements; gpart [B][nsplit,heads,ch,ch] at
+ *              g_bs floats, sqq / sqk [B][nsplit,C] at s_bs floats (one call per key segment, as turtle_chan_gram);
+ *   softmax_b: gpart [B][nseg,nsplit,heads,ch,ch] at g_bs, sqq / sqk [B][nseg,nsplit,C] at s_bs; Pout [B,heads,ch,nseg*ch]
+ *              and inv_knorm [B,nseg,C] dense;
+ *   fold_b:    Pm [B,heads,ch,nseg*ch] -> M [B,C,nseg*C] dense. */
+int turtle_chan_gram_b(const float *q, int ldq, int q_hs, int64_t q_bs, const float *k, int ldk, int k_hs, int64_t k_bs,
+                       int64_t P, int heads, int ch, int nsplit, float *gpart, float *sqq, float *sqk, int64_t g_bs,
+                       int64_t s_bs, int B, int mode, void *stream);
+int turtle_chan_softmax_b(const float *gpart, const float *sqq, const float *sqk, const int32_t *seg_prenorm,
+                          const float *temperature, int nseg, int nsplit, int heads, int ch, float *Pout, float *inv_knorm,
+                          int64_t g_bs, int64_t s_bs, int B, void *stream);
+int turtle_chan_fold_b(const float *Pm, const float *Wo, int nseg, int heads, int ch, float *M, int round_tf32, int B,
+                       void *stream);
+
 /* y[p, h*y_hs + j] = x[p, h*x_hs + j] * s[h*ch + j]  (s==NULL: copy).  Used to push the normalised
  * key rows / raw value rows of a frame into the history ring (T1:272-273, 286). */
 int turtle_scale_cols(const float *x, int ldx, int x_hs, const float *s, float *y, int ldy, int y_hs, int64_t P,

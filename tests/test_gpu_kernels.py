@@ -180,6 +180,41 @@ def test_channel_attention_chain(heads, ch, S, mode):
     assert (xd.cpu() - want).abs().max() < (5e-5 if mode == capi.FP32 else 1e-3)
 
 
+@pytest.mark.parametrize("mode", [capi.FP32, capi.TF32])
+@pytest.mark.parametrize("heads,ch,S,B", [(4, 64, 2, 3), (2, 16, 1, 5), (1, 64, 3, 2)])
+def test_channel_attention_batched_equals_per_element(heads, ch, S, B, mode):
+    """turtle_chan_{gram,softmax,fold}_b over B batch elements in one launch each == the per-element entry points."""
+    c, P, nsplit = heads * ch, 520, 3
+    maps = [rnd(B, P, 3 * c, seed=10 + s).cuda() for s in range(S)]          # segment s: [B, P, 3c]; q from the last
+    temp, Wo = (torch.rand(heads) + 0.5).cuda(), (rnd(c, c, seed=7) / c ** 0.5).cuda()
+    flags = torch.zeros(S, dtype=torch.int32, device="cuda")
+    g = torch.zeros(B, S, nsplit, heads, ch, ch, device="cuda")
+    sqq, sqk = torch.zeros(B, S, nsplit, c, device="cuda"), torch.zeros(B, S, nsplit, c, device="cuda")
+    qd = maps[-1]
+    for s in range(S):
+        call("turtle_chan_gram_b", qd.data_ptr(), 3 * c, ch, P * 3 * c, maps[s].data_ptr() + 4 * c, 3 * c, ch, P * 3 * c, P, heads,
+             ch, nsplit, g[0, s].data_ptr(), sqq[0, s].data_ptr(), sqk[0, s].data_ptr(), g[0].numel(), sqq[0].numel(), B, mode,
+             stream())
+    Pm, inv = torch.empty(B, heads, ch, S * ch, device="cuda"), torch.empty(B, S, c, device="cuda")
+    call("turtle_chan_softmax_b", g.data_ptr(), sqq.data_ptr(), sqk.data_ptr(), flags.data_ptr(), temp.data_ptr(), S, nsplit,
+         heads, ch, Pm.data_ptr(), inv.data_ptr(), g[0].numel(), sqq[0].numel(), B, stream())
+    M = torch.empty(B, c, S * c, device="cuda")
+    call("turtle_chan_fold_b", Pm.data_ptr(), Wo.data_ptr(), S, heads, ch, M.data_ptr(), 0, B, stream())
+    for b in range(B):
+        g1 = torch.zeros(S, nsplit, heads, ch, ch, device="cuda")
+        q1, k1 = torch.zeros(S, nsplit, c, device="cuda"), torch.zeros(S, nsplit, c, device="cuda")
+        for s in range(S):
+            call("turtle_chan_gram", qd[b].data_ptr(), 3 * c, ch, maps[s][b].data_ptr() + 4 * c, 3 * c, ch, P, heads, ch, nsplit,
+                 g1[s].data_ptr(), q1[s].data_ptr(), k1[s].data_ptr(), mode, stream())
+        P1, i1 = torch.empty(heads, ch, S * ch, device="cuda"), torch.empty(S, c, device="cuda")
+        call("turtle_chan_softmax", g1.data_ptr(), q1.data_ptr(), k1.data_ptr(), flags.data_ptr(), temp.data_ptr(), S, nsplit,
+             heads, ch, P1.data_ptr(), i1.data_ptr(), stream())
+        M1 = torch.empty(c, S * c, device="cuda")
+        call("turtle_chan_fold", P1.data_ptr(), Wo.data_ptr(), S, heads, ch, M1.data_ptr(), 0, stream())
+        assert torch.equal(g[b], g1) and torch.equal(sqq[b], q1) and torch.equal(sqk[b], k1)
+        assert torch.equal(Pm[b], P1) and torch.equal(inv[b], i1) and torch.equal(M[b], M1)
+
+
 @pytest.mark.parametrize("bias", [False, True])
 @pytest.mark.parametrize("ws,D", [(4, 64), (8, 32), (16, 16), (4, 20)])
 def test_sab_window_reduce(ws, D, bias):

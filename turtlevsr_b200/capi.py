@@ -49,6 +49,10 @@ _SIGS = {
                          C.c_int),
     "turtle_chan_softmax": ([_fp, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _fp, _fp, _fp], C.c_int),
     "turtle_chan_fold": ([_fp, _fp, _i32, _i32, _i32, _fp, _i32, _fp], C.c_int),
+    "turtle_chan_gram_b": ([_fp, _i32, _i32, _i64, _fp, _i32, _i32, _i64, _i64, _i32, _i32, _i32, _fp, _fp, _fp, _i64, _i64,
+                            _i32, _i32, _fp], C.c_int),
+    "turtle_chan_softmax_b": ([_fp, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _fp, _fp, _i64, _i64, _i32, _fp], C.c_int),
+    "turtle_chan_fold_b": ([_fp, _fp, _i32, _i32, _i32, _fp, _i32, _i32, _fp], C.c_int),
     "turtle_scale_cols": ([_fp, _i32, _i32, _fp, _fp, _i32, _i32, _i64, _i32, _i32, _fp], C.c_int),
     "turtle_sab_window_reduce": ([_fp, _i32, _fp, _fp, _fp, _i64, _i32, _i32, _i32, _i32, _i32, _fp], C.c_int),
     "turtle_sab_window_reduce_h16": ([_fp, _i32, _fp, _fp, _fp, _i64, _i32, _i32, _i32, _i32, _i32, _fp], C.c_int),

@@ -14,8 +14,11 @@ template <int CH>
 __global__ void __launch_bounds__(256) gram64_kernel(const float *__restrict__ q, int ldq, int q_hs,
                                                      const float *__restrict__ k, int ldk, int k_hs, int64_t P,
                                                      int heads, int64_t chunk, float *__restrict__ gpart,
-                                                     float *__restrict__ sqq, float *__restrict__ sqk) {
+                                                     float *__restrict__ sqq, float *__restrict__ sqk, int64_t q_bs,
+                                                     int64_t k_bs, int64_t g_bs, int64_t s_bs) {
     static_assert(CH == 64, "fast path is for 64-channel heads");
+    q += blockIdx.z * q_bs; k += blockIdx.z * k_bs;                  // batch element = blockIdx.z
+    gpart += blockIdx.z * g_bs; sqq += blockIdx.z * s_bs; sqk += blockIdx.z * s_bs;
     __shared__ __align__(16) float qs[GT][CH];
     __shared__ __align__(16) float ks[GT][CH];
     const int tid = threadIdx.x, h = blockIdx.y, s = blockIdx.x;
@@ -84,7 +87,10 @@ __global__ void __launch_bounds__(256) gram64_kernel(const float *__restrict__ q
 __global__ void __launch_bounds__(256) gram_generic_kernel(const float *__restrict__ q, int ldq, int q_hs,
                                                            const float *__restrict__ k, int ldk, int k_hs, int64_t P,
                                                            int heads, int ch, int64_t chunk, float *__restrict__ gpart,
-                                                           float *__restrict__ sqq, float *__restrict__ sqk) {
+                                                           float *__restrict__ sqq, float *__restrict__ sqk, int64_t q_bs,
+                                                           int64_t k_bs, int64_t g_bs, int64_t s_bs) {
+    q += blockIdx.z * q_bs; k += blockIdx.z * k_bs;
+    gpart += blockIdx.z * g_bs; sqq += blockIdx.z * s_bs; sqk += blockIdx.z * s_bs;
     __shared__ float qs[GT][64];
     __shared__ float ks[GT][64];
     const int tid = threadIdx.x, h = blockIdx.y, s = blockIdx.x;
@@ -137,9 +143,15 @@ __global__ void __launch_bounds__(1024) chan_softmax_kernel(const float *__restr
                                                             const int32_t *__restrict__ prenorm,
                                                             const float *__restrict__ temperature, int nseg,
                                                             int nsplit, int heads, int ch, float *__restrict__ Pout,
-                                                            float *__restrict__ inv_knorm) {
+                                                            float *__restrict__ inv_knorm, int64_t g_bs, int64_t s_bs) {
     pdl_trigger();
     pdl_wait();
+    {   // batch element = blockIdx.z; Pout / inv_knorm are dense per element
+        const int64_t bz = blockIdx.z;
+        gpart += bz * g_bs; sqq += bz * s_bs; sqk += bz * s_bs;
+        Pout += bz * (int64_t)heads * ch * nseg * ch;
+        if (inv_knorm) inv_knorm += bz * (int64_t)nseg * heads * ch;
+    }
     __shared__ float ps[8][4][64], pk[8][4][64], red[32];
     const int i = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
     const int C = heads * ch, ncol = nseg * ch;
@@ -214,8 +226,10 @@ __global__ void __launch_bounds__(256) chan_fold_tile_kernel(const float *__rest
     constexpr int CH = 64;
     __shared__ float ws[CH][CH + 4];      // [o][i]  (+4: conflict-free column reads)
     __shared__ float pt[CH][CH];          // [i][j]
-    const int ot = blockIdx.x, h = blockIdx.y, seg = blockIdx.z, tid = threadIdx.x;
+    const int ot = blockIdx.x, h = blockIdx.y, seg = blockIdx.z % nseg, bz = blockIdx.z / nseg, tid = threadIdx.x;
     const int C = heads * CH, ncolP = nseg * CH, K = nseg * C;
+    Pm += (int64_t)bz * heads * CH * ncolP;                           // per batch element: P [heads, ch, nseg*ch] ...
+    const int64_t m_b = (int64_t)bz * C * K;                          // ... and M [C, nseg*C]
     for (int e = tid; e < CH * CH / 4; e += 256) {
         const int r = e >> 4, c4 = (e & 15) * 4;
         const float4 w4 = __ldg(reinterpret_cast<const float4 *>(Wo + (int64_t)(ot * CH + r) * C + h * CH + c4));
@@ -240,7 +254,7 @@ __global__ void __launch_bounds__(256) chan_fold_tile_kernel(const float *__rest
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        const int64_t idx = (int64_t)(ot * CH + o0 + r) * K + (int64_t)seg * C + h * CH + j0;
+        const int64_t idx = m_b + (int64_t)(ot * CH + o0 + r) * K + (int64_t)seg * C + h * CH + j0;
         if (rnd == 2) {                                   // fp16 weights for kind::f16
             const __half2 h0 = __floats2half2_rn(acc[r].x, acc[r].y), h1 = __floats2half2_rn(acc[r].z, acc[r].w);
             *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(M) + idx) =
@@ -257,41 +271,71 @@ __global__ void chan_fold_scalar_kernel(const float *__restrict__ Pm, const floa
     const int C = heads * ch, ncolP = nseg * ch, K = nseg * C;
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (int64_t)C * K) return;
+    Pm += (int64_t)blockIdx.y * heads * ch * ncolP;
+    const int64_t m_b = (int64_t)blockIdx.y * C * K;
     int col = (int)(idx % K), o = (int)(idx / K);
     int seg = col / C, r = col - seg * C, h = r / ch, j = r - h * ch;
     const float *wp = Wo + (int64_t)o * C + h * ch;
     const float *pp = Pm + ((int64_t)h * ch) * ncolP + seg * ch + j;
     float acc = 0.f;
     for (int i = 0; i < ch; ++i) acc = fmaf(__ldg(wp + i), __ldg(pp + (int64_t)i * ncolP), acc);
-    if (rnd == 2) reinterpret_cast<__half *>(M)[idx] = __float2half_rn(acc);
-    else M[idx] = rnd ? rna_tf32(acc) : acc;
+    if (rnd == 2) reinterpret_cast<__half *>(M)[m_b + idx] = __float2half_rn(acc);
+    else M[m_b + idx] = rnd ? rna_tf32(acc) : acc;
 }
 
 }  // namespace
 
-int turtle_chan_gram_tc(const float *q, int ldq, int q_hs, const float *k, int ldk, int k_hs, int64_t P, int heads,
-                        int ch, int nsplit, float *gpart, float *sqq, float *sqk, int h16, void *stream);
+int turtle_chan_gram_tc(const float *q, int ldq, int q_hs, long long q_bs, const float *k, int ldk, int k_hs, long long k_bs,
+                        int64_t P, int heads, int ch, int nsplit, float *gpart, float *sqq, float *sqk, long long g_bs,
+                        long long s_bs, int B, int h16, void *stream);
+
+// Batched forms: B batch elements per launch (grid.z), element b of every operand at a fixed stride from element 0.
+//   q_bs / k_bs: element strides of the q and k maps (fp32 or fp16 elements);  gpart: [B][nsplit, heads, ch, ch] at
+//   g_bs floats;  sqq / sqk: [B][nsplit, C] at s_bs floats.  B = 1 ignores the strides.
+extern "C" int turtle_chan_gram_b(const float *q, int ldq, int q_hs, int64_t q_bs, const float *k, int ldk, int k_hs,
+                                  int64_t k_bs, int64_t P, int heads, int ch, int nsplit, float *gpart, float *sqq,
+                                  float *sqk, int64_t g_bs, int64_t s_bs, int B, int mode, void *stream) {
+    if (!q || !k || !gpart || !sqq || !sqk || heads < 1 || ch < 4 || ch > 64 || (ch & 3) || nsplit < 1 || P < 1 || B < 1 ||
+        B > 65535)
+        return TURTLE_EINVAL;
+    int64_t chunk = cdiv64(cdiv64(P, nsplit), GT) * GT;
+    dim3 grid(nsplit, heads, B);
+    if (mode == 2)      // q,k are fp16 (pitches in halves): tensor-core kernel only
+        return turtle_chan_gram_tc(q, ldq, q_hs, q_bs, k, ldk, k_hs, k_bs, P, heads, ch, nsplit, gpart, sqq, sqk, g_bs, s_bs, B, 1,
+                                   stream);
+    if (mode == TURTLE_TF32) {
+        int r = turtle_chan_gram_tc(q, ldq, q_hs, q_bs, k, ldk, k_hs, k_bs, P, heads, ch, nsplit, gpart, sqq, sqk, g_bs, s_bs, B,
+                                    0, stream);
+        if (r != TURTLE_ENOTSUP) return r;
+    }
+    if (ch == 64 && !(ldq & 3) && !(ldk & 3) && !(q_hs & 3) && !(k_hs & 3) && !(q_bs & 3) && !(k_bs & 3) &&
+        !(((uintptr_t)q | (uintptr_t)k) & 15))
+        gram64_kernel<64><<<grid, 256, 0, as_stream(stream)>>>(q, ldq, q_hs, k, ldk, k_hs, P, heads, chunk, gpart, sqq,
+                                                              sqk, q_bs, k_bs, g_bs, s_bs);
+    else
+        gram_generic_kernel<<<grid, 256, 0, as_stream(stream)>>>(q, ldq, q_hs, k, ldk, k_hs, P, heads, ch, chunk, gpart,
+                                                                sqq, sqk, q_bs, k_bs, g_bs, s_bs);
+    TURTLE_CHECK_LAUNCH();
+    return TURTLE_OK;
+}
 
 extern "C" int turtle_chan_gram(const float *q, int ldq, int q_hs, const float *k, int ldk, int k_hs, int64_t P,
                                 int heads, int ch, int nsplit, float *gpart, float *sqq, float *sqk, int mode,
                                 void *stream) {
-    if (!q || !k || !gpart || !sqq || !sqk || heads < 1 || ch < 4 || ch > 64 || (ch & 3) || nsplit < 1 || P < 1)
+    return turtle_chan_gram_b(q, ldq, q_hs, 0, k, ldk, k_hs, 0, P, heads, ch, nsplit, gpart, sqq, sqk, 0, 0, 1, mode, stream);
+}
+
+// gpart [B][nseg, nsplit, heads, ch, ch] at g_bs floats, sqq / sqk [B][nseg, nsplit, C] at s_bs floats;
+// Pout [B, heads, ch, nseg*ch] and inv_knorm [B, nseg, C] dense.
+extern "C" int turtle_chan_softmax_b(const float *gpart, const float *sqq, const float *sqk, const int32_t *seg_prenorm,
+                                     const float *temperature, int nseg, int nsplit, int heads, int ch, float *Pout,
+                                     float *inv_knorm, int64_t g_bs, int64_t s_bs, int B, void *stream) {
+    if (!gpart || !sqq || !sqk || !seg_prenorm || !temperature || !Pout || nseg < 1 || nseg > 8 || ch > 64 || nseg * ch > 512 ||
+        B < 1 || B > 65535)
         return TURTLE_EINVAL;
-    int64_t chunk = cdiv64(cdiv64(P, nsplit), GT) * GT;
-    dim3 grid(nsplit, heads);
-    if (mode == 2)      // q,k are fp16 (pitches in halves): tensor-core kernel only
-        return turtle_chan_gram_tc(q, ldq, q_hs, k, ldk, k_hs, P, heads, ch, nsplit, gpart, sqq, sqk, 1, stream);
-    if (mode == TURTLE_TF32) {
-        int r = turtle_chan_gram_tc(q, ldq, q_hs, k, ldk, k_hs, P, heads, ch, nsplit, gpart, sqq, sqk, 0, stream);
-        if (r != TURTLE_ENOTSUP) return r;
-    }
-    if (ch == 64 && !(ldq & 3) && !(ldk & 3) && !(q_hs & 3) && !(k_hs & 3) &&
-        !(((uintptr_t)q | (uintptr_t)k) & 15))
-        gram64_kernel<64><<<grid, 256, 0, as_stream(stream)>>>(q, ldq, q_hs, k, ldk, k_hs, P, heads, chunk, gpart, sqq,
-                                                              sqk);
-    else
-        gram_generic_kernel<<<grid, 256, 0, as_stream(stream)>>>(q, ldq, q_hs, k, ldk, k_hs, P, heads, ch, chunk, gpart,
-                                                                sqq, sqk);
+    dim3 grid(ch, heads, B);
+    launch_pdl(chan_softmax_kernel, dim3(grid), dim3(1024), 0, as_stream(stream), gpart, sqq, sqk, seg_prenorm, temperature, nseg,
+               nsplit, heads, ch, Pout, inv_knorm, g_bs, s_bs);
     TURTLE_CHECK_LAUNCH();
     return TURTLE_OK;
 }
@@ -299,25 +343,27 @@ extern "C" int turtle_chan_gram(const float *q, int ldq, int q_hs, const float *
 extern "C" int turtle_chan_softmax(const float *gpart, const float *sqq, const float *sqk, const int32_t *seg_prenorm,
                                    const float *temperature, int nseg, int nsplit, int heads, int ch, float *Pout,
                                    float *inv_knorm, void *stream) {
-    if (!gpart || !sqq || !sqk || !seg_prenorm || !temperature || !Pout || nseg < 1 || nseg > 8 || ch > 64 || nseg * ch > 512)
-        return TURTLE_EINVAL;
-    dim3 grid(ch, heads);
-    launch_pdl(chan_softmax_kernel, dim3(grid), dim3(1024), 0, as_stream(stream), gpart, sqq, sqk, seg_prenorm, temperature, nseg, nsplit,
-                                                            heads, ch, Pout, inv_knorm);
+    return turtle_chan_softmax_b(gpart, sqq, sqk, seg_prenorm, temperature, nseg, nsplit, heads, ch, Pout, inv_knorm, 0, 0, 1,
+                                 stream);
+}
+
+// Pm [B, heads, ch, nseg*ch] -> M [B, C, nseg*C] (dense per element); Wo shared
+extern "C" int turtle_chan_fold_b(const float *Pm, const float *Wo, int nseg, int heads, int ch, float *M, int round_tf32,
+                                  int B, void *stream) {
+    if (!Pm || !Wo || !M || B < 1 || nseg < 1 || (long long)nseg * B > 65535) return TURTLE_EINVAL;
+    int64_t total = (int64_t)heads * ch * nseg * heads * ch;
+    if (ch == 64 && !(((uintptr_t)Pm | (uintptr_t)M | (uintptr_t)Wo) & 15)) {
+        dim3 grid(heads, heads, nseg * B);          // (C/64 output tiles, heads, segments x batch)
+        launch_pdl(chan_fold_tile_kernel, dim3(grid), dim3(256), 0, as_stream(stream), Pm, Wo, nseg, heads, M, round_tf32);
+    } else {
+        dim3 grid((unsigned)cdiv64(total, 256), B);
+        chan_fold_scalar_kernel<<<grid, 256, 0, as_stream(stream)>>>(Pm, Wo, nseg, heads, ch, M, round_tf32);
+    }
     TURTLE_CHECK_LAUNCH();
     return TURTLE_OK;
 }
 
 extern "C" int turtle_chan_fold(const float *Pm, const float *Wo, int nseg, int heads, int ch, float *M, int round_tf32,
                                 void *stream) {
-    if (!Pm || !Wo || !M) return TURTLE_EINVAL;
-    int64_t total = (int64_t)heads * ch * nseg * heads * ch;
-    if (ch == 64 && !(((uintptr_t)Pm | (uintptr_t)M | (uintptr_t)Wo) & 15)) {
-        dim3 grid(heads, heads, nseg);          // (C/64 output tiles, heads, segments)
-        launch_pdl(chan_fold_tile_kernel, dim3(grid), dim3(256), 0, as_stream(stream), Pm, Wo, nseg, heads, M, round_tf32);
-    } else {
-        chan_fold_scalar_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, as_stream(stream)>>>(Pm, Wo, nseg, heads, ch, M, round_tf32);
-    }
-    TURTLE_CHECK_LAUNCH();
-    return TURTLE_OK;
+    return turtle_chan_fold_b(Pm, Wo, nseg, heads, ch, M, round_tf32, 1, stream);
 }

@@ -24,6 +24,7 @@ struct alignas(64) GramParams {
     int q_hs, k_hs, heads;
     long long P, chunk;
     float *gpart, *sqq, *sqk;
+    long long g_bs, s_bs;      // batch strides (floats) of gpart and of sqq / sqk; the batch index is blockIdx.z
 };
 
 // MN-major tf32 operands must use the 128B swizzle with 32-byte atoms (UMMA layout type 1,
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(128) gram_tc_kernel(const __grid_constant__ Gr
     __shared__ uint32_t tmem_base_sh;
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int s = blockIdx.x, h = blockIdx.y;
+    const int s = blockIdx.x, h = blockIdx.y, bz = blockIdx.z;
     const long long p0 = (long long)s * p.chunk, p1 = min(p.P, p0 + p.chunk);
     const int nsteps = p1 > p0 ? (int)((p1 - p0 + KP - 1) / KP) : 0;
 
@@ -95,14 +96,14 @@ __global__ void __launch_bounds__(128) gram_tc_kernel(const __grid_constant__ Gr
             const int px = (int)(p0 + (long long)it * KP);
             if (H16) {          // one 64-channel (128 B) box each for q_h and k_h
                 mbar_expect_tx(fb, 2 * BLK_BYTES);
-                tma_load_2d(sa + 0 * BLK_BYTES, &p.mapQ, h * p.q_hs, px, fb);
-                tma_load_2d(sa + 1 * BLK_BYTES, &p.mapK, h * p.k_hs, px, fb);
+                tma_load_3d(sa + 0 * BLK_BYTES, &p.mapQ, h * p.q_hs, px, bz, fb);
+                tma_load_3d(sa + 1 * BLK_BYTES, &p.mapK, h * p.k_hs, px, bz, fb);
             } else {
                 mbar_expect_tx(fb, STAGE_BYTES);
-                tma_load_2d(sa + 0 * BLK_BYTES, &p.mapQ, h * p.q_hs, px, fb);
-                tma_load_2d(sa + 1 * BLK_BYTES, &p.mapQ, h * p.q_hs + 32, px, fb);
-                tma_load_2d(sa + 2 * BLK_BYTES, &p.mapK, h * p.k_hs, px, fb);
-                tma_load_2d(sa + 3 * BLK_BYTES, &p.mapK, h * p.k_hs + 32, px, fb);
+                tma_load_3d(sa + 0 * BLK_BYTES, &p.mapQ, h * p.q_hs, px, bz, fb);
+                tma_load_3d(sa + 1 * BLK_BYTES, &p.mapQ, h * p.q_hs + 32, px, bz, fb);
+                tma_load_3d(sa + 2 * BLK_BYTES, &p.mapK, h * p.k_hs, px, bz, fb);
+                tma_load_3d(sa + 3 * BLK_BYTES, &p.mapK, h * p.k_hs + 32, px, bz, fb);
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -139,14 +140,15 @@ __global__ void __launch_bounds__(128) gram_tc_kernel(const __grid_constant__ Gr
 
     const int C = p.heads * 64;
     const int row = warp * 32 + lane;
-    float *gp = p.gpart + (((long long)s * p.heads + h) * 64) * 64;
+    float *gp = p.gpart + bz * p.g_bs + (((long long)s * p.heads + h) * 64) * 64;
+    float *sqq = p.sqq + bz * p.s_bs, *sqk = p.sqk + bz * p.s_bs;
     if (nsteps == 0) {
         // empty split: contribute zeros
         if (row < 64) {
             for (int j = 0; j < 64; ++j) gp[row * 64 + j] = 0.f;
-            p.sqq[(long long)s * C + h * 64 + row] = 0.f;
+            sqq[(long long)s * C + h * 64 + row] = 0.f;
         } else {
-            p.sqk[(long long)s * C + h * 64 + row - 64] = 0.f;
+            sqk[(long long)s * C + h * 64 + row - 64] = 0.f;
         }
     } else {
         mbar_wait(smem_u32(&accum_bar), 0);
@@ -159,8 +161,8 @@ __global__ void __launch_bounds__(128) gram_tc_kernel(const __grid_constant__ Gr
 #pragma unroll
         for (int e = 0; e < 32; ++e)
             if (e == lane) diag = v[e];
-        if (row < 64) p.sqq[(long long)s * C + h * 64 + row] = diag;
-        else p.sqk[(long long)s * C + h * 64 + row - 64] = diag;
+        if (row < 64) sqq[(long long)s * C + h * 64 + row] = diag;
+        else sqk[(long long)s * C + h * 64 + row - 64] = diag;
         // rows 0..63 (q channels) x columns 64..127 (k channels) = the Gram block
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -181,8 +183,9 @@ __global__ void __launch_bounds__(128) gram_tc_kernel(const __grid_constant__ Gr
 
 }  // namespace
 
-int turtle_chan_gram_tc(const float *q, int ldq, int q_hs, const float *k, int ldk, int k_hs, int64_t P, int heads,
-                        int ch, int nsplit, float *gpart, float *sqq, float *sqk, int h16, void *stream) {
+int turtle_chan_gram_tc(const float *q, int ldq, int q_hs, long long q_bs, const float *k, int ldk, int k_hs, long long k_bs,
+                        int64_t P, int heads, int ch, int nsplit, float *gpart, float *sqq, float *sqk, long long g_bs,
+                        long long s_bs, int B, int h16, void *stream) {
     if (ch != 64) return TURTLE_ENOTSUP;
     const int al = h16 ? 7 : 3;
     if ((ldq & al) || (ldk & al) || (q_hs & al) || (k_hs & al) || (((uintptr_t)q | (uintptr_t)k) & 15)) return TURTLE_ENOTSUP;
@@ -190,15 +193,19 @@ int turtle_chan_gram_tc(const float *q, int ldq, int q_hs, const float *k, int l
     p.q_hs = q_hs; p.k_hs = k_hs; p.heads = heads; p.P = P;
     p.chunk = cdiv64(cdiv64(P, nsplit), KP) * KP;
     p.gpart = gpart; p.sqq = sqq; p.sqk = sqk;
+    p.g_bs = g_bs; p.s_bs = s_bs;
     {
-        uint64_t dq[2] = {(uint64_t)((heads - 1) * q_hs + 64), (uint64_t)P};
-        uint64_t dk[2] = {(uint64_t)((heads - 1) * k_hs + 64), (uint64_t)P};
+        // {columns, pixels, batch}: the batch element is the third TMA coordinate (blockIdx.z)
         const uint64_t es = h16 ? 2 : 4;
-        uint64_t sq[1] = {(uint64_t)ldq * es}, sk[1] = {(uint64_t)ldk * es};
-        uint32_t box[2] = {h16 ? 64u : 32u, KP};
+        if (B > 1 && (((q_bs * es) & 15) || ((k_bs * es) & 15) || q_bs < 0 || k_bs < 0)) return TURTLE_ENOTSUP;
+        uint64_t dq[3] = {(uint64_t)((heads - 1) * q_hs + 64), (uint64_t)P, (uint64_t)B};
+        uint64_t dk[3] = {(uint64_t)((heads - 1) * k_hs + 64), (uint64_t)P, (uint64_t)B};
+        uint64_t sq[2] = {(uint64_t)ldq * es, (uint64_t)(B > 1 ? q_bs : (long long)ldq * P) * es};
+        uint64_t sk[2] = {(uint64_t)ldk * es, (uint64_t)(B > 1 ? k_bs : (long long)ldk * P) * es};
+        uint32_t box[3] = {h16 ? 64u : 32u, KP, 1};
         if (dq[0] > (uint64_t)ldq || dk[0] > (uint64_t)ldk) return TURTLE_ENOTSUP;
-        if (!turtle_get_tmap2(&p.mapQ, q, 2, dq, sq, box, h16 ? 1 : 2, h16) ||
-            !turtle_get_tmap2(&p.mapK, k, 2, dk, sk, box, h16 ? 1 : 2, h16))
+        if (!turtle_get_tmap2(&p.mapQ, q, 3, dq, sq, box, h16 ? 1 : 2, h16) ||
+            !turtle_get_tmap2(&p.mapK, k, 3, dk, sk, box, h16 ? 1 : 2, h16))
             return TURTLE_ENOTSUP;
     }
     const size_t smem = STAGES * STAGE_BYTES + 1024;
@@ -211,7 +218,7 @@ int turtle_chan_gram_tc(const float *q, int ldq, int q_hs, const float *k, int l
             return TURTLE_ELAUNCH;
         configured = true;
     }
-    dim3 grid(nsplit, heads);
+    dim3 grid(nsplit, heads, B);
     if (h16) launch_pdl(gram_tc_kernel<true>, dim3(grid), dim3(128), smem, as_stream(stream), p);
     else launch_pdl(gram_tc_kernel<false>, dim3(grid), dim3(128), smem, as_stream(stream), p);
     return cudaGetLastError() == cudaSuccess ? TURTLE_OK : TURTLE_ELAUNCH;

@@ -442,36 +442,63 @@ class FrameEngine:
         else:
             self.dwconv(_ptr(qkv), 3 * c, pre + "qkv_dwconv.weight", pre + "qkv_dwconv.bias", _ptr(qd), 3 * c, B, H, W,
                         3 * c)
-        nsplit = max(1, min((Pimg + 255) // 256, max(1, self.gram_ctas // heads)))
+        # pixel splits of the Gram: the batch elements share the CTA budget (gram / softmax / fold run once for all of them)
+        nsplit = max(1, min((Pimg + 255) // 256, max(1, self.gram_ctas // (heads * B))))
         temp = self._w(pre + "temperature")
         Wo = self._w(pre + "project_out.weight")
         gmode = 2 if h16 else self.mode
+        # key / value segments per batch element: history (oldest first), then the frame's own k / v
+        allsegs = []
         for b in range(B):
             segs = list(hist_segs[b]) if hist_segs is not None else []
             base = b * Pimg * 3 * c
             segs.append(dict(k=_ptr(qd, base + c), ldk=3 * c, khs=ch, v=_ptr(qd, base + 2 * c), ldv=3 * c, vhs=ch,
                              prenorm=False))
-            S = len(segs)
-            gpart = self.ws.get("gram", S, nsplit, heads, ch, ch)
-            sqq = self.ws.get("sqq", S, nsplit, c)
-            sqk = self.ws.get("sqk", S, nsplit, c)
-            for s, sg in enumerate(segs):
-                self._meta = (2 * es * Pimg * c, 2 * Pimg * c * ch)
-                self._call("turtle_chan_gram", _ptr(qd, base), 3 * c, ch, sg["k"], sg["ldk"], sg["khs"], Pimg, heads, ch,
-                           nsplit, _ptr(gpart[s]), _ptr(sqq[s]), _ptr(sqk[s]), gmode, self.stream)
-            flags = self._flags([1 if sg["prenorm"] else 0 for sg in segs])
-            Pm = self.ws.get("attnP", heads, ch, S * ch)
-            inv = self.ws.get("invk", S, c)
-            self._call("turtle_chan_softmax", _ptr(gpart), _ptr(sqq), _ptr(sqk), _ptr(flags), _ptr(temp), S, nsplit,
-                       heads, ch, _ptr(Pm), _ptr(inv), self.stream)
-            M = self.ws.get("attnM16" if h16 else "attnM", c, S * c, dtype=dt)
-            self._call("turtle_chan_fold", _ptr(Pm), _ptr(Wo), S, heads, ch, _ptr(M), 2 if h16 else self.rnd, self.stream)
+            allsegs.append(segs)
+        S = len(allsegs[0])
+        # one launch per segment covers every batch element when element b of a segment sits at a fixed stride from
+        # element 0 (true for the rings, the CHM frame stack and the workspace maps); otherwise one launch per (b, segment)
+        kbs = []
+        for s_ in range(S):
+            d = (int(allsegs[1][s_]["k"]) - int(allsegs[0][s_]["k"])) if B > 1 else 0
+            ok = d >= 0 and d % es == 0 and all(int(allsegs[b][s_]["k"]) - int(allsegs[0][s_]["k"]) == b * d and
+                                                 allsegs[b][s_]["ldk"] == allsegs[0][s_]["ldk"] and
+                                                 allsegs[b][s_]["khs"] == allsegs[0][s_]["khs"] for b in range(B))
+            kbs.append(d // es if ok else None)
+        gpart = self.ws.get("gram", B, S, nsplit, heads, ch, ch)
+        sqq = self.ws.get("sqq", B, S, nsplit, c)
+        sqk = self.ws.get("sqk", B, S, nsplit, c)
+        g_bs, s_bs = S * nsplit * heads * ch * ch, S * nsplit * c
+        for s_ in range(S):
+            sg = allsegs[0][s_]
+            if kbs[s_] is not None:
+                self._meta = (2 * es * P * c, 2 * P * c * ch)
+                self._call("turtle_chan_gram_b", _ptr(qd), 3 * c, ch, Pimg * 3 * c, sg["k"], sg["ldk"], sg["khs"], kbs[s_],
+                           Pimg, heads, ch, nsplit, _ptr(gpart[0, s_]), _ptr(sqq[0, s_]), _ptr(sqk[0, s_]), g_bs, s_bs, B,
+                           gmode, self.stream)
+            else:
+                for b in range(B):
+                    sgb = allsegs[b][s_]
+                    self._meta = (2 * es * Pimg * c, 2 * Pimg * c * ch)
+                    self._call("turtle_chan_gram", _ptr(qd, b * Pimg * 3 * c), 3 * c, ch, sgb["k"], sgb["ldk"], sgb["khs"],
+                               Pimg, heads, ch, nsplit, _ptr(gpart[b, s_]), _ptr(sqq[b, s_]), _ptr(sqk[b, s_]), gmode,
+                               self.stream)
+        flags = self._flags([1 if sg["prenorm"] else 0 for sg in allsegs[0]])
+        Pm = self.ws.get("attnP", B, heads, ch, S * ch)
+        inv = self.ws.get("invk", B, S, c)
+        self._call("turtle_chan_softmax_b", _ptr(gpart), _ptr(sqq), _ptr(sqk), _ptr(flags), _ptr(temp), S, nsplit, heads, ch,
+                   _ptr(Pm), _ptr(inv), g_bs, s_bs, B, self.stream)
+        M = self.ws.get("attnM16" if h16 else "attnM", B, c, S * c, dtype=dt)
+        self._call("turtle_chan_fold_b", _ptr(Pm), _ptr(Wo), S, heads, ch, _ptr(M), 2 if h16 else self.rnd, B, self.stream)
+        for b in range(B):
+            segs = allsegs[b]
             vsegs = [(sg["v"] + es * h * sg["vhs"], sg["ldv"]) for sg in segs for h in range(heads)]
             xb = _ptr(x, b * Pimg * c)
-            self.gemm(vsegs, ch, M, xb, c, Pimg, c, bias=self._w(pre + "project_out.bias"), res=xb, ldres=c, a16=h16,
+            self.gemm(vsegs, ch, M[b], xb, c, Pimg, c, bias=self._w(pre + "project_out.bias"), res=xb, ldres=c, a16=h16,
                       ln=self.ln_target(P, c, ln, b, Pimg) if ln else None)
             if ring is not None:
-                self._call("turtle_scale_cols", _ptr(qd, base + c), 3 * c, ch, _ptr(inv[S - 1]),
+                base = b * Pimg * 3 * c
+                self._call("turtle_scale_cols", _ptr(qd, base + c), 3 * c, ch, _ptr(inv[b, S - 1]),
                            ring.slot_ptr(ring.kbuf, b, ring_slot), ring.ld, ring.head_stride, Pimg, heads, ch,
                            self.stream)
                 self._call("turtle_scale_cols", _ptr(qd, base + 2 * c), 3 * c, ch, None,
