@@ -132,6 +132,14 @@ typedef struct TurtleGemmArgs {
     void *ln_out;        /* or NULL */
     int32_t ld_ln;
     const float *ln_w, *ln_b;
+    /* Per-batch weights (the folded channel-attention matrices of B images in one launch): rows
+       [b*rows_per_batch, (b+1)*rows_per_batch) are multiplied by the matrix at Wt + b*w_bstride (elements of Wt's type).
+       w_batches <= 1: one matrix for all rows.  TURTLE_TF32 only, no im2col, rows_per_batch % 128 == 0,
+       P == w_batches*rows_per_batch; TURTLE_ENOTSUP otherwise (the caller then launches once per image). */
+    int32_t w_batches;
+    int32_t reserved_;
+    int64_t w_bstride;
+    int64_t rows_per_batch;
 } TurtleGemmArgs;
 
 int turtle_gemm(const TurtleGemmArgs *args, void *stream);

@@ -35,8 +35,8 @@ def test_abi_version_and_struct_layout():
     hdr = open(os.path.join(ROOT, "include", "turtle_b200.h")).read()
     assert int(re.search(r"#define TURTLE_MAX_SEG (\d+)", hdr).group(1)) == capi.MAX_SEG
     assert int(re.search(r"#define TURTLE_SAB_SLOTS (\d+)", hdr).group(1)) == capi.SAB_SLOTS
-    assert lib.turtle_abi_version() == 4
-    assert ctypes.sizeof(capi.GemmArgs) == lib.turtle_sizeof_gemm_args() == 728
+    assert lib.turtle_abi_version() == 5
+    assert ctypes.sizeof(capi.GemmArgs) == lib.turtle_sizeof_gemm_args() == 752
 
 
 def test_bad_arguments_are_rejected_without_a_gpu():

@@ -210,3 +210,52 @@ def test_conv3x3_im2col_fp16_operands(store):
     a.Wt, a.out, a.ldo, a.store, a.a_dtype = wp.data_ptr(), out.data_ptr(), Co, store, 1
     call("turtle_gemm", C.byref(a), stream())
     assert (out.cpu().double().permute(0, 3, 1, 2) - want).abs().max() < 1e-5 * max(1.0, float(want.abs().max()))
+
+
+@pytest.mark.parametrize("a16", [True, False])
+@pytest.mark.parametrize("K,Cout,rows,B,ln", [(128, 128, 256, 3, True), (256, 256, 512, 2, False), (64, 64, 128, 5, True),
+                                              (512, 256, 1024, 2, True)])
+def test_gemm_per_batch_weights_equals_per_image_launches(K, Cout, rows, B, ln, a16):
+    """TurtleGemmArgs.w_batches: one launch with a weight matrix per image (the folded channel-attention apply of B
+    tiles) == B launches, bit for bit; shapes that do not tile into 128-row blocks per image are refused (ENOTSUP)."""
+    P = B * rows
+    dt = torch.float16 if a16 else torch.float32
+    A = (rnd(P, K) * 0.5).to(dt).cuda()
+    Wt = (rnd(B, Cout, K, seed=1) / K ** 0.5).to(dt).cuda()
+    x0 = rnd(P, Cout, seed=2).cuda()
+    lw, lb = (torch.rand(Cout) + 0.5).cuda(), rnd(Cout, seed=3).cuda()
+
+    def run(out, lnout, b0, nb):
+        a = GemmArgs()
+        a.mode, a.P, a.Cout, a.nseg, a.segw = capi.TF32, nb * rows, Cout, 1, K
+        a.A[0], a.lda[0] = A.data_ptr() + b0 * rows * K * A.element_size(), K
+        a.Wt = Wt.data_ptr() + b0 * Cout * K * Wt.element_size()
+        a.res = a.out = out.data_ptr() + b0 * rows * Cout * 4
+        a.ldres = a.ldo = Cout
+        a.a_dtype = 1 if a16 else 0
+        if ln:
+            a.ln_out, a.ld_ln, a.ln_w, a.ln_b = lnout.data_ptr() + b0 * rows * Cout * 2, Cout, lw.data_ptr(), lb.data_ptr()
+        if nb > 1:
+            a.w_batches, a.w_bstride, a.rows_per_batch = nb, Cout * K, rows
+        call("turtle_gemm", C.byref(a), stream())
+
+    one, many = x0.clone(), x0.clone()
+    ln_one = torch.zeros(P, Cout, device="cuda", dtype=torch.float16)
+    ln_many = torch.zeros_like(ln_one)
+    run(one, ln_one, 0, B)
+    for b in range(B):
+        run(many, ln_many, b, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(one, many)
+    if ln:
+        assert torch.equal(ln_one, ln_many)
+    # reference: per-image matmul on the rounded operands
+    want = x0.double() + torch.einsum("bpk,bok->bpo", A.double().view(B, rows, K).cpu().cuda(), Wt.double()).reshape(P, Cout)
+    assert (one.double() - want).abs().max().item() < (2e-3 if not a16 else 1e-3) * max(1.0, want.abs().max().item())
+    # rows per image not a multiple of the 128-row tile: refused, the caller launches per image
+    a = GemmArgs()
+    a.mode, a.P, a.Cout, a.nseg, a.segw = capi.TF32, 2 * 200, Cout, 1, K
+    a.A[0], a.lda[0], a.Wt = A.data_ptr(), K, Wt.data_ptr()
+    a.out, a.ldo, a.a_dtype = one.data_ptr(), Cout, 1 if a16 else 0
+    a.w_batches, a.w_bstride, a.rows_per_batch = 2, Cout * K, 200
+    assert capi.load().turtle_gemm(C.byref(a), stream()) == capi.ENOTSUP

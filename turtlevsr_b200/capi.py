@@ -30,6 +30,7 @@ class GemmArgs(C.Structure):
         ("bias", _fp), ("scale", _fp), ("act", _i32), ("res", _fp), ("ldres", _i32), ("out", _fp),
         ("ldo", _i32), ("store", _i32), ("round_out", _i32), ("a_dtype", _i32), ("out_dtype", _i32),
         ("ln_out", _fp), ("ld_ln", _i32), ("ln_w", _fp), ("ln_b", _fp),
+        ("w_batches", _i32), ("reserved_", _i32), ("w_bstride", _i64), ("rows_per_batch", _i64),
     ]
 
 

@@ -169,10 +169,13 @@ extern "C" int turtle_gemm(const TurtleGemmArgs *a, void *stream) {
     if ((a->a_dtype || a->out_dtype) && a->mode != TURTLE_TF32) return TURTLE_EINVAL;   // fp16 I/O is a tensor-core feature
     if (a->ln_out && (a->mode != TURTLE_TF32 || !a->ln_w || !a->ln_b || (a->ld_ln & 7) || ((uintptr_t)a->ln_out & 15)))
         return TURTLE_EINVAL;
+    if (a->w_batches > 1 && (a->mode != TURTLE_TF32 || a->im2col || a->rows_per_batch < 1 ||
+                             a->P != (int64_t)a->w_batches * a->rows_per_batch || a->w_bstride < 0))
+        return a->mode != TURTLE_TF32 ? TURTLE_ENOTSUP : TURTLE_EINVAL;
     if (a->mode == TURTLE_TF32) {
         int r = turtle_gemm_tc(a, stream);
         if (r != TURTLE_ENOTSUP) return r;
-        if (a->a_dtype || a->out_dtype || a->ln_out) return TURTLE_ENOTSUP;
+        if (a->a_dtype || a->out_dtype || a->ln_out || a->w_batches > 1) return TURTLE_ENOTSUP;
         // shapes the tensor-core kernel does not cover run on the CUDA-core kernel (still on device)
     }
     GemmParams g;

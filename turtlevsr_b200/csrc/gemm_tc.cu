@@ -329,6 +329,7 @@ struct alignas(64) Tc2Params {
     long long total_units;
     int tma_epi, epi_boxes, dbg_skip;
     int w_res;                 // 1: the whole weight matrix (one n-group) stays in shared memory for the CTA's lifetime
+    int tiles_per_img;         // > 0: per-batch weights -- pixel tile t uses matrix t / tiles_per_img (mapW is 3-D {K, Cout, batch})
     const float *bias, *scale, *res;
     int act, ldres;
     float *out;
@@ -444,7 +445,11 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
                         const int sub = r / p.kb_per_sub;
                         tma_load_3d_pair(sa, &p.mapA[seg], (r - sub * p.kb_per_sub) * KE, sub, m0, fb);
                     }
-                    tma_load_2d_pair(sa + A_STAGE_BYTES, &p.mapW, kb * KE, ng * NG + (int)rank * (NG / 2), fb);
+                    if (p.tiles_per_img)
+                        tma_load_3d_pair(sa + A_STAGE_BYTES, &p.mapW, kb * KE, ng * NG + (int)rank * (NG / 2),
+                                         (int)(tile / p.tiles_per_img), fb);
+                    else
+                        tma_load_2d_pair(sa + A_STAGE_BYTES, &p.mapW, kb * KE, ng * NG + (int)rank * (NG / 2), fb);
                 } else {
                     mbar_expect_tx(fb, stage_bytes);
                     if (p.im2col) {
@@ -453,7 +458,10 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
                         const int sub = r / p.kb_per_sub;
                         tma_load_3d(sa, &p.mapA[seg], (r - sub * p.kb_per_sub) * KE, sub, m0, fb);
                     }
-                    if (!wres) tma_load_2d(sa + A_STAGE_BYTES, &p.mapW, kb * KE, ng * NG, fb);
+                    if (p.tiles_per_img)
+                        tma_load_3d(sa + A_STAGE_BYTES, &p.mapW, kb * KE, ng * NG, (int)(tile / p.tiles_per_img), fb);
+                    else if (!wres)
+                        tma_load_2d(sa + A_STAGE_BYTES, &p.mapW, kb * KE, ng * NG, fb);
                 }
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
@@ -957,8 +965,18 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
     // 256->768, 512->2560, 1280->512, the 3x3 up-convs: -5..-10 %), lose a few % on narrow n-groups and on the two-pass LN
     // epilogue, whose longer accumulator hold now stalls two SMs
     static const bool pair_ln = getenv("TURTLE_GEMM_PAIR_LN") != nullptr;      // A/B knob: CTA pairs for the fused-LN GEMMs too
-    const bool pair = !no_pair && p.nkb >= pair_min_kb && NG == 256 && (!a->ln_out || pair_ln) && tiles >= 8;
-    {
+    // per-batch weights: every 128-row tile must lie inside one batch element (pairs: every 256-row pair)
+    const bool wbatch = a->w_batches > 1;
+    if (wbatch && (a->im2col || a->rows_per_batch % TM || ((a->w_bstride * es) & 15))) return TURTLE_ENOTSUP;
+    p.tiles_per_img = wbatch ? (int)(a->rows_per_batch / TM) : 0;
+    const bool pair = !no_pair && p.nkb >= pair_min_kb && NG == 256 && (!a->ln_out || pair_ln) && tiles >= 8 &&
+                      (!wbatch || p.tiles_per_img % 2 == 0);
+    if (wbatch) {
+        uint64_t dims[3] = {(uint64_t)K, (uint64_t)Cout, (uint64_t)a->w_batches};
+        uint64_t str[2] = {(uint64_t)K * es, (uint64_t)a->w_bstride * es};
+        uint32_t box[3] = {(uint32_t)KE, (uint32_t)(pair ? NG / 2 : NG), 1};
+        if (!turtle_get_tmap2(&p.mapW, a->Wt, 3, dims, str, box, 1, a16 ? 1 : 0)) return TURTLE_ENOTSUP;
+    } else {
         uint64_t dims[2] = {(uint64_t)K, (uint64_t)Cout};
         uint64_t str[1] = {(uint64_t)K * es};
         uint32_t box[2] = {(uint32_t)KE, (uint32_t)(pair ? NG / 2 : NG)};
@@ -975,7 +993,7 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
     const size_t w_total = (size_t)p.nkb * NG * TK * 4;
     int nsm_now = 148;
     cudaDeviceGetAttribute(&nsm_now, cudaDevAttrMultiProcessorCount, turtle_device());
-    const bool wres = !no_wres && !pair && p.ngroups == 1 && tiles >= 2LL * nsm_now &&
+    const bool wres = !no_wres && !pair && !wbatch && p.ngroups == 1 && tiles >= 2LL * nsm_now &&
                       w_total + 2 * A_STAGE_BYTES + (size_t)EPI_WARPS * 2 * EPI_BUF + 1024 <= max_smem;
     p.w_res = wres ? 1 : 0;
     const size_t ring_budget = max_smem - (wres ? w_total : 0);     // what the A(+B) ring and the staging boxes share
@@ -1087,7 +1105,7 @@ int turtle_gemm_tc(const TurtleGemmArgs *a, void *stream) {
     if (!a->a_dtype && a->segw % TK) return TURTLE_ENOTSUP;
     if (((uintptr_t)a->Wt & 15) || ((uintptr_t)a->out & 15)) return TURTLE_ENOTSUP;
     static const bool use_v1 = getenv("TURTLE_GEMM_V1") != nullptr;
-    const bool half_io = a->a_dtype || a->out_dtype || a->ln_out;
+    const bool half_io = a->a_dtype || a->out_dtype || a->ln_out || a->w_batches > 1;
     if (!use_v1 || half_io) {
         int r = turtle_gemm_tc2(a, stream);
         if (r != TURTLE_ENOTSUP || half_io) return r;
@@ -1097,7 +1115,7 @@ int turtle_gemm_tc(const TurtleGemmArgs *a, void *stream) {
 
 int turtle_gemm_tc_v1(const TurtleGemmArgs *a, void *stream) {
     const int Cout = a->Cout;
-    if (a->ln_out) return TURTLE_ENOTSUP;
+    if (a->ln_out || a->w_batches > 1) return TURTLE_ENOTSUP;
     if (Cout % 16 || Cout < 16) return TURTLE_ENOTSUP;
     if (a->segw % TK) return TURTLE_ENOTSUP;
     if (((uintptr_t)a->Wt & 15) || ((uintptr_t)a->out & 15)) return TURTLE_ENOTSUP;

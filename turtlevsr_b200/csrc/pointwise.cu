@@ -724,7 +724,7 @@ extern "C" int turtle_cast_f16(const float *x, void *y, int64_t n, void *stream)
     return TURTLE_OK;
 }
 
-extern "C" int turtle_abi_version(void) { return 4; }     // 4: bias argument of turtle_sab_window_reduce[_h16]
+extern "C" int turtle_abi_version(void) { return 5; }     // 4: bias argument of turtle_sab_window_reduce[_h16]; 5: per-batch weights in TurtleGemmArgs
 extern "C" int turtle_sizeof_gemm_args(void) { return (int)sizeof(TurtleGemmArgs); }
 extern "C" const char *turtle_build_info(void) {
     return "libturtle_b200 sm_100a, CUDA "

@@ -194,9 +194,10 @@ class FrameEngine:
     # kernel wrappers
     # ------------------------------------------------------------------------------------
     def gemm(self, segs, segw, Wt, out, ldo, P, Cout, bias=None, scale=None, act=0, res=None, ldres=0,
-             im2col=0, geom=None, store=0, round_out=False, a16=False, o16=False, ln=None):
+             im2col=0, geom=None, store=0, round_out=False, a16=False, o16=False, ln=None, wb=None):
         """segs: list of (ptr:int, lda:int).  round_out: the result feeds another tensor-core op.
-        ln = (out_ptr, ld, norm_prefix): also emit fp16 LayerNorm(out rows) for the norm that reads them next."""
+        ln = (out_ptr, ld, norm_prefix): also emit fp16 LayerNorm(out rows) for the norm that reads them next.
+        wb = (batches, stride between the weight matrices in elements, rows per batch): per-batch weights."""
         a = GemmArgs()
         a.mode = self.mode
         a.im2col = im2col
@@ -224,6 +225,8 @@ class FrameEngine:
         a.round_out = 1 if (round_out and self.mode == capi.TF32 and not o16) else 0
         a.a_dtype = 1 if a16 else 0
         a.out_dtype = 1 if o16 else 0
+        if wb is not None:
+            a.w_batches, a.w_bstride, a.rows_per_batch = wb
         if ln is not None:
             a.ln_out, a.ld_ln = ln[0], ln[1]
             lw, lb = _ptr(self._w(ln[2] + "body.weight")), _ptr(self._w(ln[2] + "body.bias"))
@@ -490,12 +493,31 @@ class FrameEngine:
                    _ptr(Pm), _ptr(inv), g_bs, s_bs, B, self.stream)
         M = self.ws.get("attnM16" if h16 else "attnM", B, c, S * c, dtype=dt)
         self._call("turtle_chan_fold_b", _ptr(Pm), _ptr(Wo), S, heads, ch, _ptr(M), 2 if h16 else self.rnd, B, self.stream)
+        # apply: x += (W_o . blockdiag(P_b)) v_b.  One launch with per-image weight matrices when every 128-row tile lies
+        # inside one image and image b's value rows follow image b-1's in memory (workspace maps and the FHR ring do; the
+        # CHM frame stack does not); otherwise one launch per image
+        batched = (B > 1 and self.mode == capi.TF32 and Pimg % 128 == 0 and not self.dry_run and
+                   all(int(allsegs[b][s_]["v"]) - int(allsegs[0][s_]["v"]) == b * Pimg * allsegs[0][s_]["ldv"] * es and
+                       allsegs[b][s_]["ldv"] == allsegs[0][s_]["ldv"] and allsegs[b][s_]["vhs"] == allsegs[0][s_]["vhs"]
+                       for b in range(B) for s_ in range(S)))
+        if batched:
+            vsegs = [(sg["v"] + es * h * sg["vhs"], sg["ldv"]) for sg in allsegs[0] for h in range(heads)]
+            try:
+                self.gemm(vsegs, ch, M, _ptr(x), c, P, c, bias=self._w(pre + "project_out.bias"), res=_ptr(x), ldres=c,
+                          a16=h16, ln=self.ln_target(P, c, ln) if ln else None, wb=(B, c * S * c, Pimg))
+            except capi.TurtleKernelError as e:
+                if e.code != capi.ENOTSUP:
+                    raise
+                batched = False
         for b in range(B):
             segs = allsegs[b]
+            if batched:
+                break
             vsegs = [(sg["v"] + es * h * sg["vhs"], sg["ldv"]) for sg in segs for h in range(heads)]
             xb = _ptr(x, b * Pimg * c)
             self.gemm(vsegs, ch, M[b], xb, c, Pimg, c, bias=self._w(pre + "project_out.bias"), res=xb, ldres=c, a16=h16,
                       ln=self.ln_target(P, c, ln, b, Pimg) if ln else None)
+        for b in range(B):
             if ring is not None:
                 base = b * Pimg * 3 * c
                 self._call("turtle_scale_cols", _ptr(qd, base + c), 3 * c, ch, _ptr(inv[b, S - 1]),

@@ -110,7 +110,8 @@ _GEMM_SCHEMA = (
     "(int mode, int im2col, int P, int B, int H, int W, int Cout, int segw, Tensor[] A, int[] A_off, int[] lda, "
     "Tensor Wt, int Wt_off, Tensor? bias, int bias_off, Tensor? scale, int scale_off, int act, Tensor? res, int res_off, "
     "int ldres, Tensor(a!) out, int out_off, int ldo, int store, int round_out, int a_dtype, int out_dtype, "
-    "Tensor(b!)? ln_out, int ln_out_off, int ld_ln, Tensor? ln_w, int ln_w_off, Tensor? ln_b, int ln_b_off) -> ()")
+    "Tensor(b!)? ln_out, int ln_out_off, int ld_ln, Tensor? ln_w, int ln_w_off, Tensor? ln_b, int ln_b_off, "
+    "int w_batches, int w_bstride, int rows_per_batch) -> ()")
 
 PROTOS = _parse_header()
 SCHEMAS: Dict[str, str] = {n[len("turtle_"):]: _schema(p) for n, p in PROTOS.items()}
@@ -159,7 +160,7 @@ def _fake(*args, **kwargs):
 
 def _gemm_impl(mode, im2col, P, B, H, W, Cout, segw, A, A_off, lda, Wt, Wt_off, bias, bias_off, scale, scale_off, act, res,
                res_off, ldres, out, out_off, ldo, store, round_out, a_dtype, out_dtype, ln_out, ln_out_off, ld_ln, ln_w,
-               ln_w_off, ln_b, ln_b_off):
+               ln_w_off, ln_b, ln_b_off, w_batches, w_bstride, rows_per_batch):
     a = capi.GemmArgs()
     a.mode, a.im2col, a.P, a.B, a.H, a.W, a.Cout, a.nseg, a.segw = mode, im2col, P, B, H, W, Cout, len(A), segw
     for i, (t, o, ld) in enumerate(zip(A, A_off, lda)):
@@ -169,6 +170,7 @@ def _gemm_impl(mode, im2col, P, B, H, W, Cout, segw, A, A_off, lda, Wt, Wt_off, 
     a.res, a.ldres, a.out, a.ldo, a.store = _addr(res, res_off), ldres, _addr(out, out_off), ldo, store
     a.round_out, a.a_dtype, a.out_dtype = round_out, a_dtype, out_dtype
     a.ln_out, a.ld_ln, a.ln_w, a.ln_b = _addr(ln_out, ln_out_off), ld_ln, _addr(ln_w, ln_w_off), _addr(ln_b, ln_b_off)
+    a.w_batches, a.w_bstride, a.rows_per_batch = w_batches, w_bstride, rows_per_batch
     capi.call("turtle_gemm", C.byref(a), _current_stream(out))
 
 
@@ -228,4 +230,4 @@ def launch_gemm(a: "capi.GemmArgs", ptrs: dict, stream) -> None:
     _OPS["gemm"](a.mode, a.im2col, a.P, a.B, a.H, a.W, a.Cout, a.segw, [t for t, _ in A], [o for _, o in A],
                  [a.lda[i] for i in range(a.nseg)], Wt[0], Wt[1], bias[0], bias[1], scale[0], scale[1], a.act, res[0],
                  res[1], a.ldres, out[0], out[1], a.ldo, a.store, a.round_out, a.a_dtype, a.out_dtype, ln_out[0],
-                 ln_out[1], a.ld_ln, ln_w[0], ln_w[1], ln_b[0], ln_b[1])
+                 ln_out[1], a.ld_ln, ln_w[0], ln_w[1], ln_b[0], ln_b[1], a.w_batches, a.w_bstride, a.rows_per_batch)
