@@ -836,9 +836,35 @@ class FrameEngine:
             static_in = torch.empty_like(inp, memory_format=torch.contiguous_format)
             static_in.copy_(inp)
             n0 = capi.launch_count
+            # host-side ring state before the capture: a capture that fails launched nothing, but ran the host protocol
+            pre_state = [(r.pos, r.count, r._sig, r.epoch) for r in rings]
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):        # private memory pool per graph: replay order is free, eviction frees it
-                out, ks, vs = self._forward_eager(static_in, k_cached, v_cached)
+            import gc
+            gc_was = gc.isenabled()
+            gc.collect()                     # dead cycles that own CUDA graphs / memory (an earlier model and its engine) go
+            gc.disable()                     # NOW: a collection in the middle of a capture would destroy them there, and
+            try:                             # freeing device memory while a stream captures invalidates the capture
+                with torch.cuda.graph(g):    # private memory pool per graph: replay order is free, eviction frees it
+                    out, ks, vs = self._forward_eager(static_in, k_cached, v_cached)
+            except Exception as e:           # never let a failed capture cost a frame: restore the rings, run eagerly
+                if gc_was:
+                    gc.enable()
+                for r, (pos, count, sig, ep) in zip(rings, pre_state):
+                    r.pos, r.count, r._sig, r.epoch = pos, count, sig, ep
+                capi.launch_count = n0
+                self._capture_failures = getattr(self, "_capture_failures", 0) + 1
+                self._graph_seen.discard(key)        # it gets another chance on a later visit
+                import warnings
+                warnings.warn(f"CUDA-graph capture of a frame failed ({type(e).__name__}: {str(e)[:120]}); frame runs eagerly")
+                try:
+                    torch.cuda.synchronize()
+                except Exception:
+                    pass
+                if self._capture_failures > 8:
+                    self.model.cuda_graphs = False   # something systematic: stop trying
+                return None
+            if gc_was:
+                gc.enable()
             post = [(r.pos, r.count, r._sig) for r in rings]
             ent = self.graphs[key] = (g, static_in, out, ks, vs, rings, post, capi.launch_count - n0)
             self.graph_captures += 1
