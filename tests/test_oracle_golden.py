@@ -127,3 +127,11 @@ def test_frame_folder_reader_decodes_in_order(tmp_path):
         paths.append(p)
     got = [t.clone().numpy() for t in FrameFolderReader(paths, depth=3)]
     assert len(got) == 7 and all(np.array_equal(a, b) for a, b in zip(got, imgs))
+    # and back out through the writer (PNG is lossless: the files decode to the same arrays)
+    from turtlevsr_b200.frameio import FrameFolderWriter
+    w = FrameFolderWriter(depth=2)
+    outs = [str(tmp_path / f"Frame_{i:04d}_Pred.png") for i in range(7)]
+    for pth, im in zip(outs, imgs):
+        w.put(pth, torch.from_numpy(im))
+    w.close()
+    assert all(np.array_equal(cv2.imread(pth, cv2.IMREAD_COLOR), im) for pth, im in zip(outs, imgs))

@@ -234,3 +234,41 @@ class FrameFolderReader:
             self._ready[s].clear()
             yield self._slots[s]
             self._free[s].set()
+
+
+class FrameFolderWriter:
+    """Encode restored 8-bit frames to image files (``cv2.imwrite`` of INFN:272-273) on a background thread, so PNG
+    encoding overlaps the GPU.  ``put(path, frame_u8_HWC)`` copies the (pinned) host frame into a small queue and returns;
+    ``close()`` drains it.  Frames are expected in cv2's BGR order (``frame_to_u8(..., swap_rb=True)``)."""
+
+    def __init__(self, depth: int = 8):
+        import queue
+        import cv2
+        self._cv2 = cv2
+        self._q: "queue.Queue" = queue.Queue(maxsize=depth)
+        self._err: Optional[BaseException] = None
+        self._t = threading.Thread(target=self._work, daemon=True)
+        self._t.start()
+
+    def _work(self):
+        while True:
+            item = self._q.get()
+            if item is None:
+                return
+            path, img = item
+            try:
+                if not self._cv2.imwrite(path, img):
+                    raise OSError(f"cv2.imwrite failed for {path}")
+            except BaseException as e:
+                self._err = e
+
+    def put(self, path: str, frame_u8: torch.Tensor) -> None:
+        if self._err is not None:
+            raise self._err
+        self._q.put((path, frame_u8.cpu().numpy().copy()))
+
+    def close(self) -> None:
+        self._q.put(None)
+        self._t.join()
+        if self._err is not None:
+            raise self._err
