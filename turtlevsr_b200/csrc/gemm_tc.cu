@@ -329,6 +329,7 @@ struct alignas(64) Tc2Params {
     long long total_units;
     int tma_epi, epi_boxes, dbg_skip;
     int w_res;                 // 1: the whole weight matrix (one n-group) stays in shared memory for the CTA's lifetime
+    int o16_2ld;               // fp16-output epilogue: both 32-column TMEM loads of a store group in flight before one wait
     int tiles_per_img;         // > 0: per-batch weights -- pixel tile t uses matrix t / tiles_per_img (mapW is 3-D {K, Cout, batch})
     const float *bias, *scale, *res;
     int act, ldres;
@@ -554,15 +555,32 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
                 const int m0 = (int)(tile * TM) + quarter * 32;
                 const int nch = NG / 32, h0 = (nch + 1) / 2;
                 const int jb = chalf ? h0 : 0, je = chalf ? nch : h0;
+                const int NBo = p.epi_boxes;              // staging boxes of this warp (2..4): a box is reused NBo groups later
                 for (int j = jb; j < je; ++gw) {
                     const int nc = (je - j >= 2) ? 2 : 1;
-                    const int b = gw & 1;
+                    const int b = (int)(gw % (uint32_t)NBo);
                     const uint32_t buf = mybuf + b * EPI_BUF;
-                    if (lane == 0 && gw >= 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    if (lane == 0 && gw >= (uint32_t)NBo) {       // the store that last used this box has read it
+                        if (NBo == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        else if (NBo == 3) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+                        else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+                    }
                     __syncwarp();
+                    uint32_t r2[2][32];
+                    const bool two = p.o16_2ld && nc == 2;
+                    if (two) {
+                        tmem_ld32_nowait(trow + j * 32, r2[0]);
+                        tmem_ld32_nowait(trow + (j + 1) * 32, r2[1]);
+                        tmem_wait_ld();
+                    }
                     for (int ci = 0; ci < nc; ++ci) {
                         float v[32];
-                        tmem_ld32(trow + (j + ci) * 32, v);
+                        if (two) {
+#pragma unroll
+                            for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r2[ci & 1][e]);
+                        } else {
+                            tmem_ld32(trow + (j + ci) * 32, v);
+                        }
                         epi_apply(eflags, v, p.bias, p.scale, n0 + (j + ci) * 32);
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
@@ -1008,6 +1026,12 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
     static const int min_st_long = getenv("TURTLE_GEMM_MINST_LONG") ? atoi(getenv("TURTLE_GEMM_MINST_LONG")) : 4;
     const int min_st = p.nkb <= 4 ? (min_st_short ? min_st_short : (NG == 256 ? 2 : 3)) : min_st_long;
     int boxes = 2;
+    static const int o16_boxes = getenv("TURTLE_GEMM_O16BOX") ? atoi(getenv("TURTLE_GEMM_O16BOX")) : 2;     // A/B knobs
+    static const int o16_2ld = getenv("TURTLE_GEMM_O16_2LD") ? atoi(getenv("TURTLE_GEMM_O16_2LD")) : 0;
+    p.o16_2ld = o16_2ld;
+    if (o16 && o16_boxes > 2 && o16_boxes <= 4 &&
+        (long long)((ring_budget - 1024 - (size_t)EPI_WARPS * o16_boxes * EPI_BUF) / stage_bytes) >= (p.nkb < 3 ? p.nkb : 3))
+        boxes = o16_boxes;
     if (a->res && !o16)
         for (int cand = box_cap < 4 ? box_cap : 4; cand > 2; --cand)
             if (ring_budget > 1024 + (size_t)EPI_WARPS * cand * EPI_BUF &&
