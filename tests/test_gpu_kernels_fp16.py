@@ -52,6 +52,24 @@ def test_dwconv_fp16(fuse, B, C_, H, W):
     assert ok, worst
 
 
+@pytest.mark.parametrize("fuse", [0, 1])
+def test_dwconv_fp16_odd_block_count(fuse):
+    """96 channels = three 32-channel blocks: the plain / GELU kernels cannot pair them up and take one block per item."""
+    B, C_, H, W = 1, 96, 11, 19
+    x = rnd(B, H, W, C_).half().cuda()
+    w = (rnd(C_, 1, 3, 3, seed=1) / 3).half()
+    b = rnd(C_, seed=2)
+    y = F.conv2d(x.cpu().double().permute(0, 3, 1, 2), w.double(), b.double(), padding=1, groups=C_)
+    if fuse == 1:
+        y = F.gelu(y)
+    out = torch.full((B, H, W, C_), float("nan"), device="cuda", dtype=torch.float16)
+    w9, bd = w.reshape(C_, 9).t().contiguous().cuda(), b.cuda()          # (kept alive until the kernel has run)
+    call("turtle_dwconv3x3", x.data_ptr(), C_, w9.data_ptr(), bd.data_ptr(), out.data_ptr(), C_, B, H, W, C_, fuse, 0, 1, 2,
+         stream())
+    ok, worst = close16(out.cpu().permute(0, 3, 1, 2), y, extra=2e-5)
+    assert ok, worst
+
+
 @pytest.mark.parametrize("C_", [64, 128, 256, 512])
 def test_layernorm_fp16_out(C_):
     P = 777

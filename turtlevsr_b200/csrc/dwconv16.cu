@@ -13,6 +13,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 bool turtle_get_tmap2(CUtensorMap *out, const void *ptr, int rank, const uint64_t *dims, const uint64_t *strides,
@@ -24,10 +26,14 @@ constexpr int TH = 8, TW = 16, CK = 32;
 constexpr int HR = TH + 2, HC = TW + 2;
 constexpr int BOXB = HR * HC * CK * 2;        // 11520 B
 // halo boxes in flight per CTA = stages-1 (HBM latency x bandwidth needs > 40 KB in flight per SM)
-template <int FUSE> struct Cfg {
-    static constexpr int NS = FUSE == 2 ? 2 : 1;
-    static constexpr int STAGES = FUSE == 2 ? 3 : 4;
-    static constexpr int CTAS = FUSE == 0 ? 4 : 3;          // resident CTAs per SM (registers / shared memory)
+// PAIR (FUSE 0 / 1 only): one work item covers TWO adjacent 32-channel blocks of the same pixel tile, staged as two halo
+// boxes like the gated variant's (u1, u2) pair.  The item bookkeeping (barrier wait, item decode, pointer and bounds
+// arithmetic, the block barrier) is ~250 of the ~450 warp instructions of a plain single-block item but only ~130 of the
+// gated variant's 711; pairing the blocks amortises it over twice the arithmetic.
+template <int FUSE, bool PAIR> struct Cfg {
+    static constexpr int NS = (FUSE == 2 || PAIR) ? 2 : 1;
+    static constexpr int STAGES = NS == 2 ? 3 : 4;
+    static constexpr int CTAS = (FUSE == 0 && !PAIR) ? 4 : 3;          // resident CTAs per SM (registers / shared memory)
 };
 
 struct alignas(64) Dw16Params {
@@ -58,9 +64,12 @@ __device__ __forceinline__ void fma4h(float4 &a, const uint2 &x, const uint2 &w)
     a.w = fhfma(hi16(x.y), hi16(w.y), a.w);
 }
 
-template <int FUSE>
-__global__ void __launch_bounds__(256, Cfg<FUSE>::CTAS) dwconv16_kernel(const __grid_constant__ Dw16Params p) {
-    constexpr int NS = Cfg<FUSE>::NS, STAGES = Cfg<FUSE>::STAGES;
+template <int FUSE, bool PAIR>
+__global__ void __launch_bounds__(256, Cfg<FUSE, PAIR>::CTAS) dwconv16_kernel(const __grid_constant__ Dw16Params p) {
+    constexpr int NS = Cfg<FUSE, PAIR>::NS, STAGES = Cfg<FUSE, PAIR>::STAGES;
+    // channel offset of stream s of channel-block index cb: the gated variant pairs block cb of u1 with block cb of u2
+    // (Cout channels further); PAIR takes the adjacent blocks 2cb, 2cb+1
+    auto chan_of = [&](int cb, int s) { return FUSE == 2 ? cb * CK + s * p.Cout : (PAIR ? (2 * cb + s) * CK : cb * CK); };
     // the host sizes the grid as a multiple of cblocks, so a CTA's channel block never changes: its taps and
     // bias are staged in shared memory once
     __shared__ __align__(16) __half wsm[NS * 9 * CK];
@@ -82,9 +91,9 @@ __global__ void __launch_bounds__(256, Cfg<FUSE>::CTAS) dwconv16_kernel(const __
         const int cb0 = (int)(blockIdx.x % (unsigned)p.cblocks);
         for (int i = tid; i < NS * 9 * CK; i += 256) {
             const int s = i / (9 * CK), t = (i / CK) % 9, ch = i % CK;
-            wsm[i] = p.w9[t * p.C + cb0 * CK + ch + s * p.Cout];
+            wsm[i] = p.w9[t * p.C + chan_of(cb0, s) + ch];
         }
-        if (tid < NS * CK) bsm[tid] = p.bias ? p.bias[cb0 * CK + (tid % CK) + (tid / CK) * p.Cout] : 0.f;
+        if (tid < NS * CK) bsm[tid] = p.bias ? p.bias[chan_of(cb0, tid / CK) + (tid % CK)] : 0.f;
     }
     __syncthreads();
     pdl_wait();          // taps and bias are constants; the map is the first thing an earlier kernel may still write
@@ -106,7 +115,7 @@ __global__ void __launch_bounds__(256, Cfg<FUSE>::CTAS) dwconv16_kernel(const __
             asm volatile(
                 "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::
                     "r"(dst + s * BOXB),
-                "l"(&p.map), "r"(bar), "r"(cb * CK + s * p.Cout), "r"(tx * TW - 1), "r"(ty * TH - 1), "r"(nb)
+                "l"(&p.map), "r"(bar), "r"(chan_of(cb, s)), "r"(tx * TW - 1), "r"(ty * TH - 1), "r"(nb)
                 : "memory");
     };
 
@@ -139,7 +148,6 @@ __global__ void __launch_bounds__(256, Cfg<FUSE>::CTAS) dwconv16_kernel(const __
             } while (!ok);
         }
         const int4 cd = coord[buf];
-        const int c0 = cd.x * CK + c4 * 4;
         const int px = cd.y * TW + col;
         const int py0 = cd.z * TH + half * 4;
         const uint8_t *sbase = sgen + buf * (NS * BOXB) + toff;
@@ -170,6 +178,9 @@ __global__ void __launch_bounds__(256, Cfg<FUSE>::CTAS) dwconv16_kernel(const __
                     for (int kx = 0; kx < 3; ++kx) fma4h(a, r[ky][kx], wv[ky * 3 + kx]);
                 if (FUSE == 0) {
                     out[i] = a;
+                } else if (FUSE == 1) {
+                    const float2 g0 = gelu_fast2(make_float2(a.x, a.y)), g1 = gelu_fast2(make_float2(a.z, a.w));
+                    out[i] = make_float4(g0.x, g0.y, g1.x, g1.y);
                 } else if (s == 0) {
                     const float2 g0 = gelu_fast2(make_float2(a.x, a.y)), g1 = gelu_fast2(make_float2(a.z, a.w));
                     out[i] = make_float4(g0.x, g0.y, g1.x, g1.y);
@@ -184,16 +195,18 @@ __global__ void __launch_bounds__(256, Cfg<FUSE>::CTAS) dwconv16_kernel(const __
                     r[1][dx] = r[2][dx];
                 }
             }
-        }
-        if (px < p.W) {
-            __half *yp = p.y + (((long long)cd.w * p.H + py0) * p.W + px) * p.ldy + c0;
-            const long long rstride = (long long)p.W * p.ldy;
+            // plain / GELU streams are independent outputs: stored as soon as they are computed; the gated pair after both
+            if ((FUSE != 2 || s == NS - 1) && px < p.W) {
+                const int c0 = (FUSE == 2 ? cd.x * CK : chan_of(cd.x, s)) + c4 * 4;
+                __half *yp = p.y + (((long long)cd.w * p.H + py0) * p.W + px) * p.ldy + c0;
+                const long long rstride = (long long)p.W * p.ldy;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                if (py0 + i < p.H) {
-                    const __half2 h0 = __floats2half2_rn(out[i].x, out[i].y), h1 = __floats2half2_rn(out[i].z, out[i].w);
-                    *reinterpret_cast<uint2 *>(yp + i * rstride) =
-                        make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+                for (int i = 0; i < 4; ++i) {
+                    if (py0 + i < p.H) {
+                        const __half2 h0 = __floats2half2_rn(out[i].x, out[i].y), h1 = __floats2half2_rn(out[i].z, out[i].w);
+                        *reinterpret_cast<uint2 *>(yp + i * rstride) =
+                            make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+                    }
                 }
             }
         }
@@ -201,27 +214,27 @@ __global__ void __launch_bounds__(256, Cfg<FUSE>::CTAS) dwconv16_kernel(const __
     }
 }
 
-template <int FUSE>
+template <int FUSE, bool PAIR>
 int launch16(const Dw16Params &p, cudaStream_t s) {
-    constexpr int NS = Cfg<FUSE>::NS;
-    const size_t smem = Cfg<FUSE>::STAGES * NS * BOXB + 128;
+    constexpr int NS = Cfg<FUSE, PAIR>::NS;
+    const size_t smem = Cfg<FUSE, PAIR>::STAGES * NS * BOXB + 128;
     static bool configured_[TURTLE_MAX_DEVICES] = {};      // cudaFuncSetAttribute is a per-device property
     const int dev_ = turtle_device();
     bool &configured = configured_[dev_];
     static int nsm_[TURTLE_MAX_DEVICES];
     int &nsm = nsm_[dev_];
     if (!configured) {
-        if (cudaFuncSetAttribute(dwconv16_kernel<FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(dwconv16_kernel<FUSE, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return TURTLE_ELAUNCH;
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
         configured = true;
     }
-    unsigned grid = (unsigned)nsm * Cfg<FUSE>::CTAS;
+    unsigned grid = (unsigned)nsm * Cfg<FUSE, PAIR>::CTAS;
     if (grid > p.nitems) grid = p.nitems;
     grid -= grid % (unsigned)p.cblocks;          // every CTA keeps one channel block (nitems is a multiple of cblocks)
-    launch_pdl(dwconv16_kernel<FUSE>, dim3(grid), dim3(256), smem, s, p);
+    launch_pdl(dwconv16_kernel<FUSE, PAIR>, dim3(grid), dim3(256), smem, s, p);
     return cudaGetLastError() == cudaSuccess ? TURTLE_OK : TURTLE_ELAUNCH;
 }
 
@@ -245,10 +258,15 @@ int turtle_dwconv3x3_h16(const void *x, int ldx, const void *w9, const float *bi
     p.ldy = ldy; p.H = H; p.W = W; p.C = C; p.Cout = Cout;
     p.tiles_x = (W + TW - 1) / TW;
     p.tiles_y = (H + TH - 1) / TH;
-    p.cblocks = Cout / CK;
+    // plain / GELU maps whose channel count is a multiple of 64 run two channel blocks per item (TURTLE_DW_PAIR=0: off)
+    static const bool no_pair = getenv("TURTLE_DW_PAIR") && atoi(getenv("TURTLE_DW_PAIR")) == 0;
+    const bool pair = fuse != 2 && !no_pair && Cout % (2 * CK) == 0;
+    p.cblocks = Cout / CK / (pair ? 2 : 1);
     const long long nitems = (long long)p.cblocks * p.tiles_x * p.tiles_y * NB;
     if (nitems >= (1LL << 31)) return TURTLE_ENOTSUP;
     p.nitems = (unsigned)nitems;
     cudaStream_t s = as_stream(stream);
-    return fuse == 0 ? launch16<0>(p, s) : fuse == 1 ? launch16<1>(p, s) : launch16<2>(p, s);
+    if (fuse == 2) return launch16<2, false>(p, s);
+    if (pair) return fuse == 0 ? launch16<0, true>(p, s) : launch16<1, true>(p, s);
+    return fuse == 0 ? launch16<0, false>(p, s) : launch16<1, false>(p, s);
 }
