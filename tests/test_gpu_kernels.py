@@ -142,7 +142,7 @@ def test_pack_frame_first_last(up):
 
 
 @pytest.mark.parametrize("mode", [capi.FP32, capi.TF32])
-@pytest.mark.parametrize("heads,ch,S", [(4, 64, 1), (2, 64, 3), (2, 16, 2), (1, 64, 2)])
+@pytest.mark.parametrize("heads,ch,S", [(4, 64, 1), (2, 64, 3), (2, 16, 2), (1, 64, 2), (1, 64, 5), (2, 64, 4), (1, 64, 8)])
 def test_channel_attention_chain(heads, ch, S, mode):
     """gram -> softmax -> fold -> apply  ==  softmax(q^ k^T * t) @ v -> project_out, with S key segments."""
     c, P = heads * ch, 700
@@ -158,7 +158,7 @@ def test_channel_attention_chain(heads, ch, S, mode):
     v = torch.cat([rows(t[:, 2 * c:]) for t in qkv], 1)
     attn = torch.softmax(q @ k.transpose(-1, -2) * temp.view(-1, 1, 1), -1)
     want = x + ((attn @ v).reshape(c, P).t() @ Wo.t())
-    nsplit = 5
+    nsplit = 5 if S < 4 else 40          # (40 splits: the softmax kernel's 8-deep unrolled partial sums run too)
     g = torch.zeros(S, nsplit, heads, ch, ch, device="cuda")
     sqq = torch.zeros(S, nsplit, c, device="cuda")
     sqk = torch.zeros(S, nsplit, c, device="cuda")
