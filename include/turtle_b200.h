@@ -249,6 +249,19 @@ int turtle_sab_select_tc(const float *qn, const float *kn, int64_t k_fstride, in
 int turtle_sab_aggregate(const int32_t *idx, const float *wgt, const float *v, int64_t v_fstride, float *y, int F,
                          int Hg, int Wg, int ws, int c, int passthrough, int round_tf32, void *stream);
 
+/* The same aggregation on the tensor cores (tensor-core mode; csrc/sab_agg_tc.cu).  For a tile of 8 x 16 neighbouring
+ * queries every local-window key lies in the 16 x 24 box of keys around the tile, so the window part is one dense
+ * tcgen05 contraction per tile (TF32 operands, fp32 accumulation; the weights are TF32-rounded here, V should hold
+ * TF32-rounded values -- turtle_dwconv3x3(round_tf32 = 1) writes them so); the top-k keys outside the box are added
+ * by a gather pass.  round_mode: 0 fp32 y, 1 fp32 y TF32-rounded, 2 fp16 y (feeds a kind::f16 GEMM).
+ * v_dtype 1: v points at an fp16 copy of the value rows (v_fstride in halves): kind::f16 MMAs and half the bytes in the
+ * contraction and in the gather (the engine keeps such a copy next to the fp32 history ring in tensor-core mode).
+ * Needs c % 32 == 0, (ws*ws*c) % 256 == 0, dense frames (v_fstride >= N*ws*ws*c) and a device workspace of
+ * turtle_sab_aggregate_tc_workspace(F, Hg, Wg) bytes; TURTLE_ENOTSUP otherwise (the caller runs turtle_sab_aggregate). */
+long long turtle_sab_aggregate_tc_workspace(int F, int Hg, int Wg);
+int turtle_sab_aggregate_tc(const int32_t *idx, const float *wgt, const void *v, int v_dtype, int64_t v_fstride, void *y,
+                            int F, int Hg, int Wg, int ws, int c, int round_mode, void *workspace, void *stream);
+
 /* T0 only: x + positionalencoding2d(c,h,w) (T0:412-439, 475-476), evaluated analytically. */
 int turtle_add_posenc(const float *x, float *y, int B, int H, int W, int C, void *stream);
 

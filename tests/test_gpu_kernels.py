@@ -270,6 +270,38 @@ def test_sab_select_and_aggregate(Hg, Wg, D, F_, tc):
     assert (y.cpu().permute(0, 3, 1, 2) - want).abs().max() < 1e-5
 
 
+@pytest.mark.parametrize("h16", [False, True])
+@pytest.mark.parametrize("rmode", [0, 1, 2])
+@pytest.mark.parametrize("Hg,Wg,ws,c,F_", [(13, 37, 2, 64, 2), (46, 80, 4, 32, 3), (8, 16, 4, 64, 1), (20, 9, 2, 64, 2),
+                                           (5, 3, 2, 128, 1), (7, 33, 2, 64, 1)])
+def test_sab_aggregate_tc(Hg, Wg, ws, c, F_, rmode, h16):
+    """Tensor-core aggregation (dense 16x24 key box per 8x16 query tile + far top-k gather) == the CUDA-core kernel."""
+    N, D, Dv = Hg * Wg, 32, ws * ws * c
+    q = orc.l2norm_rows(rnd(N, D))
+    k = orc.l2norm_rows(rnd(F_, N, D, seed=1))
+    idx = torch.empty(F_, N, capi.SAB_SLOTS, dtype=torch.int32, device="cuda")
+    wgt = torch.empty(F_, N, capi.SAB_SLOTS, device="cuda")
+    call("turtle_sab_select", dp(q), dp(k), N * D, F_, Hg, Wg, D, dp(torch.tensor([0.83])), 0, idx.data_ptr(), wgt.data_ptr(),
+         0, stream())
+    V = rnd(F_, N, Dv, seed=2)
+    if h16:         # the fp16 copy of the rows the engine keeps next to the ring
+        V = V.half().float().cuda()
+    else:           # TF32-rounded rows, as the engine writes them
+        V = ((V.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32).cuda()
+    want = torch.empty(F_, Hg * ws, Wg * ws, c, device="cuda")
+    call("turtle_sab_aggregate", idx.data_ptr(), wgt.data_ptr(), V.data_ptr(), N * Dv, want.data_ptr(), F_, Hg, Wg, ws, c, 0, 0,
+         stream())
+    wsp = torch.empty(capi.load().turtle_sab_aggregate_tc_workspace(F_, Hg, Wg) // 4, device="cuda")
+    y = torch.full((F_, Hg * ws, Wg * ws, c), float("nan"), device="cuda", dtype=torch.float16 if rmode == 2 else torch.float32)
+    Vin = V.half() if h16 else V
+    call("turtle_sab_aggregate_tc", idx.data_ptr(), wgt.data_ptr(), Vin.data_ptr(), int(h16), N * Dv, y.data_ptr(), F_, Hg, Wg, ws,
+         c, rmode, wsp.data_ptr(), stream())
+    err = (y.float() - want).abs().max().item()
+    assert err < (4e-3 if rmode == 2 else 2e-3), err
+    # the far keys (top-k outside the tile's box) must be part of the sum: without them the error is O(0.1)
+    assert (y.float() - want).abs().mean().item() < 2e-4
+
+
 def test_library_is_loaded_from_tree():
     lib = capi.load()
     assert lib.turtle_abi_version() >= 1

@@ -62,6 +62,8 @@ _SIGS = {
     "turtle_sab_select_tc_workspace": ([_i32, _i32, _i32], C.c_longlong),
     "turtle_sab_select_tc": ([_fp, _fp, _i64, _i32, _i32, _i32, _i32, _fp, _i32, _fp, _fp, _fp, _fp], C.c_int),
     "turtle_sab_aggregate": ([_fp, _fp, _fp, _i64, _fp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _fp], C.c_int),
+    "turtle_sab_aggregate_tc_workspace": ([_i32, _i32, _i32], C.c_longlong),
+    "turtle_sab_aggregate_tc": ([_fp, _fp, _fp, _i32, _i64, _fp, _i32, _i32, _i32, _i32, _i32, _i32, _fp, _fp], C.c_int),
     "turtle_cast_f16": ([_fp, _fp, _i64, _fp], C.c_int),
     "turtle_add_posenc": ([_fp, _fp, _i32, _i32, _i32, _i32, _fp], C.c_int),
     "turtle_ln2d_bwd_workspace": ([_i32, C.c_longlong], C.c_longlong),

@@ -649,6 +649,21 @@ class FrameEngine:
         idx = self.ws.get("sab_idx", B, F_, N, capi.SAB_SLOTS, dtype=torch.int32)
         wgt = self.ws.get("sab_wgt", B, F_, N, capi.SAB_SLOTS)
         temp = self._w(sa + "temperature")
+        # aggregation on the tensor cores (csrc/sab_agg_tc.cu) reads an fp16 copy of the value rows kept next to the ring
+        agg_tc = (not t0 and self.mode == capi.TF32 and getattr(self.model, "sab_agg_tc", True) and c % 32 == 0
+                  and Dv % 256 == 0)
+        if agg_tc:
+            v16 = ring.shadow()
+            lo = slot if ring.count == 0 else ring.first_live
+            have = ring.v16_lo if ring.v16_lo is not None else slot
+            for s_ in list(range(lo, min(have, slot))) + [slot]:     # history slots without a copy yet (adopted caches), then the new frame
+                for b in range(B):
+                    self._meta = (6 * N * Dv, 0)
+                    self._call("turtle_cast_f16", _ptr(ring.vbuf[b, s_]), _ptr(v16[b, s_]), N * Dv, self.stream)
+            ring.v16_lo = min(lo, have)
+            agg_ws = self.ws.get("sab_aggws", (capi.load().turtle_sab_aggregate_tc_workspace(F_, Hg, Wg) + 3) // 4)
+        else:
+            ring.v16_lo = None
         for b in range(B):
             kf = _ptr(ring.kbuf[b, first])
             vf = _ptr(ring.vbuf[b, first])
@@ -662,6 +677,11 @@ class FrameEngine:
                 else:
                     self._call("turtle_sab_select", _ptr(qn[b]), kf, N * Dk, F_, Hg, Wg, Dk, _ptr(temp), 0,
                                _ptr(idx[b]), _ptr(wgt[b]), self.mode, self.stream)
+            if agg_tc:
+                self._meta = (F_ * N * Dv * (2 + (2 if r16 else 4)) + 8 * F_ * N * capi.SAB_SLOTS, 2 * F_ * N * 46 * Dv)
+                self._call("turtle_sab_aggregate_tc", _ptr(idx[b]), _ptr(wgt[b]), _ptr(v16[b, first]), 1, N * Dv, _ptr(agg[b]), F_,
+                           Hg, Wg, ws_, c, 2 if r16 else self.rnd, _ptr(agg_ws), self.stream)
+                continue
             self._meta = (4 * (2 * F_ * N * Dv + 2 * F_ * N * capi.SAB_SLOTS), 2 * F_ * N * 46 * Dv)
             self._call("turtle_sab_aggregate", _ptr(idx[b]), _ptr(wgt[b]), vf, N * Dv, _ptr(agg[b]), F_, Hg, Wg, ws_, c,
                  1 if t0 else 0, 2 if r16 else self.rnd, self.stream)
@@ -821,7 +841,8 @@ class FrameEngine:
         key = (tuple(inp.shape), inp.device.index, m.precision, bool(getattr(m, "half_intermediates", True)),
                bool(getattr(m, "fuse_layernorm", True)), bool(getattr(m, "sab_front_half", True)),
                bool(getattr(m, "fuse_gffw", False)), bool(getattr(m, "gffw_tail", False)),
-               tuple((r.serial, r.pos) for r in rings))
+               bool(getattr(m, "sab_agg_tc", True)),
+               tuple((r.serial, r.pos, r.shadow_ok() if hasattr(r, "shadow_ok") else None) for r in rings))
         ent = self.graphs.get(key)
         if ent is None:
             if key not in self._graph_seen:
@@ -837,7 +858,7 @@ class FrameEngine:
             static_in.copy_(inp)
             n0 = capi.launch_count
             # host-side ring state before the capture: a capture that fails launched nothing, but ran the host protocol
-            pre_state = [(r.pos, r.count, r._sig, r.epoch) for r in rings]
+            pre_state = [(r.pos, r.count, r._sig, r.epoch, r.v16_lo) for r in rings]
             g = torch.cuda.CUDAGraph()
             import gc
             gc_was = gc.isenabled()
@@ -849,8 +870,8 @@ class FrameEngine:
             except Exception as e:           # never let a failed capture cost a frame: restore the rings, run eagerly
                 if gc_was:
                     gc.enable()
-                for r, (pos, count, sig, ep) in zip(rings, pre_state):
-                    r.pos, r.count, r._sig, r.epoch = pos, count, sig, ep
+                for r, (pos, count, sig, ep, v16) in zip(rings, pre_state):
+                    r.pos, r.count, r._sig, r.epoch, r.v16_lo = pos, count, sig, ep, v16
                 capi.launch_count = n0
                 self._capture_failures = getattr(self, "_capture_failures", 0) + 1
                 self._graph_seen.discard(key)        # it gets another chance on a later visit
@@ -865,14 +886,14 @@ class FrameEngine:
                 return None
             if gc_was:
                 gc.enable()
-            post = [(r.pos, r.count, r._sig) for r in rings]
+            post = [(r.pos, r.count, r._sig, r.v16_lo) for r in rings]
             ent = self.graphs[key] = (g, static_in, out, ks, vs, rings, post, capi.launch_count - n0)
             self.graph_captures += 1
         else:
             g, static_in, out, ks, vs, rings, post, nl = ent
             static_in.copy_(inp)
-            for r, (pos, count, sig) in zip(rings, post):
-                r.pos, r.count, r._sig = pos, count, sig
+            for r, (pos, count, sig, v16) in zip(rings, post):
+                r.pos, r.count, r._sig, r.v16_lo = pos, count, sig, v16
             capi.launch_count += nl
         ent[0].replay()
         self.graph_replays += 1

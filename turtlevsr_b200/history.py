@@ -63,6 +63,8 @@ class _RingBase:
         # the other way round, so dropping the caches frees the ring without a GC cycle)
         self._sig = None
         self.epoch = 0                       # number of compactions so far (see "Stale views" above)
+        # SabRing only: slots [v16_lo, pos] carry a valid fp16 copy of their value rows (None: no slot does)
+        self.v16_lo = None
 
     def _register(self):
         for buf in (self.kbuf, self.vbuf):
@@ -121,16 +123,33 @@ class SabRing(_RingBase):
         self.B, self.N, self.Dk, self.Dv = B, N, Dk, Dv
         self.kbuf = torch.empty(B, self.slots, N, Dk, device=device, dtype=torch.float32)
         self.vbuf = torch.empty(B, self.slots, N, Dv, device=device, dtype=torch.float32)
+        # fp16 copy of the value rows for the tensor-core aggregation (csrc/sab_agg_tc.cu): allocated on first use, kept
+        # slot for slot next to vbuf; it is engine-internal and never handed to the caller
+        self.vbuf16 = None
         self._register()
 
     def geometry(self):
         return (self.B, self.N, self.Dk, self.Dv)
+
+    def shadow(self) -> torch.Tensor:
+        if self.vbuf16 is None:
+            self.vbuf16 = torch.empty(self.B, self.slots, self.N, self.Dv, device=self.vbuf.device, dtype=torch.float16)
+            self.v16_lo = None
+        return self.vbuf16
+
+    def shadow_ok(self) -> bool:
+        """Every live slot (the window before this frame's push) has a valid fp16 copy."""
+        return self.vbuf16 is not None and (self.count == 0 or (self.v16_lo is not None and self.v16_lo <= self.first_live))
 
     def _compact(self):
         c, a = self.count, self.first_live
         if c:
             self.kbuf[:, :c].copy_(self.kbuf[:, a:a + c])
             self.vbuf[:, :c].copy_(self.vbuf[:, a:a + c])
+            if self.vbuf16 is not None and self.v16_lo is not None:
+                self.vbuf16[:, :c].copy_(self.vbuf16[:, a:a + c])
+        if self.v16_lo is not None:
+            self.v16_lo = max(0, self.v16_lo - a)
         self.pos = c - 1
 
     def _inside_written(self, t: torch.Tensor) -> bool:
