@@ -158,6 +158,11 @@ int turtle_gemm(const TurtleGemmArgs *args, void *stream);
  * ------------------------------------------------------------------------------------- */
 int turtle_dwconv3x3(const float *x, int ldx, const float *w, const float *bias, float *y, int ldy, int NB,
                      int H, int W, int C, int fuse, int layout, int ws, int round_tf32, void *stream);
+/* layout 1 (dilated patch rows, the StateAlignBlock value rows T1:571-574) with a second, fp16 copy of every row
+ * written by the same kernel: y fp32 [NB, N, ws*ws*C], y16 fp16 likewise.  The tensor-core aggregation reads the copy
+ * (turtle_sab_aggregate_tc, v_dtype 1).  C % 32 == 0; TURTLE_ENOTSUP otherwise (caller: turtle_dwconv3x3 + turtle_cast_f16). */
+int turtle_dwconv3x3_patch_rows(const float *x, int ldx, const float *w, const float *bias, float *y, void *y16, int NB,
+                                int H, int W, int C, int ws, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * Transposed (channel) attention: ChannelAttention T1:680-702, FrameHistoryRouter T1:243-286,

@@ -302,6 +302,25 @@ def test_sab_aggregate_tc(Hg, Wg, ws, c, F_, rmode, h16):
     assert (y.float() - want).abs().mean().item() < 2e-4
 
 
+@pytest.mark.parametrize("bias", [False, True])
+def test_dwconv_patch_rows_fp16_copy(bias):
+    """turtle_dwconv3x3_patch_rows == turtle_dwconv3x3(layout 1) bit for bit, plus the fp16 copy of the same rows."""
+    NB, H, W, c, ws = 2, 24, 40, 64, 4
+    x = rnd(NB, H, W, c).cuda()
+    w9 = rnd(9, c, seed=1).cuda()
+    b = rnd(c, seed=2).cuda() if bias else None
+    N, Dv = (H // ws) * (W // ws), ws * ws * c
+    want = torch.empty(NB, N, Dv, device="cuda")
+    call("turtle_dwconv3x3", x.data_ptr(), c, w9.data_ptr(), b.data_ptr() if bias else None, want.data_ptr(), c, NB, H, W, c, 0, 1,
+         ws, 0, stream())
+    y = torch.full((NB, N, Dv), float("nan"), device="cuda")
+    y16 = torch.full((NB, N, Dv), float("nan"), device="cuda", dtype=torch.float16)
+    call("turtle_dwconv3x3_patch_rows", x.data_ptr(), c, w9.data_ptr(), b.data_ptr() if bias else None, y.data_ptr(),
+         y16.data_ptr(), NB, H, W, c, ws, stream())
+    assert torch.equal(y, want)
+    assert torch.equal(y16, want.half())
+
+
 def test_library_is_loaded_from_tree():
     lib = capi.load()
     assert lib.turtle_abi_version() >= 1

@@ -16,6 +16,8 @@ re-creates that boundary:
 """
 from __future__ import annotations
 
+import os
+
 from typing import List, Optional
 
 import torch
@@ -288,6 +290,9 @@ class TurtleNet(nn.Module):
                                         # to the three-kernel schedule, measured slower on B200: DESIGN.md section 3)
         self.gffw_tail = False          # tf32 mode: depthwise + gate + project_out of GatedFeedForward as one kernel
                                         # (turtle_gffw_tail; parity-equal, measured slower: DESIGN.md section 3)
+        # tf32 mode: StateAlignBlock aggregation on the tensor cores (csrc/sab_agg_tc.cu: dense key-box contraction + far
+        # top-k gather over an fp16 copy of the value rows); False / TURTLE_SAB_AGG_TC=0: the CUDA-core quad kernel
+        self.sab_agg_tc = os.environ.get("TURTLE_SAB_AGG_TC", "1") != "0"
         self._engine = None
 
     # -- public knobs ------------------------------------------------------------------

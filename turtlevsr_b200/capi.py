@@ -46,6 +46,7 @@ _SIGS = {
     "turtle_gemm": ([C.POINTER(GemmArgs), _fp], C.c_int),
     "turtle_dwconv3x3": ([_fp, _i32, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _fp],
                          C.c_int),
+    "turtle_dwconv3x3_patch_rows": ([_fp, _i32, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _i32, _fp], C.c_int),
     "turtle_chan_gram": ([_fp, _i32, _i32, _fp, _i32, _i32, _i64, _i32, _i32, _i32, _fp, _fp, _fp, _i32, _fp],
                          C.c_int),
     "turtle_chan_softmax": ([_fp, _fp, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _fp, _fp, _fp], C.c_int),

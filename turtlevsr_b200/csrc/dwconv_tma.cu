@@ -25,6 +25,7 @@ struct alignas(64) DwParams {
     CUtensorMap map;
     const float *w9, *bias;
     float *y;
+    __half *y16;               // layout 1 only, nullable: fp16 copy of the patch rows, element for element
     int ldy, NB, H, W, C, Cout, fuse, layout, ws, rnd;
     int tiles_x, tiles_y, cblocks;
     long long nitems;
@@ -179,7 +180,13 @@ __global__ void __launch_bounds__(256, 2) dwconv_tma_kernel(const __grid_constan
                 } else {
                     long long n = (long long)(py % Hg) * Wg + (px % Wg);
                     long long e = ((long long)(py / Hg) * p.ws + (px / Wg)) * p.Cout + c0;
-                    stg_stream(p.y + (((long long)nb * Hg * Wg + n) * p.ws * p.ws) * p.Cout + e, o);
+                    const long long oo = (((long long)nb * Hg * Wg + n) * p.ws * p.ws) * p.Cout + e;
+                    stg_stream(p.y + oo, o);
+                    if (p.y16) {
+                        __half2 h0 = __floats2half2_rn(o.x, o.y), h1 = __floats2half2_rn(o.z, o.w);
+                        *reinterpret_cast<uint2 *>(p.y16 + oo) =
+                            make_uint2(*reinterpret_cast<uint32_t *>(&h0), *reinterpret_cast<uint32_t *>(&h1));
+                    }
                 }
             }
         }
@@ -215,12 +222,21 @@ int launch(const DwParams &p, cudaStream_t s) {
 }  // namespace
 
 // returns TURTLE_ENOTSUP when the shape does not fit the tiled kernel (caller falls back)
+int turtle_dwconv3x3_tma_ex(const float *x, int ldx, const float *w, const float *bias, float *y, void *y16, int ldy, int NB,
+                            int H, int W, int C, int fuse, int layout, int ws, int rnd, void *stream);
 int turtle_dwconv3x3_tma(const float *x, int ldx, const float *w, const float *bias, float *y, int ldy, int NB, int H,
                          int W, int C, int fuse, int layout, int ws, int rnd, void *stream) {
+    return turtle_dwconv3x3_tma_ex(x, ldx, w, bias, y, nullptr, ldy, NB, H, W, C, fuse, layout, ws, rnd, stream);
+}
+
+// y16 (nullable, layout 1 only): the patch rows are written a second time as fp16
+int turtle_dwconv3x3_tma_ex(const float *x, int ldx, const float *w, const float *bias, float *y, void *y16, int ldy, int NB,
+                            int H, int W, int C, int fuse, int layout, int ws, int rnd, void *stream) {
     const int Cout = fuse == 2 ? C / 2 : C;
     if (Cout % CK) return TURTLE_ENOTSUP;
     const bool io16 = rnd == 2;
     if (io16 && layout != 0) return TURTLE_ENOTSUP;
+    if (y16 && (layout != 1 || io16 || ((uintptr_t)y16 & 7))) return TURTLE_ENOTSUP;
     const uint64_t es = io16 ? 2 : 4;
     DwParams p{};
     uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
@@ -228,6 +244,7 @@ int turtle_dwconv3x3_tma(const float *x, int ldx, const float *w, const float *b
     uint32_t box[4] = {CK, HC, HR, 1};
     if (!turtle_get_tmap2(&p.map, x, 4, dims, str, box, 0, io16 ? 1 : 0)) return TURTLE_ENOTSUP;
     p.w9 = w; p.bias = bias; p.y = y; p.ldy = ldy;
+    p.y16 = reinterpret_cast<__half *>(y16);
     p.NB = NB; p.H = H; p.W = W; p.C = C; p.Cout = Cout; p.fuse = fuse; p.layout = layout; p.ws = ws; p.rnd = rnd;
     p.tiles_x = (W + TW - 1) / TW;
     p.tiles_y = (H + TH - 1) / TH;

@@ -640,6 +640,16 @@ extern "C" int turtle_dwconv3x3(const float *x, int ldx, const float *w, const f
     return TURTLE_OK;
 }
 
+int turtle_dwconv3x3_tma_ex(const float *x, int ldx, const float *w, const float *bias, float *y, void *y16, int ldy, int NB,
+                            int H, int W, int C, int fuse, int layout, int ws, int rnd, void *stream);   // dwconv_tma.cu
+
+extern "C" int turtle_dwconv3x3_patch_rows(const float *x, int ldx, const float *w, const float *bias, float *y, void *y16,
+                                           int NB, int H, int W, int C, int ws, void *stream) {
+    if (!x || !w || !y || !y16 || NB < 1 || C < 4 || (ldx & 3) || ws < 1 || H % ws || W % ws) return TURTLE_EINVAL;
+    if ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)w) & 15) != 0) return TURTLE_EINVAL;
+    return turtle_dwconv3x3_tma_ex(x, ldx, w, bias, y, y16, C, NB, H, W, C, 0, 1, ws, 0, stream);
+}
+
 // ------------------------------------------------------------------------------------------
 // scale_cols
 // ------------------------------------------------------------------------------------------

@@ -40,13 +40,21 @@ constexpr int B_BYTES = (NCH / 32) * BBLK;  // 24576 B
 constexpr int STAGE = A_BYTES + B_BYTES;    // 40960 B
 constexpr int STAGES = 5;
 constexpr int EPI_WARPS = 8;
+// fused far-key gather (fp16 rows): eight more warps and a [128 queries x 256 halves] buffer next to a 4-stage ring
+constexpr int FAR_WARPS = 8;
+constexpr int STAGES_FAR = 4;
+constexpr int FARBUF = 128 * NCH * 2;       // 64 KB
 
 struct alignas(64) AggParams {
     CUtensorMap mapWd, mapV;
     int F, Hg, Wg, ws, c, tiles_x, tiles_y, nchunks;
     long long total_units;
     void *y;
-    int out16;
+    int out16, rnd_tf32;       // rnd_tf32: fp32 output rounded to TF32 by the epilogue (fused far gather only)
+    const int32_t *idx;        // fused far gather only
+    const float *wgt;
+    const void *v;
+    long long v_fstride;
 };
 
 __device__ __forceinline__ uint64_t desc_mn_tf32(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
@@ -123,12 +131,19 @@ __global__ void __launch_bounds__(128) sab_wd_build_kernel(const int32_t *__rest
 // ------------------------------------------------------------------------------------------------------------
 // 2. the contraction
 // ------------------------------------------------------------------------------------------------------------
-template <bool H16>
-__global__ void __launch_bounds__(384, 1) sab_agg_tc_kernel(const __grid_constant__ AggParams p) {
+// FAR (fp16 rows only): warps 12..19 gather the top-k rows that lie outside the tile's key box while the MMAs of the unit
+// run -- warp w owns query row w of the tile (16 queries), lane l the 8 columns 8l.. of the chunk: five coalesced 512-byte
+// row reads per query, summed in fp32 and parked as fp16 in `farbuf` ([query][32 x 16 B], 16-byte chunks XOR-swizzled with
+// the query index so that the epilogue's row-per-thread reads are conflict free); the epilogue adds them to the
+// accumulator.  (Opt-in, TURTLE_SAB_FAR_FUSED=1: measured slower than the separate gather pass, see the host code.)
+template <bool H16, bool FAR>
+__global__ void __launch_bounds__(FAR ? 640 : 384, 1) sab_agg_tc_kernel(const __grid_constant__ AggParams p) {
+    static_assert(!FAR || H16, "the fused far gather exists for fp16 rows");
     constexpr int RPS = H16 ? 2 : 1;                 // key rows per stage
     constexpr int NKB = KR / RPS;                    // stages per (fully interior) unit
+    constexpr int STAGES = FAR ? STAGES_FAR : ::STAGES;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2], ffull_bar, fempty_bar;
     __shared__ uint32_t tmem_base_sh;
     pdl_trigger();
     if (threadIdx.x == 32) {
@@ -136,6 +151,7 @@ __global__ void __launch_bounds__(384, 1) sab_agg_tc_kernel(const __grid_constan
         tma_prefetch_map(&p.mapV);
     }
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t farbuf = smem0 + STAGES * STAGE;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles = p.tiles_x * p.tiles_y;
     if (threadIdx.x == 0) {
@@ -147,6 +163,8 @@ __global__ void __launch_bounds__(384, 1) sab_agg_tc_kernel(const __grid_constan
             mbar_init(smem_u32(&tfull_bar[s]), 1);
             mbar_init(smem_u32(&tempty_bar[s]), EPI_WARPS);
         }
+        mbar_init(smem_u32(&ffull_bar), FAR_WARPS);
+        mbar_init(smem_u32(&fempty_bar), EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -229,7 +247,7 @@ __global__ void __launch_bounds__(384, 1) sab_agg_tc_kernel(const __grid_constan
             }
             umma_commit(smem_u32(&tfull_bar[acc]));
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 4 + EPI_WARPS) {
         // ------------------------------ epilogue: 8 warps ------------------------------
         // warp 4+ew: TMEM lane quarter ew & 3 (queries 32*(ew&3)..+31 of the tile), 128-column half ew >> 2
         const int ew = warp - 4, quarter = ew & 3, chalf = ew >> 2;
@@ -242,6 +260,7 @@ __global__ void __launch_bounds__(384, 1) sab_agg_tc_kernel(const __grid_constan
             const int acc = it & 1;
             const int qy = qy0 + row / QTW, qx = qx0 + row % QTW;
             const bool live = qy < p.Hg && qx < p.Wg;
+            if (FAR) mbar_wait(smem_u32(&ffull_bar), it & 1);
             mbar_wait(smem_u32(&tfull_bar[acc]), (it >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * NCH + chalf * (NCH / 2);
@@ -250,6 +269,22 @@ __global__ void __launch_bounds__(384, 1) sab_agg_tc_kernel(const __grid_constan
                 float v[32];
                 __syncwarp();
                 tmem_ld32(trow + j * 32, v);
+                if (FAR) {
+                    const uint32_t frow = farbuf + (uint32_t)row * 512u;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint32_t x0, x1, x2, x3;
+                        asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
+                                     : "r"(frow + ((((uint32_t)(chalf * 16 + j * 4 + g)) ^ ((uint32_t)row & 31u)) << 4)));
+                        const uint32_t xs[4] = {x0, x1, x2, x3};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 xf = __half22float2(*reinterpret_cast<const __half2 *>(&xs[e]));
+                            v[8 * g + 2 * e] += xf.x;
+                            v[8 * g + 2 * e + 1] += xf.y;
+                        }
+                    }
+                }
                 if (live) {
                     const int e = nch * NCH + chalf * (NCH / 2) + j * 32;        // first of 32 columns, all in one patch pixel
                     const int pp = e / p.c, d = e - pp * p.c;
@@ -267,13 +302,92 @@ __global__ void __launch_bounds__(384, 1) sab_agg_tc_kernel(const __grid_constan
                     } else {
                         float4 *dst = reinterpret_cast<float4 *>(reinterpret_cast<float *>(p.y) + o);
 #pragma unroll
-                        for (int g = 0; g < 8; ++g) dst[g] = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                        for (int g = 0; g < 8; ++g) {
+                            const float4 t4 = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                            dst[g] = p.rnd_tf32 ? rna_tf32(t4) : t4;
+                        }
                     }
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
+            if (lane == 0) {
+                mbar_arrive(smem_u32(&tempty_bar[acc]));
+                if (FAR) mbar_arrive(smem_u32(&fempty_bar));
+            }
+        }
+    }
+    if (FAR && warp >= 4 + EPI_WARPS) {
+        // ------------------------------ far-key gather: 8 warps ------------------------------
+        const int fw = warp - 4 - EPI_WARPS;             // query row of the tile
+        const int N = p.Hg * p.Wg, dvv = p.ws * p.ws * p.c / 8;
+        int it = 0;
+        for (long long u = blockIdx.x; u < p.total_units; u += gridDim.x, ++it) {
+            int nch, f, tile, qy0, qx0, kr_lo, kr_hi;
+            decode(u, nch, f, tile, qy0, qx0, kr_lo, kr_hi);
+            // lane l < 16 holds the (<= 5) far entries of query (qy0 + fw, qx0 + l)
+            int key[5];
+            float w[5];
+#pragma unroll
+            for (int t = 0; t < 5; ++t) { key[t] = 0; w[t] = 0.f; }
+            const int qy = qy0 + fw, qx = qx0 + lane;
+            if (lane < QTW && qy < p.Hg && qx < p.Wg) {
+                const long long base = ((long long)f * N + (long long)qy * p.Wg + qx) * TURTLE_SAB_SLOTS;
+                int ids[5];
+                float ws5[5];
+#pragma unroll
+                for (int t = 0; t < 5; ++t) { ids[t] = __ldg(p.idx + base + t); ws5[t] = __ldg(p.wgt + base + t); }
+#pragma unroll
+                for (int t = 0; t < 5; ++t) {
+                    if (ids[t] < 0) continue;
+                    const int ky = ids[t] / p.Wg, ry = ky - (qy0 - 4), rx = ids[t] - ky * p.Wg - (qx0 - 4);
+                    if (ry >= 0 && ry < KR && rx >= 0 && rx < KW) continue;      // inside the box: the tensor cores do it
+                    key[t] = ids[t];
+                    w[t] = ws5[t];
+                }
+            }
+            const uint4 *vf = reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(p.v) + (long long)f * p.v_fstride) +
+                              (nch * (NCH / 8) + lane);
+            mbar_wait(smem_u32(&fempty_bar), (it & 1) ^ 1);      // the epilogue has read the previous unit's sums
+#pragma unroll 1
+            for (int j0 = 0; j0 < QTW; j0 += 2) {
+                uint4 x[2][5];
+                float wq[2][5];
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                    for (int t = 0; t < 5; ++t) {
+                        const int kk = __shfl_sync(0xffffffffu, key[t], j0 + jj);
+                        wq[jj][t] = __shfl_sync(0xffffffffu, w[t], j0 + jj);
+                        x[jj][t] = wq[jj][t] != 0.f ? __ldg(vf + (long long)kk * dvv) : make_uint4(0u, 0u, 0u, 0u);
+                    }
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    float a[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) a[e] = 0.f;
+#pragma unroll
+                    for (int t = 0; t < 5; ++t) {
+                        const uint32_t xs[4] = {x[jj][t].x, x[jj][t].y, x[jj][t].z, x[jj][t].w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 xf = __half22float2(*reinterpret_cast<const __half2 *>(&xs[e]));
+                            a[2 * e] = fmaf(wq[jj][t], xf.x, a[2 * e]);
+                            a[2 * e + 1] = fmaf(wq[jj][t], xf.y, a[2 * e + 1]);
+                        }
+                    }
+                    const __half2 h0 = __floats2half2_rn(a[0], a[1]), h1 = __floats2half2_rn(a[2], a[3]);
+                    const __half2 h2 = __floats2half2_rn(a[4], a[5]), h3 = __floats2half2_rn(a[6], a[7]);
+                    const int r = fw * QTW + j0 + jj;
+                    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(farbuf + (uint32_t)r * 512u +
+                                                                                  ((((uint32_t)lane) ^ ((uint32_t)r & 31u)) << 4)),
+                                 "r"(*reinterpret_cast<const uint32_t *>(&h0)), "r"(*reinterpret_cast<const uint32_t *>(&h1)),
+                                 "r"(*reinterpret_cast<const uint32_t *>(&h2)), "r"(*reinterpret_cast<const uint32_t *>(&h3))
+                                 : "memory");
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&ffull_bar));
         }
     }
     __syncwarp();
@@ -430,13 +544,23 @@ extern "C" int turtle_sab_aggregate_tc(const int32_t *idx, const float *wgt, con
         uint32_t box[4] = {(uint32_t)(128 / es), KW, h16 ? 2u : 1u, 1};
         if (!turtle_get_tmap2(&p.mapV, v, 4, dims, str, box, h16 ? 1 : 2, h16 ? 1 : 0)) return TURTLE_ENOTSUP;
     }
-    const size_t smem = (size_t)STAGES * STAGE + 1024;
+    p.idx = idx; p.wgt = wgt; p.v = v; p.v_fstride = v_fstride;
+    // Far gather inside the contraction kernel: OFF by default.  Measured (scripts/sab_micro.py, fp16 rows): 158 / 312 / 648 us
+    // fused against 154 / 274 / 514 us as two passes -- eight gather warps with two queries (ten 512-byte row reads) in
+    // flight each do not cover the L2 latency inside a unit's 5 us of MMAs, and more bytes in flight means more registers
+    // than 640 resident threads leave.  Both forms move the same bytes through the SM's L2 port, which is the bound.
+    static const bool far_fused = getenv("TURTLE_SAB_FAR_FUSED") && atoi(getenv("TURTLE_SAB_FAR_FUSED")) == 1;
+    const bool fused = h16 && far_fused;
+    p.rnd_tf32 = fused && round_mode == 1;
+    const size_t smem_far = (size_t)STAGES_FAR * STAGE + FARBUF + 1024;
+    const size_t smem = fused ? smem_far : (size_t)STAGES * STAGE + 1024;
     static bool configured_[TURTLE_MAX_DEVICES] = {};
     static int nsm_[TURTLE_MAX_DEVICES];
     const int dev_ = turtle_device();
     if (!configured_[dev_]) {
-        if (cudaFuncSetAttribute(sab_agg_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
-            cudaFuncSetAttribute(sab_agg_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        if (cudaFuncSetAttribute(sab_agg_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)STAGES * STAGE + 1024)) != cudaSuccess ||
+            cudaFuncSetAttribute(sab_agg_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)STAGES * STAGE + 1024)) != cudaSuccess ||
+            cudaFuncSetAttribute(sab_agg_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_far) != cudaSuccess)
             return TURTLE_ELAUNCH;
         int dev = 0;
         cudaGetDevice(&dev);
@@ -449,13 +573,18 @@ extern "C" int turtle_sab_aggregate_tc(const int32_t *idx, const float *wgt, con
     if (h16) {
         launch_pdl(sab_wd_build_kernel<true>, gwd, dim3(128), 0, st, idx, wgt, workspace, Hg, Wg, p.tiles_x);
         TURTLE_CHECK_LAUNCH();
-        launch_pdl(sab_agg_tc_kernel<true>, dim3((unsigned)grid), dim3(384), smem, st, p);
+        if (fused) {
+            launch_pdl(sab_agg_tc_kernel<true, true>, dim3((unsigned)grid), dim3(640), smem, st, p);
+            TURTLE_CHECK_LAUNCH();
+            return TURTLE_OK;
+        }
+        launch_pdl(sab_agg_tc_kernel<true, false>, dim3((unsigned)grid), dim3(384), smem, st, p);
         TURTLE_CHECK_LAUNCH();
         launch_pdl(sab_far_add_kernel<true>, gfar, dim3(256), 0, st, idx, wgt, v, v_fstride, y, Hg, Wg, ws, c, round_mode);
     } else {
         launch_pdl(sab_wd_build_kernel<false>, gwd, dim3(128), 0, st, idx, wgt, workspace, Hg, Wg, p.tiles_x);
         TURTLE_CHECK_LAUNCH();
-        launch_pdl(sab_agg_tc_kernel<false>, dim3((unsigned)grid), dim3(384), smem, st, p);
+        launch_pdl(sab_agg_tc_kernel<false, false>, dim3((unsigned)grid), dim3(384), smem, st, p);
         TURTLE_CHECK_LAUNCH();
         launch_pdl(sab_far_add_kernel<false>, gfar, dim3(256), 0, st, idx, wgt, v, v_fstride, y, Hg, Wg, ws, c, round_mode);
     }

@@ -629,8 +629,25 @@ class FrameEngine:
             self.conv1x1(_ptr(qkd), 2 * c, c, sa + "q2.weight", _ptr(red), 2 * c, P, 2 * c, bias=self._w(sa + "q2.bias"))
             self._call("turtle_sab_window_reduce", _ptr(red), 2 * c, _ptr(self._w(sa + "q2_dwconv.weight", "dw")),
                        _ptr(self._w(sa + "q2_dwconv.bias")), _ptr(qn), N * Dk, B, H, W, 2 * c, ws_, self.stream)
+        # aggregation on the tensor cores (csrc/sab_agg_tc.cu) reads an fp16 copy of the value rows kept next to the ring
+        agg_tc = (not t0 and self.mode == capi.TF32 and getattr(self.model, "sab_agg_tc", True) and c % 32 == 0
+                  and Dv % 256 == 0)
+        v16 = ring.shadow() if agg_tc else None
+        v16_new = False                  # the new slot's copy was written by the depthwise kernel itself
         for b in range(B):
             # v: depthwise 3x3 written directly as dilated patch rows into the ring slot
+            if agg_tc:
+                try:
+                    self._meta = (4 * Pimg * c * 2 + 2 * Pimg * c, 2 * 9 * Pimg * c)
+                    self._call("turtle_dwconv3x3_patch_rows", _ptr(vt, b * Pimg * c), c, _ptr(self._w(sa + "v_dwconv.weight", "dw")),
+                               _ptr(self._w(sa + "v_dwconv.bias")), _ptr(ring.vbuf[b, slot]), _ptr(v16[b, slot]), 1, H, W, c, ws_,
+                               self.stream)
+                    v16_new = True
+                    continue
+                except capi.TurtleKernelError as e:
+                    if e.code != capi.ENOTSUP:
+                        raise
+                    v16_new = False
             self.dwconv(_ptr(vt, b * Pimg * c), c, sa + "v_dwconv.weight", sa + "v_dwconv.bias", _ptr(ring.vbuf[b, slot]), c,
                         1, H, W, c, layout=1, ws=ws_)
             if t0:
@@ -649,14 +666,11 @@ class FrameEngine:
         idx = self.ws.get("sab_idx", B, F_, N, capi.SAB_SLOTS, dtype=torch.int32)
         wgt = self.ws.get("sab_wgt", B, F_, N, capi.SAB_SLOTS)
         temp = self._w(sa + "temperature")
-        # aggregation on the tensor cores (csrc/sab_agg_tc.cu) reads an fp16 copy of the value rows kept next to the ring
-        agg_tc = (not t0 and self.mode == capi.TF32 and getattr(self.model, "sab_agg_tc", True) and c % 32 == 0
-                  and Dv % 256 == 0)
         if agg_tc:
-            v16 = ring.shadow()
             lo = slot if ring.count == 0 else ring.first_live
             have = ring.v16_lo if ring.v16_lo is not None else slot
-            for s_ in list(range(lo, min(have, slot))) + [slot]:     # history slots without a copy yet (adopted caches), then the new frame
+            # history slots without a copy yet (adopted caches), then the new frame unless the depthwise kernel wrote it
+            for s_ in list(range(lo, min(have, slot))) + ([] if v16_new else [slot]):
                 for b in range(B):
                     self._meta = (6 * N * Dv, 0)
                     self._call("turtle_cast_f16", _ptr(ring.vbuf[b, s_]), _ptr(v16[b, s_]), N * Dv, self.stream)
