@@ -30,7 +30,8 @@ def close16(got, want, extra=1e-6):
 
 
 @pytest.mark.parametrize("fuse", [0, 1, 2])
-@pytest.mark.parametrize("B,C_,H,W", [(2, 64, 9, 14), (1, 320, 24, 40), (1, 192, 17, 33)])
+@pytest.mark.parametrize("B,C_,H,W", [(2, 64, 9, 14), (1, 320, 24, 40), (1, 192, 17, 33), (2, 128, 37, 300), (1, 64, 70, 129),
+                                      (1, 640, 23, 160)])
 def test_dwconv_fp16(fuse, B, C_, H, W):
     x = rnd(B, H, W, C_).half().cuda()                       # channels-last
     w = (rnd(C_, 1, 3, 3, seed=1) / 3).half()

@@ -240,11 +240,22 @@ int launch16(const Dw16Params &p, cudaStream_t s) {
 
 }  // namespace
 
+int turtle_dwconv3x3_h16_tc(const void *x, int ldx, const void *w9, const float *bias, void *y, int ldy, int NB, int H, int W,
+                            int C, int fuse, void *stream);       // dwconv16_tc.cu: the same conv as tcgen05 MMAs
+
 // x, w9, y are fp16 (ldx / ldy in halves); bias fp32.  TURTLE_ENOTSUP when the shape does not fit.
 int turtle_dwconv3x3_h16(const void *x, int ldx, const void *w9, const float *bias, void *y, int ldy, int NB, int H,
                          int W, int C, int fuse, void *stream) {
     const int Cout = fuse == 2 ? C / 2 : C;
     if (!x || !w9 || !y || NB < 1 || fuse < 0 || fuse > 2) return TURTLE_EINVAL;
+    // tensor-core form (dwconv16_tc.cu) only on request: TURTLE_DW_TC=N runs it for the fuse variants in bit mask N.
+    // Measured 2x SLOWER than the CUDA-core kernel on a 720p frame (14.1 vs 7.2 ms of depthwise time,
+    // profiles/r02s_dwconv_tc_ab.txt), so it is off by default and kept for the measurement only.
+    static const int tc_mask = getenv("TURTLE_DW_TC") ? atoi(getenv("TURTLE_DW_TC")) : 0;
+    if (tc_mask & (1 << fuse)) {
+        const int r = turtle_dwconv3x3_h16_tc(x, ldx, w9, bias, y, ldy, NB, H, W, C, fuse, stream);
+        if (r != TURTLE_ENOTSUP) return r;
+    }
     if (Cout % CK || (ldx & 7) || (ldy & 3) || (((uintptr_t)x) & 15) || (((uintptr_t)y | (uintptr_t)w9) & 7))
         return TURTLE_ENOTSUP;
     Dw16Params p{};

@@ -817,19 +817,20 @@ PFN_cuTensorMapEncodeTiled get_encode() {
 
 struct MapKey {
     const void *ptr;
-    uint64_t d0, d1, d2, d3, s1, s2, s3;
-    uint32_t b0, b1, b2, b3, rank, swz;
+    uint64_t d0, d1, d2, d3, d4, s1, s2, s3, s4;
+    uint32_t b0, b1, b2, b3, b4, rank, swz;
     bool operator==(const MapKey &o) const {
-        return swz == o.swz && ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && d3 == o.d3 && s1 == o.s1 && s2 == o.s2 &&
-               s3 == o.s3 && b0 == o.b0 && b1 == o.b1 && b2 == o.b2 && b3 == o.b3 && rank == o.rank;
+        return swz == o.swz && ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && d3 == o.d3 && d4 == o.d4 && s1 == o.s1 &&
+               s2 == o.s2 && s3 == o.s3 && s4 == o.s4 && b0 == o.b0 && b1 == o.b1 && b2 == o.b2 && b3 == o.b3 && b4 == o.b4 &&
+               rank == o.rank;
     }
 };
 struct MapKeyHash {
     size_t operator()(const MapKey &k) const {
         uint64_t h = (uint64_t)(uintptr_t)k.ptr * 0x9E3779B97F4A7C15ull;
         auto mix = [&](uint64_t v) { h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); };
-        mix(k.d0); mix(k.d1); mix(k.d2); mix(k.d3); mix(k.s1); mix(k.s2); mix(k.s3);
-        mix(((uint64_t)k.b0 << 32) | k.b1); mix(((uint64_t)k.b2 << 32) | k.b3); mix(k.rank); mix(k.swz);
+        mix(k.d0); mix(k.d1); mix(k.d2); mix(k.d3); mix(k.d4); mix(k.s1); mix(k.s2); mix(k.s3); mix(k.s4);
+        mix(((uint64_t)k.b0 << 32) | k.b1); mix(((uint64_t)k.b2 << 32) | k.b3); mix(k.b4); mix(k.rank); mix(k.swz);
         return (size_t)h;
     }
 };
@@ -851,9 +852,10 @@ bool turtle_get_tmap2(CUtensorMap *out, const void *ptr, int rank, const uint64_
     k.ptr = ptr;
     k.rank = (uint32_t)rank;
     k.swz = (uint32_t)swizzle128 | ((uint32_t)dtype << 8);
-    k.d0 = dims[0]; k.d1 = dims[1]; k.d2 = rank > 2 ? dims[2] : 0; k.d3 = rank > 3 ? dims[3] : 0;
-    k.s1 = strides[0]; k.s2 = rank > 2 ? strides[1] : 0; k.s3 = rank > 3 ? strides[2] : 0;
-    k.b0 = box[0]; k.b1 = box[1]; k.b2 = rank > 2 ? box[2] : 0; k.b3 = rank > 3 ? box[3] : 0;
+    if (rank < 2 || rank > 5) return false;
+    k.d0 = dims[0]; k.d1 = dims[1]; k.d2 = rank > 2 ? dims[2] : 0; k.d3 = rank > 3 ? dims[3] : 0; k.d4 = rank > 4 ? dims[4] : 0;
+    k.s1 = strides[0]; k.s2 = rank > 2 ? strides[1] : 0; k.s3 = rank > 3 ? strides[2] : 0; k.s4 = rank > 4 ? strides[3] : 0;
+    k.b0 = box[0]; k.b1 = box[1]; k.b2 = rank > 2 ? box[2] : 0; k.b3 = rank > 3 ? box[3] : 0; k.b4 = rank > 4 ? box[4] : 0;
     std::lock_guard<std::mutex> lk(g_map_mu);
     auto it = g_maps.find(k);
     if (it != g_maps.end()) {
@@ -862,7 +864,7 @@ bool turtle_get_tmap2(CUtensorMap *out, const void *ptr, int rank, const uint64_
     }
     PFN_cuTensorMapEncodeTiled enc = get_encode();
     if (!enc) return false;
-    cuuint32_t estr[4] = {1, 1, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUtensorMap m;
     CUresult r = enc(&m, dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void *>(ptr),
                      reinterpret_cast<const cuuint64_t *>(dims), reinterpret_cast<const cuuint64_t *>(strides),

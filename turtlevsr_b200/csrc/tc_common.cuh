@@ -128,6 +128,15 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// after tmem_wait_ld(): pins the loaded registers behind the wait (asm volatile statements keep their order, and every
+// later use of r[] now depends on this one) -- without it nothing stops the compiler from scheduling arithmetic on r[]
+// above the wait, where the asynchronous load has not written the registers yet
+__device__ __forceinline__ void tmem_pin(uint32_t (&r)[32]) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 8)
+        asm volatile("" : "+r"(r[i]), "+r"(r[i + 1]), "+r"(r[i + 2]), "+r"(r[i + 3]), "+r"(r[i + 4]), "+r"(r[i + 5]), "+r"(r[i + 6]),
+                          "+r"(r[i + 7]));
+}
 // registers -> TMEM (same 32x32b shape as tmem_ld32): thread t of the warp writes 32 columns of its lane
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
     asm volatile(
