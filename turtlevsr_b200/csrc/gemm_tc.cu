@@ -352,6 +352,7 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
     __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2], rfull_bar[EPI_WARPS][4], wres_bar;
     __shared__ uint32_t tmem_base_sh;
     __shared__ float2 lnstat[2][4][2][32];      // fused LN: (mean, M2) of each row half, [tile parity][quarter][chalf][lane]
+    __shared__ __align__(16) float lnwb[2][256]; // fused LN: weight / bias of the (single) n-group, staged once per CTA
     pdl_trigger();
     if (threadIdx.x == 32) {            // descriptor fetches overlap the barrier / TMEM set-up
         tma_prefetch_map(&p.mapW);
@@ -377,6 +378,12 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
     const long long ustride = PAIR ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
     constexpr int TPU = PAIR ? 2 : 1;                                   // pixel tiles per work unit
 
+    if (p.ln && threadIdx.x >= 128) {   // (launch constants, like the weights: safe to read before pdl_wait)
+        for (int i = threadIdx.x - 128; i < p.NG; i += 256) {
+            lnwb[0][i] = __ldg(p.ln_w + i);
+            lnwb[1][i] = __ldg(p.ln_b + i);
+        }
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(smem_u32(&full_bar[s]), 1);
@@ -684,8 +691,8 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
                         const int o0 = n0 + j * 32;
 #pragma unroll
                         for (int e = 0; e < 8; ++e) {
-                            const float4 w4 = __ldg(reinterpret_cast<const float4 *>(p.ln_w + o0 + 4 * e));
-                            const float4 b4 = __ldg(reinterpret_cast<const float4 *>(p.ln_b + o0 + 4 * e));
+                            const float4 w4 = *reinterpret_cast<const float4 *>(&lnwb[0][o0 + 4 * e]);      // (ngroups == 1: o0 < NG)
+                            const float4 b4 = *reinterpret_cast<const float4 *>(&lnwb[1][o0 + 4 * e]);
                             v[4 * e] = fmaf((v[4 * e] - mu) * rstd, w4.x, b4.x);
                             v[4 * e + 1] = fmaf((v[4 * e + 1] - mu) * rstd, w4.y, b4.y);
                             v[4 * e + 2] = fmaf((v[4 * e + 2] - mu) * rstd, w4.z, b4.z);
@@ -1003,7 +1010,7 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
         if (!turtle_get_tmap2(&p.mapW, a->Wt, 2, dims, str, box, 1, a16 ? 1 : 0)) return TURTLE_ENOTSUP;
     }
     p.total_units = (pair ? (tiles + 1) / 2 : tiles) * p.ngroups;
-    const size_t max_smem = 232448 - 6144;   // 227 KB opt-in limit minus the kernel's static smem (barriers, LN statistics)
+    const size_t max_smem = 232448 - 8192;   // 227 KB opt-in limit minus the kernel's static smem (barriers, LN statistics and weights)
     // resident weights: one n-group, no pairs, every CTA walks >= 2 tiles, and the whole [NG x K] matrix fits next to
     // the minimum ring (2 A stages) and the minimum staging boxes (2 per epilogue warp)
     // OFF by default: measured neutral on B200 (scripts/gemm_micro.py, every hot shape within +-1 us; 128->256 @235520
