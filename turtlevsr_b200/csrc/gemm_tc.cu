@@ -742,8 +742,10 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
                     pix = tile * TM + row;
                     live = pix < p.P;
                 }
+                const bool shuf_vec = p.store == TURTLE_STORE_SHUFFLE2 && !(p.ldo & 3) && !((uintptr_t)p.out & 15);
                 for (int c0 = chalf * 16; c0 < NG; c0 += 32) {
                     float v[16];
+                    float4 sv[4];
                     __syncwarp();
                     tmem_ld16(trow + c0, v);
                     const int o0 = n0 + c0;
@@ -775,6 +777,8 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
                             float *op = p.out + (((long long)tb * Ho + (py >> 1)) * Wo + (px >> 1)) * p.ldo +
                                         ((py & 1) * 2 + (px & 1));
                             op[(o + 0) * 4] = t.x; op[(o + 1) * 4] = t.y; op[(o + 2) * 4] = t.z; op[(o + 3) * 4] = t.w;
+                        } else if (shuf_vec) {
+                            sv[q] = t;                // stored below: four 16-byte stores instead of sixteen scalar ones
                         } else {
                             const int Wo = p.W << 1;
                             float *op = p.out + (((long long)tb * (p.H << 1) + 2 * py) * Wo + 2 * px) * p.ldo + (o >> 2);
@@ -783,6 +787,16 @@ __global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant_
                             op[(long long)Wo * p.ldo] = t.z;
                             op[(long long)Wo * p.ldo + p.ldo] = t.w;
                         }
+                    }
+                    if (shuf_vec && live) {
+                        // PixelShuffle(2): conv channel 4c+s lands in channel c of sub-pixel s, so the 16 conv channels of
+                        // this chunk are 4 consecutive output channels at each of the 4 sub-pixels
+                        const int Wo = p.W << 1;
+                        float *op = p.out + (((long long)tb * (p.H << 1) + 2 * py) * Wo + 2 * px) * p.ldo + (o0 >> 2);
+                        *reinterpret_cast<float4 *>(op) = make_float4(sv[0].x, sv[1].x, sv[2].x, sv[3].x);
+                        *reinterpret_cast<float4 *>(op + p.ldo) = make_float4(sv[0].y, sv[1].y, sv[2].y, sv[3].y);
+                        *reinterpret_cast<float4 *>(op + (long long)Wo * p.ldo) = make_float4(sv[0].z, sv[1].z, sv[2].z, sv[3].z);
+                        *reinterpret_cast<float4 *>(op + (long long)Wo * p.ldo + p.ldo) = make_float4(sv[0].w, sv[1].w, sv[2].w, sv[3].w);
                     }
                 }
             }
