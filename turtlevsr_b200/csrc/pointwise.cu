@@ -116,13 +116,15 @@ __global__ void __launch_bounds__(256) conv3x3_first_quad_kernel(const float *__
         ws[i] = w[((int64_t)co * CIN + ci) * 9 + tap];
     }
     __syncthreads();
-    const int groups = Cout >> 2, W4 = W >> 2;
-    const int64_t total = (int64_t)B * H * W4 * groups;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    // 32-bit index arithmetic (the host checks that the item count fits): three 64-bit divisions per item were as many
+    // instructions as the item's 432 FMAs
+    const unsigned groups = (unsigned)Cout >> 2, W4 = (unsigned)W >> 2;
+    const unsigned total = (unsigned)B * (unsigned)H * W4 * groups;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int g = (int)(idx % groups);
-        const int64_t q = idx / groups;
-        const int px0 = (int)(q % W4) * 4, py = (int)((q / W4) % H);
-        const int64_t b = q / ((int64_t)W4 * H);
+        const unsigned q = idx / groups, qy = q / W4;
+        const int px0 = (int)(q - qy * W4) * 4, py = (int)(qy % (unsigned)H);
+        const int64_t b = qy / (unsigned)H;
         float4 acc[4];
         const float4 b4 = bias ? *reinterpret_cast<const float4 *>(bias + g * 4) : make_float4(0, 0, 0, 0);
 #pragma unroll
@@ -168,7 +170,7 @@ extern "C" int turtle_conv3x3_first(const float *x, const float *w, const float 
     size_t smem = (size_t)9 * Cin * Cout * sizeof(float);
     if (smem > 48 * 1024) return TURTLE_EINVAL;
     int64_t total = (int64_t)B * H * W * (Cout >> 2);
-    if ((Cin == 3 || Cin == 6) && !(W & 3) && !((uintptr_t)y & 15)) {
+    if ((Cin == 3 || Cin == 6) && !(W & 3) && !((uintptr_t)y & 15) && total < (1LL << 32)) {
         const int64_t quads = total >> 2;
         const unsigned grid = (unsigned)(cdiv64(quads, 256) < 148 * 8 ? cdiv64(quads, 256) : 148 * 8);
         if (Cin == 3)
@@ -252,12 +254,12 @@ __global__ void __launch_bounds__(256) conv3x3_last_warp_kernel(const float *__r
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, sub = lane >> 4, l16 = lane & 15;
-    const int W8 = (Wc + 7) >> 3;
-    const int64_t nw = (int64_t)B * Hc * W8;
-    for (int64_t wi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wi < nw;
-         wi += (int64_t)gridDim.x * (blockDim.x >> 5)) {
-        const int x0 = (int)(wi % W8) * 8, py = (int)((wi / W8) % Hc);
-        const int64_t b = wi / ((int64_t)W8 * Hc);
+    const unsigned W8 = (unsigned)(Wc + 7) >> 3;
+    const unsigned nw = (unsigned)B * (unsigned)Hc * W8;           // (32-bit index arithmetic: the host checks the range)
+    for (unsigned wi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wi < nw; wi += gridDim.x * (blockDim.x >> 5)) {
+        const unsigned wy = wi / W8;
+        const int x0 = (int)(wi - wy * W8) * 8, py = (int)(wy % (unsigned)Hc);
+        const int64_t b = wy / (unsigned)Hc;
         float acc[4][3];
 #pragma unroll
         for (int pp = 0; pp < 4; ++pp) acc[pp][0] = acc[pp][1] = acc[pp][2] = 0.f;
@@ -313,7 +315,7 @@ extern "C" int turtle_conv3x3_last(const float *x, const float *w, const float *
                                    int cur_coff, float *out, int B, int H, int W, int Cin, int Cout, int Hc, int Wc,
                                    void *stream) {
     if (!x || !w || !cur || !out || Cout < 1 || Cout > 4 || (Cin & 3) || Hc > H || Wc > W) return TURTLE_EINVAL;
-    if (Cin == 64 && Cout <= 3 && !((uintptr_t)x & 15)) {
+    if (Cin == 64 && Cout <= 3 && !((uintptr_t)x & 15) && (int64_t)B * Hc * ((Wc + 7) >> 3) < (1LL << 31)) {
         const int64_t nw = (int64_t)B * Hc * ((Wc + 7) >> 3);
         const int64_t blocks = cdiv64(nw, 8);
         launch_pdl(conv3x3_last_warp_kernel, dim3((unsigned)(blocks < 148 * 8 ? blocks : 148 * 8)), dim3(256), 0, as_stream(stream), x, w, bias, cur, cur_ld, cur_coff, out, B, H, W, Cout, Hc, Wc);
