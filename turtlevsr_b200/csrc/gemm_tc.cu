@@ -337,31 +337,21 @@ struct alignas(64) Tc2Params {
     int ldo, store, round_out;
 };
 
-constexpr int EPI_WARPS = 8;                            // default epilogue width; EW = 16 is the wide variant (below)
-constexpr int EPI_WARPS_MAX = 16;
+constexpr int EPI_WARPS = 8;
 constexpr int EPI_BUF = 32 * 128;                       // one 32-row x 32-column staging box (4 KB)
+constexpr int EPI_BYTES = EPI_WARPS * 2 * EPI_BUF;      // 64 KB with two boxes per warp (the minimum)
 
 // PAIR: the kernel runs as clusters of two CTAs sharing one M256 x NG MMA (tcgen05 cta_group::2).  Each CTA stages its
 // own 128 rows of A and HALF of the weight rows of the n-group (the tensor core reads the other half from the peer's
 // shared memory): the operand feed per MAC drops by a third and a stage shrinks from 16+NG/8 KB to 16+NG/16 KB.  Loads
 // complete on the leader's full barrier, the leader's MMA thread multicasts its commits to both CTAs' empty / tfull
 // barriers, and both CTAs' epilogue warps hand the accumulator back on the leader's tempty barrier.
-//
-// EW = number of epilogue warps (8 or 16).  The epilogue is a latency chain per warp (ncu: 2 epilogue warps per scheduler,
-// ~11 cycles per issued instruction, 27 % issue-active on the 58880-pixel launches), and a warp can only read its own
-// TMEM lane quarter, so the way to shorten the chain is more warps per quarter: with EW = 16 the 32-column chunks of a
-// row are dealt round-robin to FOUR warps (chunk j -> warp group j % 4) instead of two.
-template <bool A16, bool O16, bool PAIR, int EW>
-__global__ void __launch_bounds__(EW == 16 ? 576 : 384, 1) gemm_tc2_kernel(const __grid_constant__ Tc2Params p) {
-    constexpr int NCH = EW / 4;                 // warps per TMEM lane quarter = column groups
-    // warp roles: 0 = TMA producer, 1 = MMA issuer, then (EW = 8) 2 = TMEM allocator, 3 idle, 4.. epilogue; the wide variant
-    // has no spare warps: warp 0 also allocates TMEM (18 warps; the register file is granted in units of four warps, so the
-    // cap is 96 registers per thread either way -- a 112-register build of this shape fails to launch)
-    constexpr int FIRST_EPI = EW == 16 ? 2 : 4, ALLOC_WARP = EW == 16 ? 0 : 2;
+template <bool A16, bool O16, bool PAIR>
+__global__ void __launch_bounds__(384, 1) gemm_tc2_kernel(const __grid_constant__ Tc2Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2], rfull_bar[EW][4], wres_bar;
+    __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2], rfull_bar[EPI_WARPS][4], wres_bar;
     __shared__ uint32_t tmem_base_sh;
-    __shared__ float2 lnstat[2][4][NCH][32];    // fused LN: (mean, M2) of each column group, [tile parity][quarter][group][lane]
+    __shared__ float2 lnstat[2][4][2][32];      // fused LN: (mean, M2) of each row half, [tile parity][quarter][chalf][lane]
     __shared__ __align__(16) float lnwb[2][256]; // fused LN: weight / bias of the (single) n-group, staged once per CTA
     pdl_trigger();
     if (threadIdx.x == 32) {            // descriptor fetches overlap the barrier / TMEM set-up
@@ -388,8 +378,8 @@ __global__ void __launch_bounds__(EW == 16 ? 576 : 384, 1) gemm_tc2_kernel(const
     const long long ustride = PAIR ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
     constexpr int TPU = PAIR ? 2 : 1;                                   // pixel tiles per work unit
 
-    if (p.ln && threadIdx.x >= FIRST_EPI * 32) {   // (launch constants, like the weights: safe to read before pdl_wait)
-        for (int i = threadIdx.x - FIRST_EPI * 32; i < p.NG; i += EW * 32) {
+    if (p.ln && threadIdx.x >= 128) {   // (launch constants, like the weights: safe to read before pdl_wait)
+        for (int i = threadIdx.x - 128; i < p.NG; i += 256) {
             lnwb[0][i] = __ldg(p.ln_w + i);
             lnwb[1][i] = __ldg(p.ln_b + i);
         }
@@ -401,15 +391,15 @@ __global__ void __launch_bounds__(EW == 16 ? 576 : 384, 1) gemm_tc2_kernel(const
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(smem_u32(&tfull_bar[s]), 1);
-            mbar_init(smem_u32(&tempty_bar[s]), EW * TPU);
+            mbar_init(smem_u32(&tempty_bar[s]), EPI_WARPS * TPU);
         }
-        for (int w = 0; w < EW; ++w) {
+        for (int w = 0; w < EPI_WARPS; ++w) {
             for (int b = 0; b < 4; ++b) mbar_init(smem_u32(&rfull_bar[w][b]), 1);
         }
         mbar_init(smem_u32(&wres_bar), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == ALLOC_WARP) {
+    if (warp == 2) {
         if (PAIR) {
             asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_sh))
                          : "memory");
@@ -517,12 +507,12 @@ __global__ void __launch_bounds__(EW == 16 ? 576 : 384, 1) gemm_tc2_kernel(const
             if (PAIR) umma_commit_pair(smem_u32(&tfull_bar[acc]));
             else umma_commit(smem_u32(&tfull_bar[acc]));
         }
-    } else if (warp >= FIRST_EPI) {
+    } else if (warp >= 4) {
         // ------------------------------ epilogue: 8 warps ------------------------------
         // warp (4+ew): TMEM lane quarter ew&3 (rows 32*(ew&3)..+31 of the tile), column chunks of
         // parity ew>>2.  Each warp stages its own 32x32 boxes and issues its own TMA loads/stores,
         // so the only synchronisation inside the epilogue is __syncwarp.
-        const int ew = warp - FIRST_EPI, quarter = warp & 3, chalf = ew >> 2;     // (a warp reads TMEM lanes 32*(warp%4)..+31)
+        const int ew = warp - 4, quarter = ew & 3, chalf = ew >> 2;
         const uint32_t mybuf = epi0 + ew * ((uint32_t)p.epi_boxes * EPI_BUF);
         const int eflags = (p.bias ? 1 : 0) | (p.act == TURTLE_ACT_GELU ? 2 : 0) | (p.scale ? 4 : 0);
         int it = 0;
@@ -530,7 +520,7 @@ __global__ void __launch_bounds__(EW == 16 ? 576 : 384, 1) gemm_tc2_kernel(const
         uint32_t rph = 0;                                    // box ring: residual-barrier phase bit per box
         // ---- box ring of the fp32-output paths (see the tma_epi branch below) ----
         const int NB = p.epi_boxes;                          // 4 KB boxes owned by this warp
-        const int n_my = (NG / 32 - chalf + NCH - 1) / NCH;  // 32-column chunks j = chalf, chalf+NCH, ... of this warp (may be 0)
+        const int n_my = (NG / 32 - chalf + 1) / 2;          // 32-column chunks j = chalf, chalf+2, ... of this warp
         const int spu = p.ln ? 2 * n_my : n_my;              // ring slots per work unit
         int slot = 0, box = 0;                               // running slot index and its box (slot % NB)
         // lane 0: cursor of the residual requests -- next slot, its position inside its unit, its box, and the unit's
@@ -548,14 +538,14 @@ __global__ void __launch_bounds__(EW == 16 ? 576 : 384, 1) gemm_tc2_kernel(const
                 if (r_q < n_my) {                             // (LN output slots have nothing to load)
                     const uint32_t rb = smem_u32(&rfull_bar[ew][r_box]);
                     mbar_expect_tx(rb, EPI_BUF);
-                    tma_load_2d(mybuf + (uint32_t)r_box * EPI_BUF, &p.mapRes, r_n0 + (chalf + NCH * r_q) * 32, r_m0, rb);
+                    tma_load_2d(mybuf + (uint32_t)r_box * EPI_BUF, &p.mapRes, r_n0 + (chalf + 2 * r_q) * 32, r_m0, rb);
                 }
                 ++next_r;
                 if (++r_box == NB) r_box = 0;
                 if (++r_q == spu) { r_q = 0; r_u += ustride; }
             }
         };
-        if (p.tma_epi && !O16 && p.res && lane == 0 && n_my > 0) issue_res(NB - 1);      // all boxes are free at the start
+        if (p.tma_epi && !O16 && p.res && lane == 0) issue_res(NB - 1);      // all boxes are free at the start
         for (long long u = u0; u < p.total_units; u += ustride, ++it) {
             const int ng = (int)(u % p.ngroups);
             const long long tile = (u / p.ngroups) * TPU + rank;
@@ -570,30 +560,21 @@ __global__ void __launch_bounds__(EW == 16 ? 576 : 384, 1) gemm_tc2_kernel(const
                 // fp16 output: contiguous chunk range per warp, two 32-column chunks (= one 128-byte row) per TMA
                 // store where possible -- TMA store cost scales with the number of row segments, not bytes.
                 const int m0 = (int)(tile * TM) + quarter * 32;
-                // the chunks are dealt to the NCH column groups in contiguous runs of an even number of chunks where possible
-                const int nch = NG / 32;
-                int jb, je;
-                if (NCH == 2) {
-                    const int h0 = (nch + 1) / 2;
-                    jb = chalf ? h0 : 0; je = chalf ? nch : h0;
-                } else {
-                    const int per = nch <= NCH ? 1 : ((nch + NCH - 1) / NCH + 1) & ~1;
-                    jb = min(chalf * per, nch); je = min(jb + per, nch);
-                }
+                const int nch = NG / 32, h0 = (nch + 1) / 2;
+                const int jb = chalf ? h0 : 0, je = chalf ? nch : h0;
                 const int NBo = p.epi_boxes;              // staging boxes of this warp (2..4): a box is reused NBo groups later
                 for (int j = jb; j < je; ++gw) {
                     const int nc = (je - j >= 2) ? 2 : 1;
                     const int b = (int)(gw % (uint32_t)NBo);
                     const uint32_t buf = mybuf + b * EPI_BUF;
                     if (lane == 0 && gw >= (uint32_t)NBo) {       // the store that last used this box has read it
-                        if (NBo == 1) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                        else if (NBo == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                        if (NBo == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                         else if (NBo == 3) asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
                         else asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
                     }
                     __syncwarp();
                     uint32_t r2[2][32];
-                    const bool two = EW == 8 && p.o16_2ld && nc == 2;
+                    const bool two = p.o16_2ld && nc == 2;
                     if (two) {
                         tmem_ld32_nowait(trow + j * 32, r2[0]);
                         tmem_ld32_nowait(trow + (j + 1) * 32, r2[1]);
@@ -641,37 +622,18 @@ __global__ void __launch_bounds__(EW == 16 ? 576 : 384, 1) gemm_tc2_kernel(const
                 float mean = 0.f, M2 = 0.f, cnt = 0.f, mu = 0.f, rstd = 0.f;
                 for (int q = 0; q < spu; ++q, ++slot) {
                     const int jj = q < n_my ? q : q - n_my;
-                    const int j = chalf + NCH * jj;
+                    const int j = chalf + 2 * jj;
                     const uint32_t buf = mybuf + (uint32_t)box * EPI_BUF;
                     if (p.ln && q == n_my) {
                         // exchange the row statistics with the warp that owns the other chunk parity of the same rows
                         tmem_wait_st();
                         lnstat[it & 1][quarter][chalf][lane] = make_float2(mean, M2);
-                        if (NCH == 2) {
-                            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-                            const float2 o = lnstat[it & 1][quarter][chalf ^ 1][lane];
-                            const float dl = o.x - mean;
-                            mu = fmaf(0.5f, dl, mean);
-                            const float var = (M2 + o.y + dl * dl * cnt * 0.5f) / (2.0f * cnt);
-                            rstd = rsqrtf(var + 1e-5f);
-                        } else {
-                            const int ngrp = NG / 32 < NCH ? NG / 32 : NCH;        // column groups that own chunks
-                            asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "r"(32 * ngrp) : "memory");
-                            // every group merges the partials in the same order (Chan et al.), so all chunks of a row are
-                            // normalised with bit-identical statistics
-                            float2 a = lnstat[it & 1][quarter][0][lane];
-                            float na = 32.0f * (float)((NG / 32 + NCH - 1) / NCH);           // elements behind group 0's partial
-                            for (int g = 1; g < ngrp; ++g) {
-                                const float2 o = lnstat[it & 1][quarter][g][lane];
-                                const float no = 32.0f * (float)((NG / 32 - g + NCH - 1) / NCH);
-                                const float tot = na + no, dl = o.x - a.x;
-                                a.x = fmaf(dl, no / tot, a.x);
-                                a.y += o.y + dl * dl * (na * no / tot);
-                                na = tot;
-                            }
-                            mu = a.x;
-                            rstd = rsqrtf(a.y / na + 1e-5f);
-                        }
+                        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+                        const float2 o = lnstat[it & 1][quarter][chalf ^ 1][lane];
+                        const float dl = o.x - mean;
+                        mu = fmaf(0.5f, dl, mean);
+                        const float var = (M2 + o.y + dl * dl * cnt * 0.5f) / (2.0f * cnt);
+                        rstd = rsqrtf(var + 1e-5f);
                     }
                     __syncwarp();        // lane 0's wait_group.read of the previous slot precedes our writes to `buf`
                     float v[32];
@@ -685,19 +647,17 @@ __global__ void __launch_bounds__(EW == 16 ? 576 : 384, 1) gemm_tc2_kernel(const
                         const uint32_t rowaddr = buf + lane * 128;
                         float cs = 0.f;
 #pragma unroll
-                        constexpr int RB = EW == 16 ? 2 : 4;     // residual vectors in flight per batch (register budget)
-#pragma unroll
-                        for (int e0 = 0; e0 < 8; e0 += RB) {
-                            float4 r[RB];
+                        for (int e0 = 0; e0 < 8; e0 += 4) {      // four residual vectors in flight per batch
+                            float4 r[4];
                             if (p.res) {
 #pragma unroll
-                                for (int e = 0; e < RB; ++e)
+                                for (int e = 0; e < 4; ++e)
                                     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
                                                  : "=f"(r[e].x), "=f"(r[e].y), "=f"(r[e].z), "=f"(r[e].w)
                                                  : "r"(rowaddr + (((uint32_t)(e0 + e) ^ ((uint32_t)lane & 7u)) << 4)));
                             }
 #pragma unroll
-                            for (int e = 0; e < RB; ++e) {
+                            for (int e = 0; e < 4; ++e) {
                                 const int i = 4 * (e0 + e);
                                 float4 t = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                                 if (p.res) { t.x += r[e].x; t.y += r[e].y; t.z += r[e].z; t.w += r[e].w; }
@@ -719,15 +679,9 @@ __global__ void __launch_bounds__(EW == 16 ? 576 : 384, 1) gemm_tc2_kernel(const
                             tmem_st32(trow + j * 32, v);
                             // chunk statistics (two-pass inside the chunk), merged with Chan's formula
                             const float cm = cs * (1.0f / 32.0f);
-                            float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;      // four chains: a single one is 32 dependent FMAs
+                            float cM2 = 0.f;
 #pragma unroll
-                            for (int e = 0; e < 32; e += 4) {
-                                q0 = fmaf(v[e] - cm, v[e] - cm, q0);
-                                q1 = fmaf(v[e + 1] - cm, v[e + 1] - cm, q1);
-                                q2 = fmaf(v[e + 2] - cm, v[e + 2] - cm, q2);
-                                q3 = fmaf(v[e + 3] - cm, v[e + 3] - cm, q3);
-                            }
-                            const float cM2 = (q0 + q1) + (q2 + q3);
+                            for (int e = 0; e < 32; ++e) cM2 = fmaf(v[e] - cm, v[e] - cm, cM2);
                             const float tot = cnt + 32.0f, delta = cm - mean;
                             mean = fmaf(delta, 32.0f / tot, mean);
                             M2 += cM2 + delta * delta * (cnt * 32.0f / tot);
@@ -789,7 +743,7 @@ __global__ void __launch_bounds__(EW == 16 ? 576 : 384, 1) gemm_tc2_kernel(const
                     live = pix < p.P;
                 }
                 const bool shuf_vec = p.store == TURTLE_STORE_SHUFFLE2 && !(p.ldo & 3) && !((uintptr_t)p.out & 15);
-                for (int c0 = chalf * 16; c0 < NG; c0 += NCH * 16) {
+                for (int c0 = chalf * 16; c0 < NG; c0 += 32) {
                     float v[16];
                     float4 sv[4];
                     __syncwarp();
@@ -860,7 +814,7 @@ __global__ void __launch_bounds__(EW == 16 ? 576 : 384, 1) gemm_tc2_kernel(const
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (PAIR) cluster_sync_all();       // no CTA frees TMEM or exits while the pair's MMAs / remote arrives are in flight
-    if (warp == ALLOC_WARP) {
+    if (warp == 2) {
         if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
         else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
     }
@@ -1056,14 +1010,7 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
     const bool wbatch = a->w_batches > 1;
     if (wbatch && (a->im2col || a->rows_per_batch % TM || ((a->w_bstride * es) & 15))) return TURTLE_ENOTSUP;
     p.tiles_per_img = wbatch ? (int)(a->rows_per_batch / TM) : 0;
-    // wide epilogue (16 warps, four per TMEM lane quarter): TURTLE_GEMM_EW = bit mask of the launch classes that take it
-    //   1: fp32-output (+residual, +LN) with NG = 256    2: fp16-output with NG = 256
-    //   4: fp32-output with NG = 128                     8: fp16-output with NG >= 128 (other than 256)
-    // Needs fp16 operands (the instantiated variants), the TMA epilogue, and a ring of >= 2 stages next to 2 boxes per warp.
-    static const int ew_mask = getenv("TURTLE_GEMM_EW") ? atoi(getenv("TURTLE_GEMM_EW")) : 0;
-    const int ew_class = NG == 256 ? (o16 ? 2 : 1) : (NG >= 128 && NG % 32 == 0 ? (o16 ? 8 : 4) : 0);
-    int EWn = (a16 && !a->im2col && a->store == TURTLE_STORE_PLAIN && (ew_mask & ew_class)) ? EPI_WARPS_MAX : EPI_WARPS;
-    const bool pair = !no_pair && p.nkb >= pair_min_kb && NG == 256 && (!a->ln_out || pair_ln || EWn == EPI_WARPS_MAX) && tiles >= 8 &&
+    const bool pair = !no_pair && p.nkb >= pair_min_kb && NG == 256 && (!a->ln_out || pair_ln) && tiles >= 8 &&
                       (!wbatch || p.tiles_per_img % 2 == 0);
     if (wbatch) {
         uint64_t dims[3] = {(uint64_t)K, (uint64_t)Cout, (uint64_t)a->w_batches};
@@ -1077,9 +1024,7 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
         if (!turtle_get_tmap2(&p.mapW, a->Wt, 2, dims, str, box, 1, a16 ? 1 : 0)) return TURTLE_ENOTSUP;
     }
     p.total_units = (pair ? (tiles + 1) / 2 : tiles) * p.ngroups;
-    const size_t max_smem_cfg = 232448 - 8192;   // 227 KB opt-in limit minus the kernel's static smem (barriers, LN statistics and weights)
-    size_t max_smem = max_smem_cfg;
-    if (EWn == EPI_WARPS_MAX) max_smem -= 6144;      // the wide variant's static smem (twice the LN statistics and barriers)
+    const size_t max_smem = 232448 - 8192;   // 227 KB opt-in limit minus the kernel's static smem (barriers, LN statistics and weights)
     // resident weights: one n-group, no pairs, every CTA walks >= 2 tiles, and the whole [NG x K] matrix fits next to
     // the minimum ring (2 A stages) and the minimum staging boxes (2 per epilogue warp)
     // OFF by default: measured neutral on B200 (scripts/gemm_micro.py, every hot shape within +-1 us; 128->256 @235520
@@ -1089,7 +1034,7 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
     const size_t w_total = (size_t)p.nkb * NG * TK * 4;
     int nsm_now = 148;
     cudaDeviceGetAttribute(&nsm_now, cudaDevAttrMultiProcessorCount, turtle_device());
-    const bool wres = !no_wres && !pair && !wbatch && p.ngroups == 1 && tiles >= 2LL * nsm_now && EWn == EPI_WARPS &&
+    const bool wres = !no_wres && !pair && !wbatch && p.ngroups == 1 && tiles >= 2LL * nsm_now &&
                       w_total + 2 * A_STAGE_BYTES + (size_t)EPI_WARPS * 2 * EPI_BUF + 1024 <= max_smem;
     p.w_res = wres ? 1 : 0;
     const size_t ring_budget = max_smem - (wres ? w_total : 0);     // what the A(+B) ring and the staging boxes share
@@ -1103,22 +1048,17 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
     static const int min_st_short = getenv("TURTLE_GEMM_MINST_SHORT") ? atoi(getenv("TURTLE_GEMM_MINST_SHORT")) : 0;
     static const int min_st_long = getenv("TURTLE_GEMM_MINST_LONG") ? atoi(getenv("TURTLE_GEMM_MINST_LONG")) : 4;
     const int min_st = p.nkb <= 4 ? (min_st_short ? min_st_short : (NG == 256 ? 2 : 3)) : min_st_long;
-    if (EWn == EPI_WARPS_MAX &&
-        (ring_budget < 1024 + (size_t)EWn * (o16 ? 1 : 2) * EPI_BUF ||
-         (ring_budget - 1024 - (size_t)EWn * (o16 ? 1 : 2) * EPI_BUF) / stage_bytes < 2))
-        EWn = EPI_WARPS;                                      // the ring would not fit next to 32 boxes
-    int boxes = (EWn == EPI_WARPS_MAX && o16) ? 1 : 2;      // wide fp16-output epilogue: one store group per warp and unit
+    int boxes = 2;
     static const int o16_boxes = getenv("TURTLE_GEMM_O16BOX") ? atoi(getenv("TURTLE_GEMM_O16BOX")) : 2;     // A/B knobs
     static const int o16_2ld = getenv("TURTLE_GEMM_O16_2LD") ? atoi(getenv("TURTLE_GEMM_O16_2LD")) : 0;
     p.o16_2ld = o16_2ld;
-    if (o16 && EWn == EPI_WARPS && o16_boxes > 2 && o16_boxes <= 4 &&
-        ring_budget > 1024 + (size_t)EWn * o16_boxes * EPI_BUF &&
-        (long long)((ring_budget - 1024 - (size_t)EWn * o16_boxes * EPI_BUF) / stage_bytes) >= (p.nkb < 3 ? p.nkb : 3))
+    if (o16 && o16_boxes > 2 && o16_boxes <= 4 &&
+        (long long)((ring_budget - 1024 - (size_t)EPI_WARPS * o16_boxes * EPI_BUF) / stage_bytes) >= (p.nkb < 3 ? p.nkb : 3))
         boxes = o16_boxes;
     if (a->res && !o16)
         for (int cand = box_cap < 4 ? box_cap : 4; cand > 2; --cand)
-            if (ring_budget > 1024 + (size_t)EWn * cand * EPI_BUF &&
-                (long long)((ring_budget - 1024 - (size_t)EWn * cand * EPI_BUF) / stage_bytes) >= (p.nkb < min_st ? p.nkb : min_st)) {
+            if (ring_budget > 1024 + (size_t)EPI_WARPS * cand * EPI_BUF &&
+                (long long)((ring_budget - 1024 - (size_t)EPI_WARPS * cand * EPI_BUF) / stage_bytes) >= (p.nkb < min_st ? p.nkb : min_st)) {
                 boxes = cand;
                 break;
             }
@@ -1129,7 +1069,7 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
 #else
     p.dbg_skip = 0;
 #endif
-    const size_t epi_bytes = (size_t)EWn * boxes * EPI_BUF;
+    const size_t epi_bytes = (size_t)EPI_WARPS * boxes * EPI_BUF;
     int stages = (int)((ring_budget - 1024 - epi_bytes) / stage_bytes);
     if (stages > 8) stages = 8;
     if (stages < 2) return TURTLE_ENOTSUP;
@@ -1170,16 +1110,13 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
     int &nsm = nsm_[dev_];
     if (!configured) {
         bool ok = true;
-        auto cfg = [&](auto kern, size_t cap = 232448 - 8192) {
-            ok = ok && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap) == cudaSuccess;
+        auto cfg = [&](auto kern) {
+            ok = ok && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem) == cudaSuccess;
         };
-        cfg(gemm_tc2_kernel<false, false, false, 8>); cfg(gemm_tc2_kernel<true, false, false, 8>);
-        cfg(gemm_tc2_kernel<true, true, false, 8>);   cfg(gemm_tc2_kernel<false, true, false, 8>);
-        cfg(gemm_tc2_kernel<false, false, true, 8>);  cfg(gemm_tc2_kernel<true, false, true, 8>);
-        cfg(gemm_tc2_kernel<true, true, true, 8>);    cfg(gemm_tc2_kernel<false, true, true, 8>);
-        const size_t cap16 = 232448 - 8192 - 6144;       // the wide variants carry 6 KB more static shared memory
-        cfg(gemm_tc2_kernel<true, false, false, 16>, cap16); cfg(gemm_tc2_kernel<true, true, false, 16>, cap16);
-        cfg(gemm_tc2_kernel<true, false, true, 16>, cap16);  cfg(gemm_tc2_kernel<true, true, true, 16>, cap16);
+        cfg(gemm_tc2_kernel<false, false, false>); cfg(gemm_tc2_kernel<true, false, false>);
+        cfg(gemm_tc2_kernel<true, true, false>);   cfg(gemm_tc2_kernel<false, true, false>);
+        cfg(gemm_tc2_kernel<false, false, true>);  cfg(gemm_tc2_kernel<true, false, true>);
+        cfg(gemm_tc2_kernel<true, true, true>);    cfg(gemm_tc2_kernel<false, true, true>);
         if (!ok) return TURTLE_ELAUNCH;
         int dev = 0;
         cudaGetDevice(&dev);
@@ -1190,22 +1127,17 @@ int turtle_gemm_tc2(const TurtleGemmArgs *a, void *stream) {
     if (pair) {
         long long pairs = nsm / 2;
         if (pairs > p.total_units) pairs = p.total_units;
-        const dim3 grid((unsigned)(2 * pairs)), block((EWn == 16 ? 64 : 128) + EWn * 32);
-        if (EWn == 16 && o16) launch_cluster(gemm_tc2_kernel<true, true, true, 16>, 2, grid, block, smem, st, p);
-        else if (EWn == 16) launch_cluster(gemm_tc2_kernel<true, false, true, 16>, 2, grid, block, smem, st, p);
-        else if (a16 && o16) launch_cluster(gemm_tc2_kernel<true, true, true, 8>, 2, grid, block, smem, st, p);
-        else if (a16) launch_cluster(gemm_tc2_kernel<true, false, true, 8>, 2, grid, block, smem, st, p);
-        else if (o16) launch_cluster(gemm_tc2_kernel<false, true, true, 8>, 2, grid, block, smem, st, p);
-        else launch_cluster(gemm_tc2_kernel<false, false, true, 8>, 2, grid, block, smem, st, p);
+        const dim3 grid((unsigned)(2 * pairs)), block(384);
+        if (a16 && o16) launch_cluster(gemm_tc2_kernel<true, true, true>, 2, grid, block, smem, st, p);
+        else if (a16) launch_cluster(gemm_tc2_kernel<true, false, true>, 2, grid, block, smem, st, p);
+        else if (o16) launch_cluster(gemm_tc2_kernel<false, true, true>, 2, grid, block, smem, st, p);
+        else launch_cluster(gemm_tc2_kernel<false, false, true>, 2, grid, block, smem, st, p);
     } else {
         const long long grid = p.total_units < nsm ? p.total_units : nsm;
-        const dim3 block((EWn == 16 ? 64 : 128) + EWn * 32);
-        if (EWn == 16 && o16) launch_pdl(gemm_tc2_kernel<true, true, false, 16>, dim3((unsigned)grid), block, smem, st, p);
-        else if (EWn == 16) launch_pdl(gemm_tc2_kernel<true, false, false, 16>, dim3((unsigned)grid), block, smem, st, p);
-        else if (a16 && o16) launch_pdl(gemm_tc2_kernel<true, true, false, 8>, dim3((unsigned)grid), block, smem, st, p);
-        else if (a16) launch_pdl(gemm_tc2_kernel<true, false, false, 8>, dim3((unsigned)grid), block, smem, st, p);
-        else if (o16) launch_pdl(gemm_tc2_kernel<false, true, false, 8>, dim3((unsigned)grid), block, smem, st, p);
-        else launch_pdl(gemm_tc2_kernel<false, false, false, 8>, dim3((unsigned)grid), block, smem, st, p);
+        if (a16 && o16) launch_pdl(gemm_tc2_kernel<true, true, false>, dim3((unsigned)grid), dim3(384), smem, st, p);
+        else if (a16) launch_pdl(gemm_tc2_kernel<true, false, false>, dim3((unsigned)grid), dim3(384), smem, st, p);
+        else if (o16) launch_pdl(gemm_tc2_kernel<false, true, false>, dim3((unsigned)grid), dim3(384), smem, st, p);
+        else launch_pdl(gemm_tc2_kernel<false, false, false>, dim3((unsigned)grid), dim3(384), smem, st, p);
     }
     return cudaGetLastError() == cudaSuccess ? TURTLE_OK : TURTLE_ELAUNCH;
 }
