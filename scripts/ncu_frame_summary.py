@@ -20,6 +20,7 @@ ENTRY = {
     "turtle_dwconv3x3": ("dwconv16_kernel", "dwconv_tma_kernel", "dwconv3x3_kernel"),
     "turtle_layernorm": ("layernorm_vec_kernel", "layernorm_kernel"),
     "turtle_sab_aggregate": ("sab_aggregate",),
+    "turtle_sab_aggregate_tc": ("sab_agg_tc_kernel", "sab_wd_build_kernel", "sab_far_add_kernel"),
     "turtle_chan_gram": ("gram_tc_kernel", "gram64_kernel", "chan_gram_kernel"),
 }
 

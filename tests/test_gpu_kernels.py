@@ -216,7 +216,7 @@ def test_channel_attention_batched_equals_per_element(heads, ch, S, B, mode):
 
 
 @pytest.mark.parametrize("bias", [False, True])
-@pytest.mark.parametrize("ws,D", [(4, 64), (8, 32), (16, 16), (4, 20)])
+@pytest.mark.parametrize("ws,D", [(4, 64), (8, 32), (16, 16), (4, 20), (8, 128), (4, 256), (4, 512)])
 def test_sab_window_reduce(ws, D, bias):
     B, H, W = 2, 32, 48
     t, w = rnd(B, D, H, W), rnd(D, 1, ws, ws, seed=1)

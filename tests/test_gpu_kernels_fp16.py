@@ -189,7 +189,7 @@ def test_gemm_fused_layernorm(Cin, C_, P, a16):
 
 
 @pytest.mark.parametrize("bias", [False, True])
-@pytest.mark.parametrize("ws,D", [(4, 64), (8, 128), (16, 32)])
+@pytest.mark.parametrize("ws,D", [(4, 64), (8, 128), (16, 32), (4, 256), (4, 512), (16, 128)])
 def test_sab_window_reduce_fp16_map(ws, D, bias):
     from oracle import turtle_oracle as orc
     B, H, W = 2, 32, 48
