@@ -26,6 +26,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -409,11 +411,15 @@ constexpr int FAR_QPW = 4;      // queries per warp
 template <bool H16>
 __global__ void __launch_bounds__(256) sab_far_add_kernel(const int32_t *__restrict__ idx, const float *__restrict__ wgt,
                                                           const void *__restrict__ v, int64_t v_fstride, void *__restrict__ y,
-                                                          int Hg, int Wg, int ws, int c, int rnd) {
+                                                          int Hg, int Wg, int ws, int c, int rnd, int cpi) {
     pdl_trigger();
     pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int f = blockIdx.y, chunk = blockIdx.z;
+    const int f = blockIdx.y;
+    // a warp item covers `cpi` consecutive 256-column chunks of its query: the per-query set-up (index / weight loads, box
+    // test, shuffles, index arithmetic) was more than half of the instructions of this issue-bound kernel (ncu: 80 %
+    // issue-active) when it was repeated for every chunk; cpi chunks of all value rows (N x cpi x 512 B) still fit L2
+    const int c_sh = (c & (c - 1)) == 0 ? 31 - __clz(c) : -1, ws_sh = (ws & (ws - 1)) == 0 ? 31 - __clz(ws) : -1;
     const int N = Hg * Wg, Dv = ws * ws * c;
     const int H = Hg * ws, W = Wg * ws;
     // 16-byte vectors: 4 floats or 8 halves; a 256-column chunk is 64 (fp32) or 32 (fp16) of them per row
@@ -448,6 +454,8 @@ __global__ void __launch_bounds__(256) sab_far_add_kernel(const int32_t *__restr
             key[t] = __shfl_sync(0xffffffffu, id_l, t);
             w[t] = __shfl_sync(0xffffffffu, w_l, t);
         }
+#pragma unroll 1
+        for (int chunk = blockIdx.z * cpi; chunk < (int)(blockIdx.z + 1) * cpi; ++chunk) {
         uint4 x[NV][5];
 #pragma unroll
         for (int h = 0; h < NV; ++h)
@@ -475,8 +483,8 @@ __global__ void __launch_bounds__(256) sab_far_add_kernel(const int32_t *__restr
                 }
             }
             const int e0 = (chunk * VPC + h * 32 + lane) * EPV;               // first of EPV columns, all in one patch pixel
-            const int pp = e0 / c, d = e0 - pp * c;
-            const int p1 = pp / ws, p2 = pp - p1 * ws;
+            const int pp = c_sh >= 0 ? e0 >> c_sh : e0 / c, d = e0 - pp * c;
+            const int p1 = ws_sh >= 0 ? pp >> ws_sh : pp / ws, p2 = pp - p1 * ws;
             const int64_t o = (((int64_t)f * H + p1 * Hg + qy) * W + p2 * Wg + qx) * c + d;
             if (rnd == 2) {
                 __half2 *dst = reinterpret_cast<__half2 *>(reinterpret_cast<__half *>(y) + o);
@@ -498,6 +506,7 @@ __global__ void __launch_bounds__(256) sab_far_add_kernel(const int32_t *__restr
                     dst[e] = rnd ? rna_tf32(r) : r;
                 }
             }
+        }
         }
     }
 }
@@ -568,7 +577,9 @@ extern "C" int turtle_sab_aggregate_tc(const int32_t *idx, const float *wgt, con
         configured_[dev_] = true;
     }
     cudaStream_t st = as_stream(stream);
-    const dim3 gwd((unsigned)tiles, F, nkb), gfar((Hg * Wg + 8 * FAR_QPW - 1) / (8 * FAR_QPW), F, p.nchunks);
+    static const int far_cpi = getenv("TURTLE_SAB_FAR_CPI") ? atoi(getenv("TURTLE_SAB_FAR_CPI")) : 2;      // chunks per warp item (measured: 1: 951, 2: 910, 4: 946, 8: 1014 us per frame)
+    const int cpi = (far_cpi > 0 && p.nchunks % far_cpi == 0) ? far_cpi : 1;
+    const dim3 gwd((unsigned)tiles, F, nkb), gfar((Hg * Wg + 8 * FAR_QPW - 1) / (8 * FAR_QPW), F, p.nchunks / cpi);
     const long long grid = p.total_units < nsm_[dev_] ? p.total_units : nsm_[dev_];
     if (h16) {
         launch_pdl(sab_wd_build_kernel<true>, gwd, dim3(128), 0, st, idx, wgt, workspace, Hg, Wg, p.tiles_x);
@@ -580,13 +591,13 @@ extern "C" int turtle_sab_aggregate_tc(const int32_t *idx, const float *wgt, con
         }
         launch_pdl(sab_agg_tc_kernel<true, false>, dim3((unsigned)grid), dim3(384), smem, st, p);
         TURTLE_CHECK_LAUNCH();
-        launch_pdl(sab_far_add_kernel<true>, gfar, dim3(256), 0, st, idx, wgt, v, v_fstride, y, Hg, Wg, ws, c, round_mode);
+        launch_pdl(sab_far_add_kernel<true>, gfar, dim3(256), 0, st, idx, wgt, v, v_fstride, y, Hg, Wg, ws, c, round_mode, cpi);
     } else {
         launch_pdl(sab_wd_build_kernel<false>, gwd, dim3(128), 0, st, idx, wgt, workspace, Hg, Wg, p.tiles_x);
         TURTLE_CHECK_LAUNCH();
         launch_pdl(sab_agg_tc_kernel<false, false>, dim3((unsigned)grid), dim3(384), smem, st, p);
         TURTLE_CHECK_LAUNCH();
-        launch_pdl(sab_far_add_kernel<false>, gfar, dim3(256), 0, st, idx, wgt, v, v_fstride, y, Hg, Wg, ws, c, round_mode);
+        launch_pdl(sab_far_add_kernel<false>, gfar, dim3(256), 0, st, idx, wgt, v, v_fstride, y, Hg, Wg, ws, c, round_mode, cpi);
     }
     TURTLE_CHECK_LAUNCH();
     return TURTLE_OK;
