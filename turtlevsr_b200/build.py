@@ -58,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def run(job):
         src, obj = job
-        cmd = [nvcc, *NVCC_FLAGS, "-c", src, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("TURTLE_NVCC_EXTRA", "").split(), "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         return src, r
 

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(1024) chan_softmax_kernel(const float *__restr
                                                             const float *__restrict__ temperature, int nseg,
                                                             int nsplit, int heads, int ch, float *__restrict__ Pout,
                                                             float *__restrict__ inv_knorm, int64_t g_bs, int64_t s_bs) {
-    pdl_trigger();
+    pdl_trigger_mw();
     pdl_wait();
     {   // batch element = blockIdx.z; Pout / inv_knorm are dense per element
         const int64_t bz = blockIdx.z;
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(1024) chan_softmax_kernel(const float *__restr
 // L2 latency: 22 us for a 4 MFLOP launch), then every thread produces a 4x4 register tile.
 __global__ void __launch_bounds__(256) chan_fold_tile_kernel(const float *__restrict__ Pm, const float *__restrict__ Wo,
                                                              int nseg, int heads, float *__restrict__ M, int rnd) {
-    pdl_trigger();
+    pdl_trigger_mw();
     pdl_wait();
     constexpr int CH = 64;
     __shared__ float ws[CH][CH + 4];      // [o][i]  (+4: conflict-free column reads)

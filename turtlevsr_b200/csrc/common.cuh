@@ -32,6 +32,13 @@ static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// multi-wave kernels (more CTAs than fit the GPU at once): with TURTLE_PDL_LATE they do not release their successor early --
+// its CTAs would take SM slots from this kernel's later waves -- so the dependent launch happens at grid completion
+__device__ __forceinline__ void pdl_trigger_mw() {
+#ifndef TURTLE_PDL_LATE
+    pdl_trigger();
+#endif
+}
 
 #ifdef __CUDACC__
 #include <cstdlib>
@@ -66,8 +73,10 @@ static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 blo
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    // measured on B200 (bench.py A/B, 20 steps x 2): 30.2-30.4 ms/frame with the attribute, 29.6-29.8 without -- early
-    // resident successors cost more than the hidden launch latency, so plain stream order is the default
+    // measured on B200 (bench.py A/B, 20 steps x 2): 30.2-30.4 ms/frame with the attribute, 29.6-29.8 without (round 1);
+    // round 2, graph replay (scripts/gpu_r02z3.sh): off 26.95 / 27.02 ms, on 27.64 / 27.64 ms, on with the multi-wave kernels
+    // releasing their successor only at completion (-DTURTLE_PDL_LATE) 27.51 / 27.55 ms -- programmatic edges cost more
+    // than the launch latency they hide, whoever triggers, so plain stream order is the default
     static const bool off = getenv("TURTLE_PDL") == nullptr;
     cfg.attrs = at;
     cfg.numAttrs = off ? 0 : 1;

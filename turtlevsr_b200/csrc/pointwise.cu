@@ -10,7 +10,7 @@
 // ------------------------------------------------------------------------------------------
 __global__ void pack_frame_kernel(const float *__restrict__ src, int64_t bstride, float *__restrict__ dst, int B,
                                   int C, int Hs, int Ws, int Hp, int Wp, int up) {
-    pdl_trigger();
+    pdl_trigger_mw();
     pdl_wait();
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t total = (int64_t)B * Hp * Wp;
@@ -410,7 +410,7 @@ template <int NV, int G, int U, bool O16>
 __global__ void __launch_bounds__(256) layernorm_vec_kernel(const float *__restrict__ x, int ldx,
                                                             const float *__restrict__ w, const float *__restrict__ b,
                                                             float *__restrict__ y, int ldy, int64_t P, int rnd) {
-    pdl_trigger();
+    pdl_trigger_mw();
     pdl_wait();
     constexpr int C = 4 * NV * G;
     constexpr int GPW = 32 / G;                       // pixel groups per warp
@@ -657,7 +657,7 @@ extern "C" int turtle_dwconv3x3_patch_rows(const float *x, int ldx, const float 
 // ------------------------------------------------------------------------------------------
 __global__ void scale_cols_kernel(const float *__restrict__ x, int ldx, int x_hs, const float *__restrict__ s,
                                   float *__restrict__ y, int ldy, int y_hs, int64_t P, int heads, int ch) {
-    pdl_trigger();
+    pdl_trigger_mw();
     pdl_wait();
     int per = heads * (ch >> 2);
     int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

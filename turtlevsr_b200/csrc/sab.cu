@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(256) window_reduce_vec_kernel(const float *__r
                                                                 const float *__restrict__ bias /* [D] or null */,
                                                                 float *__restrict__ out, int64_t out_bstride, int H,
                                                                 int W, int D, int ws) {
-    pdl_trigger();
+    pdl_trigger_mw();
     pdl_wait();
     __shared__ float4 part[256];
     __shared__ float red[8];
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(256) sab_aggregate_quad_kernel(const int32_t *
                                                                  const float *__restrict__ v, int64_t v_fstride,
                                                                  float *__restrict__ y, int Hg, int Wg, int ws, int c,
                                                                  int quads_x, int rnd) {
-    pdl_trigger();
+    pdl_trigger_mw();
     pdl_wait();
     __shared__ float bw[QB * QB][4];      // weight of window-box key for each of the 4 queries
     __shared__ int ekey[QMAX];

@@ -89,7 +89,7 @@ __device__ __forceinline__ uint64_t desc_mn_f16(uint32_t saddr, uint32_t lbo, ui
 template <bool H16>
 __global__ void __launch_bounds__(128) sab_wd_build_kernel(const int32_t *__restrict__ idx, const float *__restrict__ wgt,
                                                            void *__restrict__ wd, int Hg, int Wg, int tiles_x) {
-    pdl_trigger();
+    pdl_trigger_mw();
     pdl_wait();
     constexpr int RPB = H16 ? 2 : 1;                 // key rows per block
     const int tile = blockIdx.x, f = blockIdx.y, kb = blockIdx.z, q = threadIdx.x;
@@ -412,7 +412,7 @@ template <bool H16>
 __global__ void __launch_bounds__(256) sab_far_add_kernel(const int32_t *__restrict__ idx, const float *__restrict__ wgt,
                                                           const void *__restrict__ v, int64_t v_fstride, void *__restrict__ y,
                                                           int Hg, int Wg, int ws, int c, int rnd, int cpi) {
-    pdl_trigger();
+    pdl_trigger_mw();
     pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.y;

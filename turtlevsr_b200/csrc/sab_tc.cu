@@ -24,7 +24,7 @@ constexpr int KSPLIT = 2;
 constexpr int NLOC = 41;
 
 __global__ void split_tf32_kernel(const float *__restrict__ x, float *__restrict__ y, long long rows, int D, int is_key) {
-    pdl_trigger();
+    pdl_trigger_mw();
     pdl_wait();
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= rows * D) return;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(256) sab_finalize_kernel(const float *__restri
                                                            const float *__restrict__ tau_ptr, int halve, const float *__restrict__ topv,
                                                            const int *__restrict__ topi, int32_t *__restrict__ idx,
                                                            float *__restrict__ wgt) {
-    pdl_trigger();
+    pdl_trigger_mw();
     pdl_wait();
     const int N = Hg * Wg;
     const int lane = threadIdx.x & 31;
