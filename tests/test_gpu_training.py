@@ -80,7 +80,8 @@ def test_channel_layernorm_forward_backward_kernels(dtype, tol, B, C, H, W):
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 3e-6), (torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
-@pytest.mark.parametrize("B,C,H,W,bias", [(2, 24, 37, 70, True), (1, 640, 32, 32, False), (3, 5, 64, 33, True)])
+@pytest.mark.parametrize("B,C,H,W,bias", [(2, 24, 37, 70, True), (1, 640, 32, 32, False), (3, 5, 64, 33, True),
+                                            (2, 6, 70, 128, True), (1, 9, 24, 64, False), (2, 3, 256, 256, True)])   # W % 64 == 0: two-column kernels
 def test_depthwise3x3_forward_backward_kernels(dtype, tol, B, C, H, W, bias):
     """turtle_dwconv3x3_nchw / _wgrad behind autograd vs F.conv2d(groups=C) in float64."""
     import torch.nn.functional as F
