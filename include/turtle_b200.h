@@ -311,6 +311,13 @@ long long turtle_dwconv3x3_nchw_wgrad_workspace(int B, int C, int H, int W);
 int turtle_dwconv3x3_nchw_wgrad(const void *x, const void *dy, int dtype, float *dw9, float *db, void *workspace, int B,
                                 int C, int H, int W, void *stream);
 
+/* GELU gate of the TRAINING graph on NCHW maps (GatedFeedForward T1:175-176: `x1, x2 = dwconv(..).chunk(2, dim=1);
+ * F.gelu(x1) * x2` and what autograd runs for its backward): u [B, 2*Ch, HW] dense, y / dy [B, Ch, HW], du like u; dtype
+ * as in turtle_ln2d_fwd; intermediates are rounded to the map's dtype where the ATen chain rounds them under autocast.
+ * HW % 8 == 0 and 16-byte (fp32: 32-byte) aligned pointers; TURTLE_ENOTSUP otherwise (caller: the torch ops). */
+int turtle_gelu_gate_nchw(const void *u, int dtype, void *y, int B, int Ch, long long HW, void *stream);
+int turtle_gelu_gate_nchw_bwd(const void *u, const void *dy, int dtype, void *du, int B, int Ch, long long HW, void *stream);
+
 /* GatedFeedForward (T1:159-178) as one kernel, tensor-core mode:  x += W_out . ( gelu(u1) * u2 ),
  * [u1 | u2] = dw3x3( W_in . xn ), with the 5c-wide hidden map kept on the SM (project_in recomputed on the 1-pixel halo
  * of each 8x16 tile, depthwise + gate feeding the second tcgen05 contraction through shared memory).

@@ -110,6 +110,38 @@ def test_depthwise3x3_forward_backward_kernels(dtype, tol, B, C, H, W, bias):
     assert torch.equal(w1, w.grad)                                   # deterministic weight gradient
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
+@pytest.mark.parametrize("B,Ch,H,W", [(2, 5, 8, 12), (1, 96, 32, 32), (3, 7, 64, 40)])
+def test_gelu_gate_forward_backward_kernels(dtype, tol, B, Ch, H, W):
+    """turtle_gelu_gate_nchw / _bwd behind autograd vs `gelu(a) * g` on the chunk views: float64 reference within the
+    dtype's tolerance, and bit-identical to the ATen chain in the same dtype (it rounds where ATen rounds)."""
+    import torch.nn.functional as F
+    from turtlevsr_b200.training import _GeluGate
+    g = torch.Generator(device=DEV).manual_seed(Ch + W)
+    u = (torch.randn(B, 2 * Ch, H, W, device=DEV, generator=g) * 1.5).to(dtype).requires_grad_()
+    dy = torch.randn(B, Ch, H, W, device=DEV, generator=g).to(dtype)
+    y = _GeluGate.apply(u)
+    assert y.dtype == dtype and y.shape == (B, Ch, H, W)
+    y.backward(dy)
+    ud = u.detach().double().requires_grad_()
+    a, gg = ud.chunk(2, dim=1)
+    yd = F.gelu(a) * gg
+    yd.backward(dy.double())
+    assert (y.double() - yd).abs().max() < tol * max(1.0, yd.abs().max().item())
+    assert (u.grad.double() - ud.grad).abs().max() < 2 * tol * max(1.0, ud.grad.abs().max().item())
+    ut = u.detach().clone().requires_grad_()
+    a, gg = ut.chunk(2, dim=1)
+    yt = F.gelu(a) * gg
+    yt.backward(dy)
+    if dtype == torch.float32:
+        assert (y - yt).abs().max() < 1e-6 and (u.grad - ut.grad).abs().max() < 2e-6
+    else:
+        # the same intermediate roundings as the ATen chain: at most one ulp of the 16-bit type apart (erff / expf variants)
+        ulp = 2.0 ** -10 if dtype == torch.float16 else 2.0 ** -7
+        assert ((y.float() - yt.float()).abs() <= ulp * yt.float().abs() + 1e-6).all()
+        assert ((u.grad.float() - ut.grad.float()).abs() <= 2 * ulp * ut.grad.float().abs() + 1e-5).all()
+
+
 def test_non_finite_gradients_skip_the_update():
     lin = torch.nn.Linear(1000, 37).to(DEV)
     flat = FlatParams(lin)

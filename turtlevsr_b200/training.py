@@ -20,6 +20,7 @@ What runs where (stated plainly):
 from __future__ import annotations
 
 import math
+import os
 from typing import List, Optional, Sequence
 
 import torch
@@ -108,6 +109,45 @@ class _Depthwise3x3(torch.autograd.Function):
         return dx, dw9.view(ctx.w_shape), db
 
 
+class _GeluGate(torch.autograd.Function):
+    """`a, g = u.chunk(2, dim=1); F.gelu(a) * g` (GatedFeedForward, T1:175-176) on turtle_gelu_gate_nchw / _bwd: one launch
+    forward and one backward instead of ATen's strided elementwise kernels on the channel-chunk views (gelu, mul, two
+    mul-backwards, gelu_backward and the zero-filled cat of the halves)."""
+
+    @staticmethod
+    def forward(ctx, u):
+        from . import capi
+        u = u.contiguous()
+        B, C2, H, W = u.shape
+        y = torch.empty(B, C2 // 2, H, W, device=u.device, dtype=u.dtype)
+        capi.call("turtle_gelu_gate_nchw", u.data_ptr(), _LN_DTYPES[u.dtype], y.data_ptr(), B, C2 // 2, H * W,
+                  torch.cuda.current_stream(u.device).cuda_stream)
+        ctx.save_for_backward(u)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import capi
+        (u,) = ctx.saved_tensors
+        B, C2, H, W = u.shape
+        dy = dy.contiguous()
+        if dy.dtype != u.dtype:
+            dy = dy.to(u.dtype)
+        du = torch.empty_like(u)
+        capi.call("turtle_gelu_gate_nchw_bwd", u.data_ptr(), dy.data_ptr(), _LN_DTYPES[u.dtype], du.data_ptr(), B, C2 // 2,
+                  H * W, torch.cuda.current_stream(u.device).cuda_stream)
+        return du
+
+
+def _gelu_gate(u: Tensor) -> Tensor:
+    """gelu(first half of the channels) * second half."""
+    if (u.is_cuda and u.dtype in _LN_DTYPES and u.shape[1] % 2 == 0 and (u.shape[2] * u.shape[3]) % 8 == 0
+            and os.environ.get("TURTLE_TRAIN_GATE", "1") != "0"):
+        return _GeluGate.apply(u)
+    a, g = u.chunk(2, dim=1)
+    return F.gelu(a) * g
+
+
 def _dw(conv, x: Tensor) -> Tensor:
     """A depthwise conv module of the arch tree: the hand-written kernels for the 3x3 / stride 1 / pad 1 case on CUDA."""
     if (x.is_cuda and x.dtype in _LN_DTYPES and conv.kernel_size == (3, 3) and conv.stride == (1, 1)
@@ -188,8 +228,7 @@ def _clipped_softmax(z: Tensor) -> Tensor:                      # T1:115-132
 
 
 def _gated_ffw(m, x):                                           # T1:173-178
-    a, g = _dw(m.dwconv, m.project_in(x)).chunk(2, dim=1)
-    return m.project_out(F.gelu(a) * g)
+    return m.project_out(_gelu_gate(_dw(m.dwconv, m.project_in(x))))
 
 
 def _plain_ffw(m, x):                                           # T1:204-210
