@@ -298,6 +298,15 @@ int turtle_ln2d_fwd(const void *x, int x_dtype, const float *w, const float *b, 
 int turtle_ln2d_bwd(const float *dy, const void *x, int x_dtype, const float *w, const float *mean, const float *rstd,
                     void *dx, float *dw, float *db, void *workspace, int B, int C, long long HW, void *stream);
 
+/* The same with y (forward) / dy (backward) in a chosen dtype (0 fp32, 1 fp16, 2 bf16): under autocast the conv that
+ * consumes the LayerNorm casts its output to the 16-bit type and sends the gradient back in it; writing / reading that
+ * type directly is the same single rounding and saves two ATen cast launches per LayerNorm and direction. */
+int turtle_ln2d_fwd_cast(const void *x, int x_dtype, const float *w, const float *b, void *y, int y_dtype, float *mean,
+                         float *rstd, int B, int C, long long HW, void *stream);
+int turtle_ln2d_bwd_cast(const void *dy, int dy_dtype, const void *x, int x_dtype, const float *w, const float *mean,
+                         const float *rstd, void *dx, float *dw, float *db, void *workspace, int B, int C, long long HW,
+                         void *stream);
+
 /* Depthwise 3x3 (stride 1, zero pad 1, groups = C) of the TRAINING graph on NCHW maps x [B,C,H,W] dense; dtype as in
  * turtle_ln2d_fwd; w9 [C,9] fp32 taps (row-major 3x3), bias [C] fp32 or NULL.  Replaces nn.Conv2d(groups=C).forward
  * (e.g. GatedFeedForward.dwconv T1:163, qkv_dwconv T1:674) and the three kernels autograd runs for it:

@@ -79,6 +79,27 @@ def test_channel_layernorm_forward_backward_kernels(dtype, tol, B, C, H, W):
     assert torch.equal(w1, w.grad)
 
 
+@pytest.mark.parametrize("od", [torch.float16, torch.bfloat16])
+def test_channel_layernorm_cast_variants(od):
+    """y written / dy read in the autocast dtype == the fp32 kernel followed by ATen's casts (one rounding either way)."""
+    from turtlevsr_b200.training import _ChannelLayerNorm
+    B, C, H, W = 2, 48, 16, 24
+    g = torch.Generator(device=DEV).manual_seed(5)
+    x = (torch.randn(B, C, H, W, device=DEV, generator=g) * 1.3 - 0.2).requires_grad_()
+    w = (torch.rand(C, device=DEV, generator=g) + 0.5).requires_grad_()
+    b = torch.randn(C, device=DEV, generator=g).requires_grad_()
+    dy = torch.randn(B, C, H, W, device=DEV, generator=g).to(od)
+    y = _ChannelLayerNorm.apply(x, w, b, od)
+    assert y.dtype == od
+    y.backward(dy)
+    got = (y.detach().clone(), x.grad.clone(), w.grad.clone(), b.grad.clone())
+    x.grad = w.grad = b.grad = None
+    y32 = _ChannelLayerNorm.apply(x, w, b)
+    y32.to(od).backward(dy)
+    assert torch.equal(got[0], y32.detach().to(od))
+    assert torch.equal(got[1], x.grad) and torch.equal(got[2], w.grad) and torch.equal(got[3], b.grad)
+
+
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 3e-6), (torch.float16, 2e-3), (torch.bfloat16, 1.6e-2)])
 @pytest.mark.parametrize("B,C,H,W,bias", [(2, 24, 37, 70, True), (1, 640, 32, 32, False), (3, 5, 64, 33, True),
                                             (2, 6, 70, 128, True), (1, 9, 24, 64, False), (2, 3, 256, 256, True)])   # W % 64 == 0: two-column kernels

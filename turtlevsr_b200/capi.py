@@ -70,6 +70,9 @@ _SIGS = {
     "turtle_ln2d_bwd_workspace": ([_i32, C.c_longlong], C.c_longlong),
     "turtle_ln2d_fwd": ([_fp, _i32, _fp, _fp, _fp, _fp, _fp, _i32, _i32, C.c_longlong, _fp], C.c_int),
     "turtle_ln2d_bwd": ([_fp, _fp, _i32, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i32, _i32, C.c_longlong, _fp], C.c_int),
+    "turtle_ln2d_fwd_cast": ([_fp, _i32, _fp, _fp, _fp, _i32, _fp, _fp, _i32, _i32, C.c_longlong, _fp], C.c_int),
+    "turtle_ln2d_bwd_cast": ([_fp, _i32, _fp, _i32, _fp, _fp, _fp, _fp, _fp, _fp, _fp, _i32, _i32, C.c_longlong, _fp],
+                             C.c_int),
     "turtle_dwconv3x3_nchw": ([_fp, _i32, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _i32, _fp], C.c_int),
     "turtle_dwconv3x3_nchw_wgrad_workspace": ([_i32, _i32, _i32, _i32], C.c_longlong),
     "turtle_gelu_gate_nchw": ([_fp, _i32, _fp, _i32, _i32, _i64, _fp], C.c_int),

@@ -27,12 +27,25 @@ __device__ __forceinline__ float ldf(const __nv_bfloat16 *p) { return __bfloat16
 __device__ __forceinline__ void stf(float *p, float v) { *p = v; }
 __device__ __forceinline__ void stf(__half *p, float v) { *p = __float2half_rn(v); }
 __device__ __forceinline__ void stf(__nv_bfloat16 *p, float v) { *p = __float2bfloat16_rn(v); }
+// y / dy in a run-time dtype (0 fp32, 1 fp16, 2 bf16; warp-uniform branch): under autocast the LayerNorm output is
+// cast to the 16-bit type by the conv that consumes it and its gradient comes back in that type, so the kernels write /
+// read it directly -- one rounding either way, and two ATen cast launches per LayerNorm and direction less
+__device__ __forceinline__ void st_any(void *p, int dt, int64_t i, float v) {
+    if (dt == 0) reinterpret_cast<float *>(p)[i] = v;
+    else if (dt == 1) reinterpret_cast<__half *>(p)[i] = __float2half_rn(v);
+    else reinterpret_cast<__nv_bfloat16 *>(p)[i] = __float2bfloat16_rn(v);
+}
+__device__ __forceinline__ float ld_any(const void *p, int dt, int64_t i) {
+    if (dt == 0) return reinterpret_cast<const float *>(p)[i];
+    if (dt == 1) return __half2float(reinterpret_cast<const __half *>(p)[i]);
+    return __bfloat162float(reinterpret_cast<const __nv_bfloat16 *>(p)[i]);
+}
 
 // Block = 32 consecutive pixels (lanes) x 8 channel groups (warps): every load / store of a warp is one contiguous
 // row segment, a thread walks only C/8 channels, and even the 32x32 latent map of a 256x256 crop fills 64 CTAs.
 template <int DT>
 __global__ void __launch_bounds__(LT) ln2d_fwd_kernel(const void *__restrict__ xv, const float *__restrict__ w,
-                                                      const float *__restrict__ b, float *__restrict__ y,
+                                                      const float *__restrict__ b, void *__restrict__ y, int ydt,
                                                       float *__restrict__ mean_out, float *__restrict__ rstd_out,
                                                       int C, int64_t HW, int64_t NP) {
     using T = typename Elem<DT>::T;
@@ -69,12 +82,12 @@ __global__ void __launch_bounds__(LT) ln2d_fwd_kernel(const void *__restrict__ x
     if (grp == 0) mean_out[pix] = mean, rstd_out[pix] = rstd;
     for (int c = grp; c < C; c += LG) {
         const float v = ldf(x + base + c * HW);
-        y[base + c * HW] = fmaf((v - mean) * rstd, __ldg(w + c), __ldg(b + c));
+        st_any(y, ydt, base + c * HW, fmaf((v - mean) * rstd, __ldg(w + c), __ldg(b + c)));
     }
 }
 
 template <int DT>
-__global__ void __launch_bounds__(LT) ln2d_bwd_kernel(const float *__restrict__ dy, const void *__restrict__ xv,
+__global__ void __launch_bounds__(LT) ln2d_bwd_kernel(const void *__restrict__ dy, int dydt, const void *__restrict__ xv,
                                                       const float *__restrict__ w, const float *__restrict__ mean_in,
                                                       const float *__restrict__ rstd_in, void *__restrict__ dxv,
                                                       float *__restrict__ part, int C, int64_t HW, int64_t NP) {
@@ -90,7 +103,7 @@ __global__ void __launch_bounds__(LT) ln2d_bwd_kernel(const float *__restrict__ 
     float s1 = 0.f, s2 = 0.f;
     if (live)
         for (int c = grp; c < C; c += LG) {
-            const float g = dy[base + c * HW] * __ldg(w + c);
+            const float g = ld_any(dy, dydt, base + c * HW) * __ldg(w + c);
             const float xh = (ldf(x + base + c * HW) - mean) * rstd;
             s1 += g;
             s2 = fmaf(g, xh, s2);
@@ -104,7 +117,7 @@ __global__ void __launch_bounds__(LT) ln2d_bwd_kernel(const float *__restrict__ 
     s1 *= inv_c;
     s2 *= inv_c;
     for (int c = grp; c < C; c += LG) {                // (warp-uniform trip count: the shuffles below are convergent)
-        const float d = live ? dy[base + c * HW] : 0.f;
+        const float d = live ? ld_any(dy, dydt, base + c * HW) : 0.f;
         const float xh = live ? (ldf(x + base + c * HW) - mean) * rstd : 0.f;
         if (live) stf(dx + base + c * HW, rstd * (d * __ldg(w + c) - s1 - xh * s2));
         const float a = warp_sum(d * xh), bsum = warp_sum(d);
@@ -133,32 +146,50 @@ extern "C" long long turtle_ln2d_bwd_workspace(int C, long long n_pixels) {
     return (long long)cdiv64(n_pixels, LP) * 2 * C * (long long)sizeof(float);
 }
 
+extern "C" int turtle_ln2d_fwd_cast(const void *x, int x_dtype, const float *w, const float *b, void *y, int y_dtype,
+                                    float *mean, float *rstd, int B, int C, long long HW, void *stream);
 extern "C" int turtle_ln2d_fwd(const void *x, int x_dtype, const float *w, const float *b, float *y, float *mean,
                                float *rstd, int B, int C, long long HW, void *stream) {
-    if (!x || !w || !b || !y || !mean || !rstd || B < 1 || C < 1 || HW < 1 || x_dtype < 0 || x_dtype > 2) return TURTLE_EINVAL;
+    return turtle_ln2d_fwd_cast(x, x_dtype, w, b, y, 0, mean, rstd, B, C, HW, stream);
+}
+
+extern "C" int turtle_ln2d_fwd_cast(const void *x, int x_dtype, const float *w, const float *b, void *y, int y_dtype,
+                                    float *mean, float *rstd, int B, int C, long long HW, void *stream) {
+    if (!x || !w || !b || !y || !mean || !rstd || B < 1 || C < 1 || HW < 1 || x_dtype < 0 || x_dtype > 2 || y_dtype < 0 ||
+        y_dtype > 2)
+        return TURTLE_EINVAL;
     const int64_t NP = (int64_t)B * HW;
     const unsigned grid = (unsigned)cdiv64(NP, LP);
     cudaStream_t s = as_stream(stream);
-    if (x_dtype == 0) ln2d_fwd_kernel<0><<<grid, LT, 0, s>>>(x, w, b, y, mean, rstd, C, HW, NP);
-    else if (x_dtype == 1) ln2d_fwd_kernel<1><<<grid, LT, 0, s>>>(x, w, b, y, mean, rstd, C, HW, NP);
-    else ln2d_fwd_kernel<2><<<grid, LT, 0, s>>>(x, w, b, y, mean, rstd, C, HW, NP);
+    if (x_dtype == 0) ln2d_fwd_kernel<0><<<grid, LT, 0, s>>>(x, w, b, y, y_dtype, mean, rstd, C, HW, NP);
+    else if (x_dtype == 1) ln2d_fwd_kernel<1><<<grid, LT, 0, s>>>(x, w, b, y, y_dtype, mean, rstd, C, HW, NP);
+    else ln2d_fwd_kernel<2><<<grid, LT, 0, s>>>(x, w, b, y, y_dtype, mean, rstd, C, HW, NP);
     TURTLE_CHECK_LAUNCH();
     return TURTLE_OK;
 }
 
+extern "C" int turtle_ln2d_bwd_cast(const void *dy, int dy_dtype, const void *x, int x_dtype, const float *w,
+                                    const float *mean, const float *rstd, void *dx, float *dw, float *db, void *workspace,
+                                    int B, int C, long long HW, void *stream);
 extern "C" int turtle_ln2d_bwd(const float *dy, const void *x, int x_dtype, const float *w, const float *mean,
                                const float *rstd, void *dx, float *dw, float *db, void *workspace, int B, int C,
                                long long HW, void *stream) {
+    return turtle_ln2d_bwd_cast(dy, 0, x, x_dtype, w, mean, rstd, dx, dw, db, workspace, B, C, HW, stream);
+}
+
+extern "C" int turtle_ln2d_bwd_cast(const void *dy, int dy_dtype, const void *x, int x_dtype, const float *w,
+                                    const float *mean, const float *rstd, void *dx, float *dw, float *db, void *workspace,
+                                    int B, int C, long long HW, void *stream) {
     if (!dy || !x || !w || !mean || !rstd || !dx || !dw || !db || !workspace || B < 1 || C < 1 || HW < 1 || x_dtype < 0 ||
-        x_dtype > 2)
+        x_dtype > 2 || dy_dtype < 0 || dy_dtype > 2)
         return TURTLE_EINVAL;
     const int64_t NP = (int64_t)B * HW;
     const unsigned grid = (unsigned)cdiv64(NP, LP);
     float *part = reinterpret_cast<float *>(workspace);
     cudaStream_t s = as_stream(stream);
-    if (x_dtype == 0) ln2d_bwd_kernel<0><<<grid, LT, 0, s>>>(dy, x, w, mean, rstd, dx, part, C, HW, NP);
-    else if (x_dtype == 1) ln2d_bwd_kernel<1><<<grid, LT, 0, s>>>(dy, x, w, mean, rstd, dx, part, C, HW, NP);
-    else ln2d_bwd_kernel<2><<<grid, LT, 0, s>>>(dy, x, w, mean, rstd, dx, part, C, HW, NP);
+    if (x_dtype == 0) ln2d_bwd_kernel<0><<<grid, LT, 0, s>>>(dy, dy_dtype, x, w, mean, rstd, dx, part, C, HW, NP);
+    else if (x_dtype == 1) ln2d_bwd_kernel<1><<<grid, LT, 0, s>>>(dy, dy_dtype, x, w, mean, rstd, dx, part, C, HW, NP);
+    else ln2d_bwd_kernel<2><<<grid, LT, 0, s>>>(dy, dy_dtype, x, w, mean, rstd, dx, part, C, HW, NP);
     TURTLE_CHECK_LAUNCH();
     ln2d_reduce_kernel<<<(unsigned)cdiv64((int64_t)2 * C * 32, 256), 256, 0, s>>>(part, (int)grid, C, dw, db);
     TURTLE_CHECK_LAUNCH();

@@ -40,16 +40,19 @@ class _ChannelLayerNorm(torch.autograd.Function):
     backward, instead of the ~30 ATen launches autograd records for the mean / var / sqrt / div / mul / add chain."""
 
     @staticmethod
-    def forward(ctx, x, w, b):
+    def forward(ctx, x, w, b, out_dtype=torch.float32):
+        """``out_dtype``: fp32 as autocast leaves the reference's formula, or the autocast dtype when the only consumer
+        is a convolution (which would cast it there: the same single rounding, without the cast launches)."""
         from . import capi
         x = x.contiguous()
         B, C, H, W = x.shape
-        y = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+        y = torch.empty(x.shape, device=x.device, dtype=out_dtype)
         mean = torch.empty(B * H * W, device=x.device, dtype=torch.float32)
         rstd = torch.empty_like(mean)
         wf, bf = w.detach().float().contiguous(), b.detach().float().contiguous()
-        capi.call("turtle_ln2d_fwd", x.data_ptr(), _LN_DTYPES[x.dtype], wf.data_ptr(), bf.data_ptr(), y.data_ptr(),
-                  mean.data_ptr(), rstd.data_ptr(), B, C, H * W, torch.cuda.current_stream(x.device).cuda_stream)
+        capi.call("turtle_ln2d_fwd_cast", x.data_ptr(), _LN_DTYPES[x.dtype], wf.data_ptr(), bf.data_ptr(), y.data_ptr(),
+                  _LN_DTYPES[out_dtype], mean.data_ptr(), rstd.data_ptr(), B, C, H * W,
+                  torch.cuda.current_stream(x.device).cuda_stream)
         ctx.save_for_backward(x, wf, mean, rstd)
         return y
 
@@ -58,16 +61,18 @@ class _ChannelLayerNorm(torch.autograd.Function):
         from . import capi
         x, wf, mean, rstd = ctx.saved_tensors
         B, C, H, W = x.shape
-        dy = dy.float().contiguous()
+        dy = dy.contiguous()
+        if dy.dtype not in _LN_DTYPES:
+            dy = dy.float()
         dx = torch.empty_like(x)
         dw = torch.empty(C, device=x.device, dtype=torch.float32)
         db = torch.empty_like(dw)
         nbytes = capi.load().turtle_ln2d_bwd_workspace(C, B * H * W)
         wsp = torch.empty(nbytes // 4, device=x.device, dtype=torch.float32)
-        capi.call("turtle_ln2d_bwd", dy.data_ptr(), x.data_ptr(), _LN_DTYPES[x.dtype], wf.data_ptr(), mean.data_ptr(),
-                  rstd.data_ptr(), dx.data_ptr(), dw.data_ptr(), db.data_ptr(), wsp.data_ptr(), B, C, H * W,
-                  torch.cuda.current_stream(x.device).cuda_stream)
-        return dx, dw, db
+        capi.call("turtle_ln2d_bwd_cast", dy.data_ptr(), _LN_DTYPES[dy.dtype], x.data_ptr(), _LN_DTYPES[x.dtype],
+                  wf.data_ptr(), mean.data_ptr(), rstd.data_ptr(), dx.data_ptr(), dw.data_ptr(), db.data_ptr(),
+                  wsp.data_ptr(), B, C, H * W, torch.cuda.current_stream(x.device).cuda_stream)
+        return dx, dw, db, None
 
 
 class _Depthwise3x3(torch.autograd.Function):
@@ -159,10 +164,15 @@ def _dw(conv, x: Tensor) -> Tensor:
     return conv(x)
 
 
-def _layernorm(norm, x: Tensor) -> Tensor:                      # T1:83-112
+def _layernorm(norm, x: Tensor, conv_next: bool = False) -> Tensor:                      # T1:83-112
+    """``conv_next``: the result feeds convolutions only, so under autocast it may leave the kernel in the autocast dtype."""
     b = getattr(norm.body, "bias", None)
     if x.is_cuda and b is not None and x.dtype in _LN_DTYPES:
-        return _ChannelLayerNorm.apply(x, norm.body.weight, b)
+        od = torch.float32
+        if (conv_next and torch.is_autocast_enabled("cuda") and os.environ.get("TURTLE_TRAIN_LN_CAST", "1") != "0"
+                and torch.get_autocast_dtype("cuda") in _LN_DTYPES):
+            od = torch.get_autocast_dtype("cuda")
+        return _ChannelLayerNorm.apply(x, norm.body.weight, b, od)
     # BiasFree variant (unused by the shipped ymls) and the CPU host-logic tests: the reference's formula on torch ops
     w = norm.body.weight.view(1, -1, 1, 1)
     mu = x.mean(dim=1, keepdim=True)
@@ -299,7 +309,7 @@ def _block(blk, x, variant, k_hist=None, v_hist=None):          # T1:804-811
     kc = vc = None
     t = blk.attention_type
     if t != "NoAttn":
-        y = _layernorm(blk.norm1, x)
+        y = _layernorm(blk.norm1, x, conv_next=t in ("Channel", "ReducedAttn", "FHR"))
         if t == "Channel":
             o, _, _ = _channel_attn(blk.attn, y)
         elif t == "ReducedAttn":
@@ -309,7 +319,7 @@ def _block(blk, x, variant, k_hist=None, v_hist=None):          # T1:804-811
         else:
             o, kc, vc = _causal_history(blk.attn, y, variant, k_hist, v_hist)
         x = x + o
-    y = _layernorm(blk.norm2, x)
+    y = _layernorm(blk.norm2, x, conv_next=True)
     return x + (_gated_ffw(blk.ffn, y) if blk.FFW_type == "GFFW" else _plain_ffw(blk.ffn, y)), kc, vc
 
 
