@@ -307,7 +307,7 @@ def train_arm(args, rank, world, local_rank, dev, dist, barrier):
                                               else "launched from the gradient hooks during backward")),
                            "allreduce_alone_ms": round(ar_ms, 3),
                            "forward_backward": "autograd graph: cuDNN/cuBLAS/ATen convs and matmuls, hand-written LayerNorm, "
-                                               "depthwise 3x3 and GELU-gate forward/backward; optimizer on libturtle_b200",
+                                               "depthwise 3x3, GELU-gate and q/k row-normalise forward/backward; optimizer on libturtle_b200",
                            "launch": "forward+backward replayed from one CUDA graph" if ts.cuda_graph else "eager"},
                 "clocks": clk.summary(), "loss": loss, "loss_mean_over_ranks": loss_mean, "skipped_steps": ts.skipped_steps,
                 "e2e": {"value": world * K * B * T / (ms * 1e-3), "unit": "frames/s",

@@ -327,6 +327,15 @@ int turtle_dwconv3x3_nchw_wgrad(const void *x, const void *dy, int dtype, float 
 int turtle_gelu_gate_nchw(const void *u, int dtype, void *y, int B, int Ch, long long HW, void *stream);
 int turtle_gelu_gate_nchw_bwd(const void *u, const void *dy, int dtype, void *du, int B, int Ch, long long HW, void *stream);
 
+/* F.normalize(x, dim=-1) of the channel attention's q / k rows (T1:686-687) in the TRAINING graph.  Row (b, ch) of x is
+ * the H*W = len contiguous elements at x + b * bstride + ch * len (a channel chunk of the NCHW qkv map); y [B*CH, len] fp32
+ * (autocast runs normalize in fp32), denom [B*CH] = max(||row||, 1e-12).  Backward: dx = (dy - y <dy, y>) / denom in x's
+ * dtype, [rows, len] dense.  len % 4 == 0. */
+int turtle_rownorm_fwd(const void *x, int dtype, long long bstride, int B, int CH, int len, float *y, float *denom,
+                       void *stream);
+int turtle_rownorm_bwd(const float *dy, const float *y, const float *denom, int dtype, long long rows, int len, void *dx,
+                       void *stream);
+
 /* GatedFeedForward (T1:159-178) as one kernel, tensor-core mode:  x += W_out . ( gelu(u1) * u2 ),
  * [u1 | u2] = dw3x3( W_in . xn ), with the 5c-wide hidden map kept on the SM (project_in recomputed on the 1-pixel halo
  * of each 8x16 tile, depthwise + gate feeding the second tcgen05 contraction through shared memory).

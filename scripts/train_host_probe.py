@@ -29,3 +29,7 @@ tot = sum(v[0] for v in agg.values()) / 1e3
 print(f"sum of device kernel time {tot:.1f} ms over {sum(v[1] for v in agg.values())} kernels")
 for name, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:28]:
     print(f"  {name[:86]:86s} {t/1e3:8.2f} ms  x{n}")
+print("full names of the ATen elementwise / reduce fallbacks:")
+for name, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
+    if "elementwise_kernel" in name or "reduce_kernel" in name:
+        print(f"  {t/1e3:7.2f} ms x{n}: {name[:400]}")

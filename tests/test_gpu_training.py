@@ -163,6 +163,32 @@ def test_gelu_gate_forward_backward_kernels(dtype, tol, B, Ch, H, W):
         assert ((u.grad.float() - ut.grad.float()).abs() <= 2 * ulp * ut.grad.float().abs() + 1e-5).all()
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-6), (torch.float16, 1e-3), (torch.bfloat16, 8e-3)])
+@pytest.mark.parametrize("b,hd,cc,h,w", [(2, 2, 6, 8, 12), (1, 4, 16, 32, 32), (3, 1, 5, 4, 300)])
+def test_unit_rows_forward_backward_kernels(dtype, tol, b, hd, cc, h, w):
+    """turtle_rownorm_fwd / _bwd behind autograd on the q chunk of a qkv map vs F.normalize in float64."""
+    import torch.nn.functional as F
+    from turtlevsr_b200.training import _UnitRows, _unit_rows
+    c = hd * cc
+    g = torch.Generator(device=DEV).manual_seed(c + w)
+    qkv = torch.randn(b, 3 * c, h, w, device=DEV, generator=g).to(dtype).requires_grad_()
+    dy = torch.randn(b, hd, cc, h * w, device=DEV, generator=g)
+    q = qkv.chunk(3, dim=1)[1].reshape(b, hd, cc, h * w)               # the k chunk: a strided view
+    assert q.data_ptr() != qkv.data_ptr() and (b == 1 or not q.is_contiguous())
+    y = _unit_rows(q)
+    assert y.dtype == torch.float32 and isinstance(y.grad_fn, _UnitRows._backward_cls)
+    y.backward(dy)
+    qd = qkv.detach().double().requires_grad_()
+    yd = F.normalize(qd.chunk(3, dim=1)[1].reshape(b, hd, cc, h * w), dim=-1)
+    yd.backward(dy.double())
+    assert (y.double() - yd).abs().max() < 2e-6
+    assert (qkv.grad.double() - qd.grad).abs().max() < tol * max(1.0, qd.grad.abs().max().item())
+    z = torch.zeros(1, 1, 2, 8, device=DEV, requires_grad=True)        # zero rows: the eps clamp, no NaN
+    yz = _unit_rows(z)
+    yz.sum().backward()
+    assert torch.equal(yz, torch.zeros_like(yz)) and torch.isfinite(z.grad).all()
+
+
 def test_non_finite_gradients_skip_the_update():
     lin = torch.nn.Linear(1000, 37).to(DEV)
     flat = FlatParams(lin)

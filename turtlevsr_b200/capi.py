@@ -75,6 +75,8 @@ _SIGS = {
                              C.c_int),
     "turtle_dwconv3x3_nchw": ([_fp, _i32, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _i32, _fp], C.c_int),
     "turtle_dwconv3x3_nchw_wgrad_workspace": ([_i32, _i32, _i32, _i32], C.c_longlong),
+    "turtle_rownorm_fwd": ([_fp, _i32, _i64, _i32, _i32, _i32, _fp, _fp, _fp], C.c_int),
+    "turtle_rownorm_bwd": ([_fp, _fp, _fp, _i32, _i64, _i32, _fp, _fp], C.c_int),
     "turtle_gelu_gate_nchw": ([_fp, _i32, _fp, _i32, _i32, _i64, _fp], C.c_int),
     "turtle_gelu_gate_nchw_bwd": ([_fp, _fp, _i32, _fp, _i32, _i32, _i64, _fp], C.c_int),
     "turtle_dwconv3x3_nchw_wgrad": ([_fp, _fp, _i32, _fp, _fp, _fp, _i32, _i32, _i32, _i32, _fp], C.c_int),

@@ -97,3 +97,125 @@ extern "C" int turtle_gelu_gate_nchw_bwd(const void *u, const void *dy, int dtyp
                                          void *stream) {
     return launch_gate<true>(u, dy, du, dtype, B, Ch, HW, stream);
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// F.normalize(x, dim=-1) of the channel attention's q / k rows (T1:686-687) in the TRAINING graph, forward and backward.
+// Through autograd the reference runs norm + clamp_min + expand + div forward and a dozen broadcast div / mul / sum
+// launches backward, after a strided cast of the bf16 chunk view to fp32 (autocast runs normalize in fp32): together the
+// largest ATen item of the cfg-5 step (scripts/train_host_probe.py: ~45 ms of 259 ms).  A row is one (image, channel)
+// plane of H*W contiguous elements; one block per row, two passes over it (the second one hits L2).
+//   forward :  denom = max(||x||_2, 1e-12);  y = x / denom  (fp32, as autocast leaves it);  denom saved
+//   backward:  dx = (dy - y * <dy, y>) / denom                (x's dtype)
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int RN_T = 512;
+
+// four consecutive elements (16-byte aligned fp32 / 8-byte aligned 16-bit)
+__device__ __forceinline__ float4 rn_ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ float4 rn_ld4(const __half *p) {
+    const uint2 u = *reinterpret_cast<const uint2 *>(p);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2 *>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ float4 rn_ld4(const __nv_bfloat16 *p) {
+    const uint2 u = *reinterpret_cast<const uint2 *>(p);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u.x)),
+                 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162 *>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void rn_st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+__device__ __forceinline__ void rn_st4(__half *p, float4 v) {
+    const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+    *reinterpret_cast<uint2 *>(p) = make_uint2(*reinterpret_cast<const uint32_t *>(&a), *reinterpret_cast<const uint32_t *>(&b));
+}
+__device__ __forceinline__ void rn_st4(__nv_bfloat16 *p, float4 v) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    *reinterpret_cast<uint2 *>(p) = make_uint2(*reinterpret_cast<const uint32_t *>(&a), *reinterpret_cast<const uint32_t *>(&b));
+}
+
+__device__ __forceinline__ float rn_block_sum(float v, float *red) {
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < RN_T / 32; ++w) t += red[w];
+    return t;
+}
+
+// x: row r = (b, ch) at x + b * bstride + ch * len (elements); y: [rows, len] fp32 dense; len % 4 == 0
+template <int DT>
+__global__ void __launch_bounds__(RN_T) rownorm_fwd_kernel(const void *__restrict__ xv, long long bstride, int CH, int len,
+                                                           float *__restrict__ y, float *__restrict__ denom_out) {
+    using T = typename GEl<DT>::T;
+    __shared__ float red[RN_T / 32];
+    const long long r = blockIdx.x, b = r / CH, ch = r - b * CH;
+    const T *x = reinterpret_cast<const T *>(xv) + b * bstride + ch * (long long)len;
+    float ss = 0.f;
+    for (int i = threadIdx.x * 4; i < len; i += RN_T * 4) {
+        const float4 a = rn_ld4(x + i);
+        ss += (a.x * a.x + a.y * a.y) + (a.z * a.z + a.w * a.w);
+    }
+    ss = rn_block_sum(ss, red);
+    const float denom = fmaxf(sqrtf(ss), 1e-12f);
+    if (threadIdx.x == 0) denom_out[r] = denom;
+    float *yr = y + r * (long long)len;
+    for (int i = threadIdx.x * 4; i < len; i += RN_T * 4) {
+        const float4 a = rn_ld4(x + i);
+        *reinterpret_cast<float4 *>(yr + i) = make_float4(a.x / denom, a.y / denom, a.z / denom, a.w / denom);
+    }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(RN_T) rownorm_bwd_kernel(const float *__restrict__ dy, const float *__restrict__ y,
+                                                           const float *__restrict__ denom_in, int len, void *__restrict__ dxv) {
+    using T = typename GEl<DT>::T;
+    __shared__ float red[RN_T / 32];
+    const long long r = blockIdx.x;
+    const float *dr = dy + r * (long long)len, *yr = y + r * (long long)len;
+    float dot = 0.f;
+    for (int i = threadIdx.x * 4; i < len; i += RN_T * 4) {
+        const float4 d = *reinterpret_cast<const float4 *>(dr + i), v = *reinterpret_cast<const float4 *>(yr + i);
+        dot += (d.x * v.x + d.y * v.y) + (d.z * v.z + d.w * v.w);
+    }
+    dot = rn_block_sum(dot, red);
+    const float denom = denom_in[r];
+    T *dx = reinterpret_cast<T *>(dxv) + r * (long long)len;
+    for (int i = threadIdx.x * 4; i < len; i += RN_T * 4) {
+        const float4 d = *reinterpret_cast<const float4 *>(dr + i), v = *reinterpret_cast<const float4 *>(yr + i);
+        rn_st4(dx + i, make_float4((d.x - v.x * dot) / denom, (d.y - v.y * dot) / denom, (d.z - v.z * dot) / denom,
+                                   (d.w - v.w * dot) / denom));
+    }
+}
+
+}  // namespace
+
+extern "C" int turtle_rownorm_fwd(const void *x, int dtype, long long bstride, int B, int CH, int len, float *y, float *denom,
+                                  void *stream) {
+    if (!x || !y || !denom || B < 1 || CH < 1 || len < 1 || dtype < 0 || dtype > 2) return TURTLE_EINVAL;
+    const uintptr_t xal = dtype == 0 ? 15 : 7;
+    if (len % 4 || ((uintptr_t)y & 15) || ((uintptr_t)x & xal) || (bstride & 3) || (long long)B * CH > 2147483647LL)
+        return TURTLE_ENOTSUP;
+    cudaStream_t s = as_stream(stream);
+    const unsigned grid = (unsigned)((long long)B * CH);
+    if (dtype == 0) rownorm_fwd_kernel<0><<<grid, RN_T, 0, s>>>(x, bstride, CH, len, y, denom);
+    else if (dtype == 1) rownorm_fwd_kernel<1><<<grid, RN_T, 0, s>>>(x, bstride, CH, len, y, denom);
+    else rownorm_fwd_kernel<2><<<grid, RN_T, 0, s>>>(x, bstride, CH, len, y, denom);
+    TURTLE_CHECK_LAUNCH();
+    return TURTLE_OK;
+}
+
+extern "C" int turtle_rownorm_bwd(const float *dy, const float *y, const float *denom, int dtype, long long rows, int len,
+                                  void *dx, void *stream) {
+    if (!dy || !y || !denom || !dx || rows < 1 || len < 1 || dtype < 0 || dtype > 2) return TURTLE_EINVAL;
+    if (len % 4 || (((uintptr_t)dy | (uintptr_t)y | (uintptr_t)dx) & 15) || rows > 2147483647LL) return TURTLE_ENOTSUP;
+    cudaStream_t s = as_stream(stream);
+    const unsigned grid = (unsigned)rows;
+    if (dtype == 0) rownorm_bwd_kernel<0><<<grid, RN_T, 0, s>>>(dy, y, denom, len, dx);
+    else if (dtype == 1) rownorm_bwd_kernel<1><<<grid, RN_T, 0, s>>>(dy, y, denom, len, dx);
+    else rownorm_bwd_kernel<2><<<grid, RN_T, 0, s>>>(dy, y, denom, len, dx);
+    TURTLE_CHECK_LAUNCH();
+    return TURTLE_OK;
+}

@@ -182,7 +182,40 @@ def _layernorm(norm, x: Tensor, conv_next: bool = False) -> Tensor:             
     return (x - mu) / torch.sqrt(var + 1e-5) * w + b.view(1, -1, 1, 1)
 
 
+class _UnitRows(torch.autograd.Function):
+    """F.normalize(x, dim=-1) on turtle_rownorm_fwd / _bwd for rows that are whole (image, channel) planes of a channel
+    chunk of an NCHW map: one launch forward (reading the 16-bit view directly; fp32 out as autocast's normalize) and one
+    backward instead of the strided cast + norm / clamp / div chain and its broadcast-heavy autograd backward."""
+
+    @staticmethod
+    def forward(ctx, x):
+        from . import capi
+        b, hd, cc, n = x.shape
+        y = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+        denom = torch.empty(b * hd * cc, device=x.device, dtype=torch.float32)
+        capi.call("turtle_rownorm_fwd", x.data_ptr(), _LN_DTYPES[x.dtype], x.stride(0), b, hd * cc, n, y.data_ptr(),
+                  denom.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream)
+        ctx.save_for_backward(y, denom)
+        ctx.x_dtype = x.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import capi
+        y, denom = ctx.saved_tensors
+        dy = dy.float().contiguous()
+        dx = torch.empty(y.shape, device=y.device, dtype=ctx.x_dtype)
+        capi.call("turtle_rownorm_bwd", dy.data_ptr(), y.data_ptr(), denom.data_ptr(), _LN_DTYPES[ctx.x_dtype],
+                  y.numel() // y.shape[-1], y.shape[-1], dx.data_ptr(), torch.cuda.current_stream(y.device).cuda_stream)
+        return dx
+
+
 def _unit_rows(x: Tensor) -> Tensor:
+    """F.normalize(x, dim=-1) (T1:686-687); the fused kernels when the rows are the planes of a channel chunk."""
+    if (x.is_cuda and x.dim() == 4 and x.dtype in _LN_DTYPES and x.shape[-1] % 4 == 0 and x.stride(3) == 1
+            and x.stride(2) == x.shape[3] and x.stride(1) == x.shape[2] * x.shape[3]
+            and x.stride(0) % 4 == 0 and x.data_ptr() % 16 == 0 and os.environ.get("TURTLE_TRAIN_ROWNORM", "1") != "0"):
+        return _UnitRows.apply(x)
     return F.normalize(x, dim=-1)
 
 
