@@ -114,6 +114,12 @@ class _Depthwise3x3(torch.autograd.Function):
         return dx, dw9.view(ctx.w_shape), db
 
 
+def _aligned(t: Tensor, nbytes: int = 32) -> Tensor:
+    """A dense tensor whose storage starts on the kernels' vector alignment (an offset view of a larger buffer may not)."""
+    t = t.contiguous()
+    return t if t.data_ptr() % nbytes == 0 else t.clone()
+
+
 class _GeluGate(torch.autograd.Function):
     """`a, g = u.chunk(2, dim=1); F.gelu(a) * g` (GatedFeedForward, T1:175-176) on turtle_gelu_gate_nchw / _bwd: one launch
     forward and one backward instead of ATen's strided elementwise kernels on the channel-chunk views (gelu, mul, two
@@ -122,7 +128,7 @@ class _GeluGate(torch.autograd.Function):
     @staticmethod
     def forward(ctx, u):
         from . import capi
-        u = u.contiguous()
+        u = _aligned(u)
         B, C2, H, W = u.shape
         y = torch.empty(B, C2 // 2, H, W, device=u.device, dtype=u.dtype)
         capi.call("turtle_gelu_gate_nchw", u.data_ptr(), _LN_DTYPES[u.dtype], y.data_ptr(), B, C2 // 2, H * W,
@@ -135,9 +141,9 @@ class _GeluGate(torch.autograd.Function):
         from . import capi
         (u,) = ctx.saved_tensors
         B, C2, H, W = u.shape
-        dy = dy.contiguous()
         if dy.dtype != u.dtype:
             dy = dy.to(u.dtype)
+        dy = _aligned(dy)
         du = torch.empty_like(u)
         capi.call("turtle_gelu_gate_nchw_bwd", u.data_ptr(), dy.data_ptr(), _LN_DTYPES[u.dtype], du.data_ptr(), B, C2 // 2,
                   H * W, torch.cuda.current_stream(u.device).cuda_stream)
@@ -203,7 +209,7 @@ class _UnitRows(torch.autograd.Function):
     def backward(ctx, dy):
         from . import capi
         y, denom = ctx.saved_tensors
-        dy = dy.float().contiguous()
+        dy = _aligned(dy.float())
         dx = torch.empty(y.shape, device=y.device, dtype=ctx.x_dtype)
         capi.call("turtle_rownorm_bwd", dy.data_ptr(), y.data_ptr(), denom.data_ptr(), _LN_DTYPES[ctx.x_dtype],
                   y.numel() // y.shape[-1], y.shape[-1], dx.data_ptr(), torch.cuda.current_stream(y.device).cuda_stream)
